@@ -1,0 +1,20 @@
+"""B200-native denoising hot path for dnnhhuy/stable-diffusion-pytorch.
+
+Drop-in replacements for the reference's ``models/unet`` ``UNet.forward(x, timestep, cond)``
+and ``models/scheduler`` samplers, running on hand-written sm_100a CUDA kernels behind a C-ABI
+library (include/sdb200.h).  See DESIGN.md / INTEGRATION.md.
+"""
+from .scheduler import DDIMSampler, DDPMSampler, x0_from_eps  # noqa: F401
+
+__all__ = ["DDIMSampler", "DDPMSampler", "x0_from_eps", "UNet", "DenoiseLoop"]
+
+
+def __getattr__(name):
+    # UNet / pipeline import torch.nn machinery lazily (keeps `import` cheap for host-only users)
+    if name == "UNet":
+        from .unet import UNet
+        return UNet
+    if name in ("DenoiseLoop", "denoise", "one_step"):
+        from . import pipeline
+        return getattr(pipeline, name)
+    raise AttributeError(name)

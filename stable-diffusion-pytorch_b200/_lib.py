@@ -1,0 +1,93 @@
+"""ctypes binding of the C-ABI kernel library (include/sdb200.h).
+
+The library is built in-tree by ``build.py`` (nvcc, sm_100a) as
+``stable-diffusion-pytorch_b200/libsdb200.so``.  Loading is lazy; every product
+entry point goes through :func:`lib`, which raises if the library is missing —
+there is no Python/CPU fallback for any kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdb200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+P, I64, I32, F32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
+
+# name -> argtypes; every function returns int (0 = ok) unless noted.  Kept in the same
+# order as include/sdb200.h (tests/test_capi.py checks the two against each other).
+SIGNATURES = {
+    # --- sampler_kernels.cu
+    "sdk_ddim_step": [P, P, P, F32, P, P, I64, P, I32, P, I64, I32, P],
+    "sdk_ddpm_step": [P, P, P, F32, P, P, I64, P, I32, P, I64, P],
+    "sdk_forward_process": [P, P, P, I64, I64, P, I32, P, P],
+    "sdk_x0_from_eps": [P, P, F32, F32, P, I64, P],
+    # --- norm_kernels.cu
+    "sdk_groupnorm_stats": [P, P, I32, I32, I32, I32, I32, I32, P, I32, P],
+    "sdk_groupnorm_apply": [P, P, I32, I32, I32, I32, I32, I32, P, I32, P, P, F32, I32, P, P, I32, P],
+    "sdk_layernorm": [P, P, P, F32, P, I32, I64, I32, P],
+    "sdk_cast_upsample": [P, P, I32, I32, I32, I32, I32, I32, P],
+    "sdk_nchw_to_nhwc": [P, P, I32, I32, I32, I32, I32, P],
+    "sdk_nhwc_to_nchw": [P, P, I32, I32, I32, I32, P],
+    "sdk_cast": [P, P, I64, I32, I32, P],
+    # --- time_embed.cu
+    "sdk_time_sinusoid": [P, I32, I32, I32, P, P],
+    "sdk_gemv": [P, I32, P, P, P, I32, I32, I32, I32, I32, P],
+    # --- gemm_simt.cu (fp32 exact mode + small/odd shapes)
+    "sdk_conv_gemm_f32": [P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32,
+                          P, P, P, I32, P, I32, P, I32, I32, I32, I32, P],
+    # --- attention
+    "sdk_attention_f32": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, I32, P],
+    "sdk_attention_bf16": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, P],
+    # --- gemm_tc.cu (tcgen05 / TMA implicit GEMM)
+    "sdk_tmap_encode": [P, P, I32, I32, P, P, P, I32],
+    "sdk_conv_gemm_tc": [P, P, P],
+    "sdk_conv_gemm_tc_workspace_bytes": [P],
+    # --- misc
+    "sdk_im2col_s2": [P, P, I32, I32, I32, I32, I32, P],
+    "sdk_device_info": [P, I32],
+}
+RESTYPES = {"sdk_last_error": C.c_char_p, "sdk_version": C.c_int, "sdk_conv_gemm_tc_workspace_bytes": C.c_int64}
+SIGNATURES.update({"sdk_last_error": [], "sdk_version": []})
+
+
+class ExtensionMissing(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded C-ABI library; raises ExtensionMissing if it was never built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ExtensionMissing(
+                    f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(nvcc, sm_100a). The B200 path has no CPU/PyTorch fallback.")
+            h = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+            for name, argtypes in SIGNATURES.items():
+                fn = getattr(h, name)          # AttributeError here == header/library drift
+                fn.argtypes = argtypes
+                fn.restype = RESTYPES.get(name, C.c_int)
+            _lib = h
+    return _lib
+
+
+def check(status: int):
+    if status != 0:
+        msg = lib().sdk_last_error()
+        raise RuntimeError(f"sdb200 kernel library error {status}: {msg.decode() if msg else '?'}")
+
+
+def current_stream(device) -> int:
+    """cudaStream_t of torch's current stream on ``device`` (what every launch is enqueued on)."""
+    return torch.cuda.current_stream(device).cuda_stream
