@@ -1,0 +1,114 @@
+/* sdb200 — C ABI of the B200 (sm_100a) kernel library behind the Stable-Diffusion denoising hot path.
+ *
+ * The reference (dnnhhuy/stable-diffusion-pytorch) is pure Python/PyTorch and has NO FFI of its own;
+ * every entry point below replaces a span of eager PyTorch calls in the reference, cited as
+ * file:line relative to the reference root.  The Python host (stable-diffusion-pytorch_b200/) binds
+ * these with ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; all pointers are DEVICE pointers unless stated.
+ *   - every function returns int: 0 = ok, <0 = error (SDK_ERR_*); text via sdk_last_error().
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*), never synchronise,
+ *     never allocate: graph-capturable.  Scratch memory is caller-provided.
+ *   - activations are NHWC ("rows x channels", rows = B*H*W); dtype codes: 0 = fp32, 1 = bf16.
+ *   - handles are not thread-safe; use one stream per caller thread.
+ */
+#ifndef SDB200_H
+#define SDB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDK_OK 0
+#define SDK_ERR_ARG (-1)
+#define SDK_ERR_CUDA (-2)
+#define SDK_ERR_UNSUPPORTED (-3)
+#define SDK_F32 0
+#define SDK_BF16 1
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* sdk_last_error(void);
+int sdk_version(void);
+/* out[0]=SM count, out[1..2]=compute capability, out[3]=max opt-in shared memory per block */
+int sdk_device_info(int* out, int n);
+
+/* ---- sampler: fused CFG blend + scheduler update (models/diffusion.py:233-236) ------------------
+ * coef_table: [T][8] fp32 per-timestep scalars built by the host sampler; the timestep is read from
+ * t_dev[0] (device int64) when t_dev != NULL, else t_host.  eps_c == NULL -> no CFG blend.
+ * DDIM  replaces models/scheduler/ddim.py:58-87 ; prediction_type 0 = epsilon, 1 = v_prediction.
+ * DDPM  replaces models/scheduler/ddpm.py:62-82 (noise = the randn draw of :80, caller-supplied). */
+int sdk_ddim_step(const float* x, const float* eps_u, const float* eps_c, float cfg_scale,
+                  const float* noise, float* out, int64_t n, const float* coef_table, int T,
+                  const int64_t* t_dev, int64_t t_host, int prediction_type, void* stream);
+int sdk_ddpm_step(const float* x, const float* eps_u, const float* eps_c, float cfg_scale,
+                  const float* noise, float* out, int64_t n, const float* coef_table, int T,
+                  const int64_t* t_dev, int64_t t_host, void* stream);
+/* models/scheduler/ddim.py:46-55 — per-sample timesteps t_dev[batch] */
+int sdk_forward_process(const float* x0, const float* noise, float* out, int64_t batch, int64_t per_sample,
+                        const float* coef_table, int T, const int64_t* t_dev, void* stream);
+/* models/diffusion.py:111-113 — one-step x0 = (x - sigma*eps)/alpha */
+int sdk_x0_from_eps(const float* x, const float* eps, float sigma, float alpha, float* out, int64_t n, void* stream);
+
+/* ---- normalisation / layout (models/unet/unet.py:66,102-108,157,160,250,343,399) ------------- */
+int64_t sdk_groupnorm_workspace_bytes(int B, int HW);
+/* GroupNorm(32) statistics over the channel-concat [src0 | src1] (src1 may be NULL with C1 = 0);
+ * stats = [B][32][2] (mean, rstd).  workspace: sdk_groupnorm_workspace_bytes, zeroed once. */
+int sdk_groupnorm_stats(const float* src0, int C0, const float* src1, int C1, int B, int HW, float eps,
+                        float* stats, void* workspace, void* stream);
+/* y = (x-mean)*rstd*gamma+beta, optional SiLU, written as out_dtype; raw_out (optional) receives the
+ * un-normalised concat in the same dtype (operand of the ResBlock's 1x1 shortcut conv). */
+int sdk_groupnorm_apply(const float* src0, int C0, const float* src1, int C1, int B, int HW,
+                        const float* stats, const float* gamma, const float* beta, int silu,
+                        void* out, void* raw_out, int out_dtype, void* stream);
+int sdk_layernorm(const float* x, const float* gamma, const float* beta, float eps, void* out,
+                  int out_dtype, int64_t rows, int C, void* stream);
+/* fp32 NHWC -> out_dtype NHWC, nearest upsample by `up` (1 or 2)  (unet.py:250) */
+int sdk_cast_upsample(const float* src, void* dst, int out_dtype, int B, int H, int W, int C, int up, void* stream);
+/* dst[b][p][c] = src[b % B_src][c][p]: NCHW latent -> NHWC, with latent.repeat(2,...) (diffusion.py:228) folded in */
+int sdk_nchw_to_nhwc(const float* src, float* dst, int B_src, int B_dst, int C, int HW, void* stream);
+
+/* ---- time embedding (unet.py:209-220 and the per-ResBlock Linear(SiLU(t_emb)) :182-183) ---- */
+/* out[i][0:half] = cos(t_i f_j), out[i][half:] = sin(t_i f_j), f_j = exp(-ln(1e4) j/half) */
+int sdk_time_sinusoid(const int64_t* t_dev, int n, int dim, float* out, void* stream);
+/* y[i][r] = act_out( dot(W[r][:], act_in(x[i][:])) + bias[r] ); act codes: 0 none, 1 SiLU.  W dtype fp32|bf16. */
+int sdk_gemv(const void* W, int w_dtype, const float* bias, const float* x, float* y,
+             int n, int R, int K, int act_in, int act_out, void* stream);
+
+/* ---- implicit-GEMM convolution / linear --------------------------------------------------------
+ * out[m][n] = epilogue( sum_{tap,c} A(m,tap,c) * W[n][tap*Cin + c] ),  m = (b*Hout + oy)*Wout + ox.
+ * A is the channel-concat of up to two NHWC sources (skip concat, unet.py:343), optionally read
+ * through a nearest 2x upsample (unet.py:250), with ksize 1|3, stride 1|2, zero pad ksize/2.
+ * A Linear is ksize=1 on a [1][1][rows] "image".  Weights are K-major [N][ksize*ksize*Cin].
+ * Epilogue: + bias[n] + tbias[b*tb_stride + n] + residual[m][n]; geglu: columns are (value, gate)
+ * pairs and out[m][j] = v * gelu_erf(g)  (models/activation_fn.py:17-20); out as NHWC or NCHW. */
+typedef struct SdkConvParams {
+    const void* src0; const void* src1;   /* NHWC activations, in_dtype */
+    const void* weight;                   /* [N][K] K-major, w_dtype == in_dtype */
+    const float* bias;                    /* [N] or NULL */
+    const float* tbias;                   /* per-sample additive term or NULL */
+    const float* residual;                /* [M][N_out] fp32 or NULL */
+    void* out;
+    int64_t tb_stride;                    /* 0: one row broadcast over the batch */
+    int C0, C1;
+    int B, Hin, Win, Hout, Wout;
+    int ksize, stride, upsample;
+    int N;                                /* GEMM N (2*N_out when geglu) */
+    int in_dtype, out_dtype;
+    int out_nchw, geglu;
+} SdkConvParams;
+/* exact fp32 path (FFMA); also serves shapes the tensor-core path does not take (Cin = 4). in_dtype must be fp32. */
+int sdk_conv_gemm_f32(const SdkConvParams* p, void* stream);
+
+/* ---- attention (models/unet/attention.py:29-50): out = softmax(q k^T * scale) v per head ------
+ * q/k/v/out element strides: row stride (between tokens) and batch stride; head h occupies columns
+ * [h*D, (h+1)*D).  kv_batch_stride may be 0 (context broadcast). */
+int sdk_attention_f32(const float* q, int64_t q_row, int64_t q_batch, const float* k, int64_t k_row, int64_t k_batch,
+                      const float* v, int64_t v_row, int64_t v_batch, float* out, int64_t o_row, int64_t o_batch,
+                      int B, int heads, int Sq, int Sk, int D, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H */

@@ -30,31 +30,35 @@ SIGNATURES = {
     "sdk_forward_process": [P, P, P, I64, I64, P, I32, P, P],
     "sdk_x0_from_eps": [P, P, F32, F32, P, I64, P],
     # --- norm_kernels.cu
-    "sdk_groupnorm_stats": [P, P, I32, I32, I32, I32, I32, I32, P, I32, P],
-    "sdk_groupnorm_apply": [P, P, I32, I32, I32, I32, I32, I32, P, I32, P, P, F32, I32, P, P, I32, P],
+    "sdk_groupnorm_workspace_bytes": [I32, I32],
+    "sdk_groupnorm_stats": [P, I32, P, I32, I32, I32, F32, P, P, P],
+    "sdk_groupnorm_apply": [P, I32, P, I32, I32, I32, P, P, P, I32, P, P, I32, P],
     "sdk_layernorm": [P, P, P, F32, P, I32, I64, I32, P],
     "sdk_cast_upsample": [P, P, I32, I32, I32, I32, I32, I32, P],
-    "sdk_nchw_to_nhwc": [P, P, I32, I32, I32, I32, I32, P],
-    "sdk_nhwc_to_nchw": [P, P, I32, I32, I32, I32, P],
-    "sdk_cast": [P, P, I64, I32, I32, P],
+    "sdk_nchw_to_nhwc": [P, P, I32, I32, I32, I32, P],
     # --- time_embed.cu
-    "sdk_time_sinusoid": [P, I32, I32, I32, P, P],
+    "sdk_time_sinusoid": [P, I32, I32, P, P],
     "sdk_gemv": [P, I32, P, P, P, I32, I32, I32, I32, I32, P],
-    # --- gemm_simt.cu (fp32 exact mode + small/odd shapes)
-    "sdk_conv_gemm_f32": [P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32,
-                          P, P, P, I32, P, I32, P, I32, I32, I32, I32, P],
-    # --- attention
-    "sdk_attention_f32": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, I32, P],
-    "sdk_attention_bf16": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, P],
-    # --- gemm_tc.cu (tcgen05 / TMA implicit GEMM)
-    "sdk_tmap_encode": [P, P, I32, I32, P, P, P, I32],
-    "sdk_conv_gemm_tc": [P, P, P],
-    "sdk_conv_gemm_tc_workspace_bytes": [P],
+    # --- gemm_simt.cu
+    "sdk_conv_gemm_f32": [P, P],
+    # --- attention_simt.cu
+    "sdk_attention_f32": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, P],
     # --- misc
-    "sdk_im2col_s2": [P, P, I32, I32, I32, I32, I32, P],
     "sdk_device_info": [P, I32],
 }
-RESTYPES = {"sdk_last_error": C.c_char_p, "sdk_version": C.c_int, "sdk_conv_gemm_tc_workspace_bytes": C.c_int64}
+
+
+class ConvParams(C.Structure):
+    """Mirror of SdkConvParams (include/sdb200.h)."""
+    _fields_ = [("src0", P), ("src1", P), ("weight", P), ("bias", P), ("tbias", P), ("residual", P), ("out", P),
+                ("tb_stride", I64), ("C0", I32), ("C1", I32),
+                ("B", I32), ("Hin", I32), ("Win", I32), ("Hout", I32), ("Wout", I32),
+                ("ksize", I32), ("stride", I32), ("upsample", I32), ("N", I32),
+                ("in_dtype", I32), ("out_dtype", I32), ("out_nchw", I32), ("geglu", I32)]
+
+
+F32_T, BF16_T = 0, 1
+RESTYPES = {"sdk_last_error": C.c_char_p, "sdk_version": C.c_int, "sdk_groupnorm_workspace_bytes": C.c_int64}
 SIGNATURES.update({"sdk_last_error": [], "sdk_version": []})
 
 

@@ -1,0 +1,29 @@
+// Library-level C-ABI entry points: error text, version, device info.
+#include "common.cuh"
+#include <string.h>
+
+static thread_local char g_err[512] = {0};
+char* sdk_err_buf() { return g_err; }
+
+int sdk_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char* sdk_last_error() { return g_err; }
+extern "C" int sdk_version() { return 100; }
+
+// out[0]=sm count, out[1]=cc major, out[2]=cc minor, out[3]=max opt-in smem per block
+extern "C" int sdk_device_info(int* out, int n) {
+    SDK_CHECK_ARG(out && n >= 4, "sdk_device_info: need 4 ints");
+    int dev = 0;
+    SDK_CUDA(cudaGetDevice(&dev));
+    SDK_CUDA(cudaDeviceGetAttribute(&out[0], cudaDevAttrMultiProcessorCount, dev));
+    SDK_CUDA(cudaDeviceGetAttribute(&out[1], cudaDevAttrComputeCapabilityMajor, dev));
+    SDK_CUDA(cudaDeviceGetAttribute(&out[2], cudaDevAttrComputeCapabilityMinor, dev));
+    SDK_CUDA(cudaDeviceGetAttribute(&out[3], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return SDK_OK;
+}

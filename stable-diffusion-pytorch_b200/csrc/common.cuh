@@ -1,0 +1,64 @@
+// Shared helpers for the sdb200 kernel library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#define SDK_OK 0
+#define SDK_ERR_ARG (-1)
+#define SDK_ERR_CUDA (-2)
+#define SDK_ERR_UNSUPPORTED (-3)
+
+// thread-local last-error text, readable through sdk_last_error()
+char* sdk_err_buf();
+int sdk_fail(int code, const char* fmt, ...);
+
+#define SDK_CHECK_ARG(cond, ...) \
+    do { if (!(cond)) return sdk_fail(SDK_ERR_ARG, __VA_ARGS__); } while (0)
+
+#define SDK_CUDA(call) \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+        return sdk_fail(SDK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+#define SDK_LAUNCH_CHECK() \
+    do { cudaError_t e_ = cudaPeekAtLastError(); if (e_ != cudaSuccess) \
+        return sdk_fail(SDK_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+static inline int sdk_num_sms() {
+    static int n = 0;
+    if (n == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// exact-erf GELU (nn.GELU() default, reference models/activation_fn.py:15)
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// dtype codes used across the C ABI
+#define SDK_F32 0
+#define SDK_BF16 1

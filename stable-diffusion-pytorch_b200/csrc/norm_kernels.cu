@@ -1,0 +1,308 @@
+// Bandwidth-bound normalisation / layout kernels of the UNet.
+//
+// Activations are NHWC == [rows = B*H*W][C] with the fp32 "residual stream" as the stored type.
+// Each kernel reads its input once with 16-byte vector loads along C (coalesced), reduces with warp
+// shuffles, and writes the operand for the following GEMM in that GEMM's operand type (bf16 on the
+// tensor-core path, fp32 on the exact path), so cast / SiLU / concat / nearest-upsample never cost a
+// pass of their own.
+//
+//   GroupNorm(32 groups) [+SiLU] over a virtual channel-concat of two sources  (unet.py:66,157,160,343,399)
+//   LayerNorm over C                                                             (unet.py:102-108)
+//   cast (+ nearest 2x upsample)                                                 (unet.py:250)
+//   NCHW -> NHWC for the 4-channel latent                                        (unet.py:256 input)
+#include "common.cuh"
+
+namespace {
+
+constexpr int GROUPS = 32;
+constexpr int GN_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm statistics.  grid = (chunks, B).  Thread t owns channel quads {t, t+256, ...}; for each
+// quad it walks the chunk's pixels (coalesced across the CTA), keeping fp32 partial sums per channel
+// which are folded into per-group double sums.  The last CTA of a sample (atomic ticket) adds the
+// per-chunk partials in fixed chunk order -> deterministic mean / rstd.
+// ---------------------------------------------------------------------------------------------
+struct GNStatsArgs {
+    const float* src0; const float* src1;
+    int C0, C1, HW, chunks, pix_per_chunk;
+    double* partial;        // [B][chunks][GROUPS][2]
+    unsigned int* ticket;   // [B], zero on entry, self-resetting
+    float* stats;           // [B][GROUPS][2] = mean, rstd
+    float eps;
+};
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(GNStatsArgs a) {
+    __shared__ double s_sum[GROUPS], s_sq[GROUPS];
+    __shared__ bool s_last;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int C = a.C0 + a.C1, cpg = C / GROUPS;
+    if (threadIdx.x < GROUPS) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
+    __syncthreads();
+    const int p0 = chunk * a.pix_per_chunk;
+    const int p1 = min(a.HW, p0 + a.pix_per_chunk);
+    const int nquads = C >> 2;
+    for (int q = threadIdx.x; q < nquads; q += GN_THREADS) {
+        const int c = q << 2;
+        const float* base; int cs, cl;
+        if (c < a.C0) { base = a.src0; cs = a.C0; cl = c; } else { base = a.src1; cs = a.C1; cl = c - a.C0; }
+        const float* p = base + ((size_t)b * a.HW + p0) * cs + cl;
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+        double ds[4] = {0, 0, 0, 0}, dss[4] = {0, 0, 0, 0};
+        int cnt = 0;
+        for (int pix = p0; pix < p1; ++pix, p += cs) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+            if (++cnt == 32) {            // bound fp32 accumulation length, then promote
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dss[j] += ss[j]; s[j] = 0.f; ss[j] = 0.f; }
+                cnt = 0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ds[j] += s[j]; dss[j] += ss[j];
+            const int g = (c + j) / cpg;
+            atomicAdd(&s_sum[g], ds[j]);
+            atomicAdd(&s_sq[g], dss[j]);
+        }
+    }
+    __syncthreads();
+    double* part = a.partial + ((size_t)b * a.chunks + chunk) * GROUPS * 2;
+    if (threadIdx.x < GROUPS) { part[threadIdx.x * 2] = s_sum[threadIdx.x]; part[threadIdx.x * 2 + 1] = s_sq[threadIdx.x]; }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&a.ticket[b], 1u) == (unsigned)a.chunks - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < GROUPS) {
+        double sum = 0.0, sq = 0.0;
+        const double* pp = a.partial + (size_t)b * a.chunks * GROUPS * 2 + threadIdx.x * 2;
+        for (int k = 0; k < a.chunks; ++k) { sum += __ldcg(pp + (size_t)k * GROUPS * 2); sq += __ldcg(pp + (size_t)k * GROUPS * 2 + 1); }
+        const double n = (double)cpg * (double)a.HW;
+        const double mean = sum / n;
+        double var = sq / n - mean * mean;      // biased variance (nn.GroupNorm)
+        if (var < 0.0) var = 0.0;
+        a.stats[((size_t)b * GROUPS + threadIdx.x) * 2] = (float)mean;
+        a.stats[((size_t)b * GROUPS + threadIdx.x) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
+    }
+    if (threadIdx.x == 0) a.ticket[b] = 0u;
+}
+
+// GroupNorm apply (+SiLU) (+ raw cast copy).  One thread per channel quad per pixel; grid-stride over rows.
+struct GNApplyArgs {
+    const float* src0; const float* src1;
+    int C0, C1, HW, B;
+    const float* stats; const float* gamma; const float* beta;
+    void* out; void* raw_out;
+    int silu;
+};
+
+template <typename TOut>
+__device__ __forceinline__ void store4(TOut* p, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u; u.x = *reinterpret_cast<unsigned*>(&lo); u.y = *reinterpret_cast<unsigned*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(GNApplyArgs a) {
+    const int C = a.C0 + a.C1, cpg = C / GROUPS, nquads = C >> 2;
+    const long long total = (long long)a.B * a.HW * nquads;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % nquads);
+        const long long row = i / nquads;
+        const int b = (int)(row / a.HW);
+        const int c = q << 2;
+        const float* p = (c < a.C0) ? a.src0 + row * a.C0 + c : a.src1 + row * a.C1 + (c - a.C0);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+        const float xs[4] = {v.x, v.y, v.z, v.w}, gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int g = (c + j) / cpg;
+            const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats) + (size_t)b * GROUPS + g);
+            float y = (xs[j] - st.x) * st.y * gs[j] + bs[j];
+            r[j] = a.silu ? silu_f(y) : y;
+        }
+        store4<TOut>(reinterpret_cast<TOut*>(a.out) + row * C + c, r[0], r[1], r[2], r[3]);
+        if (a.raw_out) store4<TOut>(reinterpret_cast<TOut*>(a.raw_out) + row * C + c, xs[0], xs[1], xs[2], xs[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row lives in registers (C <= 2048), exact two-pass statistics.
+// ---------------------------------------------------------------------------------------------
+template <typename TOut, int MAXQ>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 float eps, TOut* __restrict__ out, int C, long long rows) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int nquads = C >> 2;
+    for (long long row = warp; row < rows; row += nwarps) {
+        const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+        float4 v[MAXQ];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXQ; ++k) {
+            const int q = lane + k * 32;
+            if (q < nquads) { v[k] = __ldg(xr + q); s += (v[k].x + v[k].y) + (v[k].z + v[k].w); }
+        }
+        const float mean = warp_sum(s) / (float)C;
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXQ; ++k) {
+            const int q = lane + k * 32;
+            if (q < nquads) {
+                const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+                ss += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+#pragma unroll
+        for (int k = 0; k < MAXQ; ++k) {
+            const int q = lane + k * 32;
+            if (q < nquads) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + q);
+                store4<TOut>(out + row * C + (q << 2),
+                             (v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y,
+                             (v[k].z - mean) * rstd * g.z + b.z, (v[k].w - mean) * rstd * g.w + b.w);
+            }
+        }
+    }
+}
+
+// cast fp32 NHWC -> TOut NHWC with optional nearest 2x upsample (dst pixel (y,x) <- src (y/2,x/2)).
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+cast_upsample_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int B, int H, int W, int C, int up) {
+    const int Ho = H * up, Wo = W * up, nquads = C >> 2;
+    const long long total = (long long)B * Ho * Wo * nquads;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % nquads);
+        long long r = i / nquads;
+        const int x = (int)(r % Wo); r /= Wo;
+        const int y = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * H + y / up) * W + x / up) * C) + q);
+        store4<TOut>(dst + (i << 2), v.x, v.y, v.z, v.w);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B_src, int B_dst, int C, int HW) {
+    // dst[b][p][c] = src[b % B_src][c][p]   (b % B_src implements latent.repeat(2,1,1,1), diffusion.py:228)
+    const long long total = (long long)B_dst * HW * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int p = (int)(r % HW);
+        const int b = (int)(r / HW);
+        dst[i] = __ldg(src + ((size_t)(b % B_src) * C + c) * HW + p);
+    }
+}
+
+inline int grid_for(long long items, int threads) {
+    long long blocks = (items + threads - 1) / threads;
+    long long cap = (long long)sdk_num_sms() * 8;
+    return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace
+
+extern "C" int64_t sdk_groupnorm_workspace_bytes(int B, int HW) {
+    // partial sums [B][chunks<=64][32][2] doubles + tickets [B]
+    return (int64_t)B * 64 * GROUPS * 2 * sizeof(double) + (int64_t)B * sizeof(unsigned int) + 256;
+}
+
+// stats [B][32][2] fp32 (mean, rstd).  workspace must be zero-initialised ONCE (tickets self-reset).
+extern "C" int sdk_groupnorm_stats(const float* src0, int C0, const float* src1, int C1, int B, int HW, float eps,
+                                   float* stats, void* workspace, void* stream) {
+    SDK_CHECK_ARG(src0 && stats && workspace, "sdk_groupnorm_stats: null pointer");
+    const int C = C0 + C1;
+    SDK_CHECK_ARG(C0 > 0 && C1 >= 0 && (C1 == 0 || src1), "sdk_groupnorm_stats: bad sources");
+    SDK_CHECK_ARG(C % GROUPS == 0 && C0 % 4 == 0 && C1 % 4 == 0, "sdk_groupnorm_stats: C=%d+%d must be a multiple of 32 (quads of 4)", C0, C1);
+    SDK_CHECK_ARG(B > 0 && B < 65536 && HW > 0, "sdk_groupnorm_stats: bad B/HW");
+    int chunks = (sdk_num_sms() * 2 + B - 1) / B;      // ~2 CTAs per SM over the whole batch
+    if (chunks > 64) chunks = 64;
+    if (chunks > HW) chunks = HW;
+    if (chunks < 1) chunks = 1;
+    const int ppc = (HW + chunks - 1) / chunks;
+    chunks = (HW + ppc - 1) / ppc;
+    GNStatsArgs a;
+    a.src0 = src0; a.src1 = src1; a.C0 = C0; a.C1 = C1; a.HW = HW; a.chunks = chunks; a.pix_per_chunk = ppc;
+    a.ticket = reinterpret_cast<unsigned int*>(workspace);
+    a.partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + (((size_t)B * sizeof(unsigned int) + 255) / 256) * 256);
+    a.stats = stats; a.eps = eps;
+    gn_stats_kernel<<<dim3(chunks, B), GN_THREADS, 0, (cudaStream_t)stream>>>(a);
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
+extern "C" int sdk_groupnorm_apply(const float* src0, int C0, const float* src1, int C1, int B, int HW,
+                                   const float* stats, const float* gamma, const float* beta, int silu,
+                                   void* out, void* raw_out, int out_dtype, void* stream) {
+    SDK_CHECK_ARG(src0 && stats && gamma && beta && out, "sdk_groupnorm_apply: null pointer");
+    const int C = C0 + C1;
+    SDK_CHECK_ARG(C % GROUPS == 0 && C0 % 4 == 0 && C1 % 4 == 0 && (C1 == 0 || src1), "sdk_groupnorm_apply: bad channels %d+%d", C0, C1);
+    GNApplyArgs a;
+    a.src0 = src0; a.src1 = src1; a.C0 = C0; a.C1 = C1; a.HW = HW; a.B = B;
+    a.stats = stats; a.gamma = gamma; a.beta = beta; a.out = out; a.raw_out = raw_out; a.silu = silu;
+    const int grid = grid_for((long long)B * HW * (C / 4), 256);
+    if (out_dtype == SDK_F32) gn_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else if (out_dtype == SDK_BF16) gn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else return sdk_fail(SDK_ERR_ARG, "sdk_groupnorm_apply: out_dtype %d", out_dtype);
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
+extern "C" int sdk_layernorm(const float* x, const float* gamma, const float* beta, float eps, void* out,
+                             int out_dtype, int64_t rows, int C, void* stream) {
+    SDK_CHECK_ARG(x && gamma && beta && out, "sdk_layernorm: null pointer");
+    SDK_CHECK_ARG(C > 0 && C % 4 == 0 && C <= 2048, "sdk_layernorm: C=%d must be a multiple of 4 and <= 2048", C);
+    if (rows <= 0) return SDK_OK;
+    const int grid = grid_for(rows * 32, 256);
+    cudaStream_t s = (cudaStream_t)stream;
+#define LN_LAUNCH(T, MAXQ) layernorm_kernel<T, MAXQ><<<grid, 256, 0, s>>>(x, gamma, beta, eps, reinterpret_cast<T*>(out), C, rows)
+    const int nq = (C / 4 + 31) / 32;
+    if (out_dtype == SDK_F32) {
+        if (nq <= 3) LN_LAUNCH(float, 3); else if (nq <= 5) LN_LAUNCH(float, 5); else if (nq <= 10) LN_LAUNCH(float, 10); else LN_LAUNCH(float, 16);
+    } else if (out_dtype == SDK_BF16) {
+        if (nq <= 3) LN_LAUNCH(__nv_bfloat16, 3); else if (nq <= 5) LN_LAUNCH(__nv_bfloat16, 5); else if (nq <= 10) LN_LAUNCH(__nv_bfloat16, 10); else LN_LAUNCH(__nv_bfloat16, 16);
+    } else return sdk_fail(SDK_ERR_ARG, "sdk_layernorm: out_dtype %d", out_dtype);
+#undef LN_LAUNCH
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
+extern "C" int sdk_cast_upsample(const float* src, void* dst, int out_dtype, int B, int H, int W, int C, int up, void* stream) {
+    SDK_CHECK_ARG(src && dst && (up == 1 || up == 2) && C % 4 == 0, "sdk_cast_upsample: bad args (C=%d up=%d)", C, up);
+    const long long total = (long long)B * H * up * W * up * (C / 4);
+    if (total <= 0) return SDK_OK;
+    const int grid = grid_for(total, 256);
+    if (out_dtype == SDK_F32) cast_upsample_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(src, (float*)dst, B, H, W, C, up);
+    else if (out_dtype == SDK_BF16) cast_upsample_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, B, H, W, C, up);
+    else return sdk_fail(SDK_ERR_ARG, "sdk_cast_upsample: out_dtype %d", out_dtype);
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
+extern "C" int sdk_nchw_to_nhwc(const float* src, float* dst, int B_src, int B_dst, int C, int HW, void* stream) {
+    SDK_CHECK_ARG(src && dst && B_src > 0 && B_dst > 0 && C > 0 && HW > 0, "sdk_nchw_to_nhwc: bad args");
+    nchw_to_nhwc_kernel<<<grid_for((long long)B_dst * HW * C, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, B_src, B_dst, C, HW);
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}

@@ -234,6 +234,8 @@ class DDIMSampler(_SamplerBase):
         tab = self._coef_table(x.device, eta)
         t_ptr, t_host, keep = self._timestep_args(timestep, x.device)
         out = torch.empty_like(x)
+        if n == 0:
+            return out
         _lib.check(_lib.lib().sdk_ddim_step(
             x.data_ptr(), eps_u, eps_c, scale, noise.data_ptr() if noise is not None else 0,
             out.data_ptr(), n, tab.data_ptr(), self.noise_step, t_ptr, t_host,
@@ -315,6 +317,8 @@ class DDPMSampler(_SamplerBase):
         nz = noise.to(x.device, torch.float32).contiguous()
         t_ptr, t_host, keep = self._timestep_args(timestep, x.device)
         out = torch.empty_like(x)
+        if n == 0:
+            return out
         _lib.check(_lib.lib().sdk_ddpm_step(
             x.data_ptr(), eps_u, eps_c, scale, nz.data_ptr(), out.data_ptr(), n,
             tab.data_ptr(), self.noise_step, t_ptr, t_host, _lib.current_stream(x.device)))

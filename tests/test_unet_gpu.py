@@ -1,0 +1,119 @@
+"""GPU parity of the UNet step program (through the C-ABI) against golden vectors from the
+unmodified reference and against the oracle.  fp32 mode gate: rel-L2 <= 1e-4; bf16: <= 1e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_oracle as UO
+from stable_diffusion_pytorch_b200 import DDIMSampler, UNet
+
+pytestmark = pytest.mark.gpu
+FP32_TOL, BF16_TOL = 1e-4, 1e-2
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _make(cfg, seed, dev, precision):
+    sd = UO.make_state_dict(seed, **cfg)
+    net = UNet(attention_head_dim=cfg["attention_head_dim"], cross_attention_dim=cfg["cross_attention_dim"])
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval().set_precision(precision)
+    return net, sd
+
+
+@pytest.fixture(scope="module")
+def sd15_fp32(dev):
+    return _make(UO.SD15, 0, dev, "fp32")
+
+
+@pytest.fixture(scope="module")
+def g15(golden_dir):
+    return np.load(os.path.join(golden_dir, "unet_sd15_golden.npz"))
+
+
+def test_param_contract(sd15_fp32):
+    net, sd = sd15_fp32
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    assert sum(p.numel() for p in net.parameters()) == 859_520_964
+
+
+def test_fp32_forward_golden(sd15_fp32, g15, dev):
+    net, _ = sd15_fp32
+    T = lambda k: torch.from_numpy(g15[k]).to(dev)
+    with torch.no_grad():
+        for t in (981, 1):
+            y = net(T("lat16").repeat(2, 1, 1, 1), torch.tensor([t], device=dev), T("ctx"))
+            e = rel_l2(y.cpu().numpy(), g15[f"out16_t{t}"])
+            print(f"fp32 out16 t={t}: rel-L2 {e:.3e}")
+            assert y.shape == (2, 4, 16, 16) and y.dtype == torch.float32 and e < FP32_TOL
+        # second + third call: CUDA-graph capture and replay must give the same answer
+        y2 = net(T("lat16").repeat(2, 1, 1, 1), torch.tensor([1], device=dev), T("ctx"))
+        y3 = net(x=T("lat16").repeat(2, 1, 1, 1), timestep=torch.tensor([1], device=dev), cond=T("ctx"))
+        assert torch.equal(y2, y) and torch.equal(y3, y)
+        # per-sample timesteps, broadcast context, non-square latent
+        y = net(T("lat8").repeat(2, 1, 1, 1), torch.tensor([500, 20], device=dev), T("ctx8"))
+        assert rel_l2(y.cpu().numpy(), g15["out8_t500_20"]) < FP32_TOL
+        y = net(T("lat8").repeat(2, 1, 1, 1), torch.tensor([999], device=dev), T("ctx8")[:1])
+        assert rel_l2(y.cpu().numpy(), g15["out8_ctx1_t999"]) < FP32_TOL
+        y = net(T("lat8x16"), torch.tensor([301], device=dev), T("ctx8")[1:])
+        assert rel_l2(y.cpu().numpy(), g15["out8x16_t301"]) < FP32_TOL
+
+
+def test_fp32_ddim_loop_golden(sd15_fp32, g15, dev):
+    """Loop body of models/diffusion.py:223-236 (16x16 latent, DDIM-10, CFG 7.5)."""
+    net, _ = sd15_fp32
+    latent = torch.from_numpy(g15["lat16"]).to(dev)
+    ctx = torch.from_numpy(g15["ctx"]).to(dev)
+    smp = DDIMSampler()
+    smp._set_inference_steps(10)
+    with torch.no_grad():
+        for i, ts in enumerate(smp.timesteps.to(dev)):
+            ts = ts.unsqueeze(0)
+            out = net(latent.repeat(2, 1, 1, 1), ts, ctx)
+            latent = smp.reverse_process(latent, ts, out, cfg_scale=7.5)
+            if i == 0:
+                assert rel_l2(latent.cpu().numpy(), g15["loop16_ddim10_step1"]) < FP32_TOL
+    e = rel_l2(latent.cpu().numpy(), g15["loop16_ddim10_final"])
+    print(f"fp32 DDIM-10 loop final latent rel-L2 {e:.3e}")
+    assert e < FP32_TOL
+
+
+def test_fp32_sd21_golden(golden_dir, dev):
+    g = np.load(os.path.join(golden_dir, "unet_sd21_golden.npz"))
+    net, _ = _make(UO.SD21, 1, dev, "fp32")
+    T = lambda k: torch.from_numpy(g[k]).to(dev)
+    with torch.no_grad():
+        y = net(T("lat16").repeat(2, 1, 1, 1), torch.tensor([961], device=dev), T("ctx"))
+        assert rel_l2(y.cpu().numpy(), g["out16_t961"]) < FP32_TOL
+        smp = DDIMSampler(prediction_type="v_prediction")
+        smp._set_inference_steps(5)
+        latent = T("lat16")
+        for ts in smp.timesteps.to(dev):
+            ts = ts.unsqueeze(0)
+            latent = smp.reverse_process(latent, ts, net(latent.repeat(2, 1, 1, 1), ts, T("ctx")), cfg_scale=7.5)
+        assert rel_l2(latent.cpu().numpy(), g["loop16_ddim5_v_final"]) < FP32_TOL
+        pn = net(T("onestep_lat"), torch.tensor([999], device=dev), T("ctx")[:1])
+        assert rel_l2(pn.cpu().numpy(), g["onestep_pred"]) < FP32_TOL
+    del net
+    torch.cuda.empty_cache()
+
+
+def test_rejects_cpu_and_bad_shapes(sd15_fp32, dev):
+    net, _ = sd15_fp32
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 4, 8, 8), torch.tensor([1]), torch.zeros(1, 77, 768))
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 4, 12, 12, device=dev), torch.tensor([1], device=dev), torch.zeros(1, 77, 768, device=dev))
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(2, 4, 8, 8, device=dev), torch.tensor([1, 2, 3], device=dev), torch.zeros(2, 77, 768, device=dev))
