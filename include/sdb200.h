@@ -108,6 +108,40 @@ int sdk_attention_f32(const float* q, int64_t q_row, int64_t q_batch, const floa
                       const float* v, int64_t v_row, int64_t v_batch, float* out, int64_t o_row, int64_t o_batch,
                       int B, int heads, int Sq, int Sk, int D, float scale, void* stream);
 
+/* bf16 tensor-core attention (mma.sync m16n8k16, fp32 softmax statistics); same contract as sdk_attention_f32 with bf16 tensors */
+int sdk_attention_bf16(const void* q, int64_t q_row, int64_t q_batch, const void* k, int64_t k_row, int64_t k_batch,
+                       const void* v, int64_t v_row, int64_t v_batch, void* out, int64_t o_row, int64_t o_batch,
+                       int B, int heads, int Sq, int Sk, int D, float scale, void* stream);
+
+/* ---- tcgen05 / TMEM / TMA implicit GEMM (bf16 operands, fp32 accumulate) -----------------------------
+ * Same math as sdk_conv_gemm_f32 for stride-1 "same" convolutions (ksize 1|3) and linears, with up to two
+ * (activation, weight) segments accumulated into one output (segment 1 = a fused 1x1 shortcut conv,
+ * unet.py:192).  Activations: NHWC bf16 [B][H][W][C], C % 64 == 0; weights bf16 [N][ksize*ksize*C].
+ * A plan object holds the TMA descriptors; launches are async and graph-capturable.
+ * Replaces nn.Conv2d/nn.Linear at unet.py:67,71,158,161,168,246,401; attention.py:19-25; activation_fn.py:14. */
+typedef struct SdkTcGemmDesc {
+    const void* a[2];
+    const void* w[2];
+    int C[2];
+    int ksize[2];
+    int nseg;
+    int B, H, W;
+    int N;
+    const float* bias; const float* tbias; int64_t tb_stride; const float* residual;
+    void* out;
+    int out_dtype, geglu, out_nchw;
+    int block_n;        /* 0 = auto (32|64|128|160|256) */
+    int splits;         /* 0 = auto split-K */
+} SdkTcGemmDesc;
+int sdk_tc_gemm_create(const SdkTcGemmDesc* desc, void** handle);
+int64_t sdk_tc_gemm_workspace_bytes(void* handle);
+int sdk_tc_gemm_set_workspace(void* handle, void* workspace);   /* zeroed once by the caller; shared across plans run on one stream */
+int sdk_tc_gemm_info(void* handle, int* out, int n);            /* block_n, splits, grid.x, grid.y, TW, TH, TB, k-blocks */
+int sdk_tc_gemm_launch(void* handle, void* stream);
+int sdk_tc_gemm_destroy(void* handle);
+/* stride-2 3x3 conv (unet.py:236): gather fp32 NHWC -> bf16 [B*Ho*Wo][9*C] rows, then a 1-tap sdk_tc_gemm */
+int sdk_im2col_s2(const float* src, void* dst, int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

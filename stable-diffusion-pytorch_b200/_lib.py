@@ -43,6 +43,16 @@ SIGNATURES = {
     "sdk_conv_gemm_f32": [P, P],
     # --- attention_simt.cu
     "sdk_attention_f32": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, P],
+    # --- attention_mma.cu
+    "sdk_attention_bf16": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, P],
+    # --- gemm_tc.cu
+    "sdk_tc_gemm_create": [P, P],
+    "sdk_tc_gemm_workspace_bytes": [P],
+    "sdk_tc_gemm_set_workspace": [P, P],
+    "sdk_tc_gemm_info": [P, P, I32],
+    "sdk_tc_gemm_launch": [P, P],
+    "sdk_tc_gemm_destroy": [P],
+    "sdk_im2col_s2": [P, P, I32, I32, I32, I32, P],
     # --- misc
     "sdk_device_info": [P, I32],
 }
@@ -57,8 +67,17 @@ class ConvParams(C.Structure):
                 ("in_dtype", I32), ("out_dtype", I32), ("out_nchw", I32), ("geglu", I32)]
 
 
+class TcGemmDesc(C.Structure):
+    """Mirror of SdkTcGemmDesc (include/sdb200.h)."""
+    _fields_ = [("a", P * 2), ("w", P * 2), ("C", I32 * 2), ("ksize", I32 * 2), ("nseg", I32),
+                ("B", I32), ("H", I32), ("W", I32), ("N", I32),
+                ("bias", P), ("tbias", P), ("tb_stride", I64), ("residual", P), ("out", P),
+                ("out_dtype", I32), ("geglu", I32), ("out_nchw", I32), ("block_n", I32), ("splits", I32)]
+
+
 F32_T, BF16_T = 0, 1
-RESTYPES = {"sdk_last_error": C.c_char_p, "sdk_version": C.c_int, "sdk_groupnorm_workspace_bytes": C.c_int64}
+RESTYPES = {"sdk_last_error": C.c_char_p, "sdk_version": C.c_int, "sdk_groupnorm_workspace_bytes": C.c_int64,
+            "sdk_tc_gemm_workspace_bytes": C.c_int64}
 SIGNATURES.update({"sdk_last_error": [], "sdk_version": []})
 
 

@@ -1,0 +1,519 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution and linear layers — the tensor-core path of the
+// UNet (84 % of the step's FLOPs).
+//
+//   out[m][n] = epilogue( sum_seg sum_tap sum_c  A_seg(m, tap, c) * W_seg[n][tap*C + c] )
+//
+// * A operand: NHWC bf16 activations, fetched by 4-D TMA boxes {64 ch, TW, TH, TB} (<= 128 pixels per
+//   tile).  A 3x3 tap is the same box shifted by (dx, dy); the zero padding of the convolution is the
+//   TMA out-of-bounds zero fill, so no im2col buffer exists.  A Linear / 1x1 conv is the 1-tap case.
+// * B operand: K-major bf16 weights [N][taps*C], 2-D TMA boxes {64, BN}.
+// * Both land in shared memory in the 128-byte-swizzled K-major layout that tcgen05.mma reads
+//   directly through shared-memory descriptors; the fp32 accumulator lives in TMEM (BN columns).
+// * A second (A, W) segment accumulates into the same TMEM tile (ResBlock 1x1 shortcut fused into conv_2).
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner, warps 2..5 =
+//   epilogue (tcgen05.ld 32 lanes x 32 columns -> bias / time-bias / residual / GEGLU -> global).
+//   smem stages are recycled through full/empty mbarriers (tcgen05.commit releases a stage).
+// * Small-M layers (deep UNet levels at small batch) are weight-streaming bound: split-K over
+//   blockIdx.z with per-tile fp32 partials and a last-CTA fix-up in fixed split order (deterministic).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/sdb200.h"
+#include <new>
+#include <string.h>
+
+namespace {
+
+constexpr int BM = 128, BK = 64, TC_THREADS = 192;
+constexpr int A_STAGE_BYTES = BM * BK * 2;           // 16 KiB
+
+struct alignas(64) TcParams {
+    CUtensorMap tmA[2];
+    CUtensorMap tmB[2];
+    int seg_taps[2], seg_kb[2], seg_ksize[2], seg_C[2];
+    int nseg;
+    int TW, TH, TB, rows;
+    int W, H, B;
+    int tiles_w, tiles_h, tiles_b;
+    int N, Nout;
+    int total_kb, splits, kb_per_split;
+    const float* bias; const float* tbias; long long tb_stride; const float* residual;
+    void* out; int out_dtype, geglu, out_nchw;
+    float* partial; unsigned int* counters;
+};
+
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<unsigned*>(&a); u.y = *reinterpret_cast<unsigned*>(&b);
+    u.z = *reinterpret_cast<unsigned*>(&c); u.w = *reinterpret_cast<unsigned*>(&d);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// Epilogue for one thread = one output row, 32 consecutive GEMM columns starting at n (absolute).
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int n, long long grow, int b, int oy, int ox) {
+    const int N = p.N;
+    if (n >= N) return;
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(p.bias + n + j);
+    }
+    if (p.tbias) {
+        const float* tb = p.tbias + (long long)b * p.tb_stride + n;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(tb + j);
+    }
+    if (p.geglu) {
+        // (value, gate) column pairs -> 16 outputs   (models/activation_fn.py:17-20)
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf_f(v[2 * j + 1]);
+        const long long off = grow * p.Nout + (n >> 1);
+        if (p.residual) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] += __ldg(p.residual + off + j);
+        }
+        if (p.out_dtype == SDK_BF16) {
+            store_bf16x8((__nv_bfloat16*)p.out + off, o);
+            store_bf16x8((__nv_bfloat16*)p.out + off + 8, o + 8);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>((float*)p.out + off + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+        return;
+    }
+    if (p.out_nchw) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (n + j < N) {
+                float y = v[j];
+                const long long o = (((long long)b * N + n + j) * p.H + oy) * p.W + ox;
+                if (p.residual) y += __ldg(p.residual + o);
+                if (p.out_dtype == SDK_BF16) ((__nv_bfloat16*)p.out)[o] = __float2bfloat16_rn(y);
+                else ((float*)p.out)[o] = y;
+            }
+        }
+        return;
+    }
+    const long long off = grow * N + n;
+    if (n + 32 <= N) {
+        if (p.residual) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + off + j));
+                v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
+            }
+        }
+        if (p.out_dtype == SDK_BF16) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) store_bf16x8((__nv_bfloat16*)p.out + off + j, v + j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>((float*)p.out + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (n + j < N) {
+                float y = v[j];
+                if (p.residual) y += __ldg(p.residual + off + j);
+                if (p.out_dtype == SDK_BF16) ((__nv_bfloat16*)p.out)[off + j] = __float2bfloat16_rn(y);
+                else ((float*)p.out)[off + j] = y;
+            }
+        }
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
+    constexpr int B_STAGE_BYTES = BN * BK * 2;
+    constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM, BN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint32_t* last_flag = tmem_slot + 1;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- tile coordinates
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    const int tb = t;
+    const int w0 = tw * p.TW, h0 = th * p.TH, b0 = tb * p.TB;
+    const int n0 = blockIdx.y * BN;
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
+    const int n_it = kb_end - kb_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        ptx::mbar_init(tmem_full, 1);
+        ptx::fence_barrier_init();
+        ptx::prefetch_tmap(&p.tmA[0]);
+        ptx::prefetch_tmap(&p.tmB[0]);
+        if (p.nseg > 1) { ptx::prefetch_tmap(&p.tmA[1]); ptx::prefetch_tmap(&p.tmB[1]); }
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            const uint32_t stage_bytes = (uint32_t)p.rows * (BK * 2) + (uint32_t)B_STAGE_BYTES;
+            const int seg0_its = p.seg_taps[0] * p.seg_kb[0];
+            for (int i = 0; i < n_it; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                int it = kb_begin + i, seg = 0;
+                if (it >= seg0_its) { it -= seg0_its; seg = 1; }
+                const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
+                int dx = 0, dy = 0;
+                if (p.seg_ksize[seg] == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
+                ptx::mbar_wait(&empty[s], ph ^ 1u);
+                ptx::mbar_expect_tx(&full[s], stage_bytes);
+                ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 + dx, h0 + dy, b0);
+                ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            for (int i = 0; i < n_it; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                ptx::mbar_wait(&full[s], ph);
+                ptx::tc_fence_after();
+                const uint64_t da = ptx::umma_smem_desc_sw128(ptx::smem_u32(sA + s * A_STAGE_BYTES));
+                const uint64_t db = ptx::umma_smem_desc_sw128(ptx::smem_u32(sB + s * B_STAGE_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)      // +32 B per K=16 step inside the 128 B swizzle atom
+                    ptx::umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                ptx::umma_commit(&empty[s]);           // frees the smem stage when these MMAs retire
+            }
+            ptx::umma_commit(tmem_full);               // accumulator complete
+        }
+    } else {
+        // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                    // tile row == TMEM lane
+        const int tw_i = r % p.TW, th_i = (r / p.TW) % p.TH, tb_i = r / (p.TW * p.TH);
+        const int ox = w0 + tw_i, oy = h0 + th_i, b = b0 + tb_i;
+        const bool valid = r < p.rows && ox < p.W && oy < p.H && b < p.B;
+        const long long grow = ((long long)b * p.H + oy) * p.W + ox;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+
+        ptx::mbar_wait(tmem_full, 0);
+        ptx::tc_fence_after();
+        if (p.splits == 1) {
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t u[32];
+                ptx::tmem_ld32(taddr + c * 32, u);
+                ptx::tmem_ld_wait();
+                if (valid) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                    epilogue_chunk(p, v, n0 + c * 32, grow, b, oy, ox);
+                }
+            }
+        } else {
+            float* mine = p.partial + (((size_t)tile_id * p.splits + blockIdx.z) * BM + r) * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t u[32];
+                ptx::tmem_ld32(taddr + c * 32, u);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    __stcg(reinterpret_cast<float4*>(mine + c * 32 + j),
+                           make_float4(__uint_as_float(u[j]), __uint_as_float(u[j + 1]), __uint_as_float(u[j + 2]), __uint_as_float(u[j + 3])));
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+                const unsigned prev = atomicAdd(&p.counters[tile_id], 1u);
+                const unsigned last = (prev == (unsigned)p.splits - 1u) ? 1u : 0u;
+                if (last) p.counters[tile_id] = 0u;      // self-reset for the next launch
+                *last_flag = last;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*last_flag) {
+                __threadfence();
+                if (valid) {
+                    const float* base = p.partial + (((size_t)tile_id * p.splits) * BM + r) * BN;
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        for (int s = 0; s < p.splits; ++s) {          // fixed order -> deterministic
+                            const float4* src = reinterpret_cast<const float4*>(base + (size_t)s * BM * BN + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 x = __ldcg(src + j);
+                                v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+                            }
+                        }
+                        epilogue_chunk(p, v, n0 + c * 32, grow, b, oy, ox);
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, CUtensorMapL2promotion promo) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return sdk_fail(SDK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[4]; cuuint64_t gstride[3]; cuuint32_t bdim[4]; cuuint32_t estr[4];
+    uint64_t stride = 2;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) gstride[i] = stride;
+    }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sdk_fail(SDK_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rank %d dims %llu %llu box %u %u)", (int)r, rank,
+                                           (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return SDK_OK;
+}
+
+struct TcGemm {
+    TcParams prm;
+    int block_n, stages, smem_bytes;
+    dim3 grid;
+    int64_t ws_bytes;
+};
+
+template <int BN, int STAGES>
+int launch_cfg(const TcGemm* g, cudaStream_t s) {
+    constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        SDK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    conv_gemm_tc_kernel<BN, STAGES><<<g->grid, TC_THREADS, smem, s>>>(g->prm);
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
+void pick_tile(int W, int H, int B, int* TW, int* TH, int* TB) {
+    // rectangular pixel tile of <= 128 rows maximising MMA row occupancy
+    double best = -1.0;
+    int bw = 1, bh = 1, bb = 1;
+    for (int w = 1; w <= 128 && w <= W; ++w) {
+        if (W % w != 0 && w != 128) continue;               // divisors of W, or the full 128-wide strip
+        int h = 128 / w; if (h > H) h = H; if (h < 1) h = 1;
+        int b = 1;
+        if (w == W && h == H) { b = 128 / (w * h); if (b > B) b = B; if (b < 1) b = 1; }
+        const long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((B + b - 1) / b);
+        const double eff = (double)W * H * B / (double)(tiles * 128) + 1e-6 * w;   // tie-break: wider rows
+        if (eff > best) { best = eff; bw = w; bh = h; bb = b; }
+    }
+    *TW = bw; *TH = bh; *TB = bb;
+}
+
+}  // namespace
+
+extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
+    SDK_CHECK_ARG(d && handle, "sdk_tc_gemm_create: null pointer");
+    SDK_CHECK_ARG(d->nseg == 1 || d->nseg == 2, "sdk_tc_gemm_create: nseg %d", d->nseg);
+    SDK_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->N > 0 && d->out, "sdk_tc_gemm_create: bad sizes");
+    SDK_CHECK_ARG(!d->geglu || (d->N % 32 == 0 && !d->out_nchw), "sdk_tc_gemm_create: geglu needs N %% 32 == 0");
+    SDK_CHECK_ARG(d->out_nchw || d->geglu || d->N % 4 == 0, "sdk_tc_gemm_create: N %% 4 != 0 needs NCHW output");
+    SDK_CHECK_ARG(d->out_nchw || d->out_dtype != SDK_BF16 || d->N % 16 == 0, "sdk_tc_gemm_create: bf16 output needs N %% 16 == 0");
+    TcGemm* g = new (std::nothrow) TcGemm();
+    if (!g) return sdk_fail(SDK_ERR_CUDA, "out of host memory");
+    TcParams& p = g->prm;
+    memset(&p, 0, sizeof(p));
+    pick_tile(d->W, d->H, d->B, &p.TW, &p.TH, &p.TB);
+    p.rows = p.TW * p.TH * p.TB;
+    p.W = d->W; p.H = d->H; p.B = d->B;
+    p.tiles_w = (d->W + p.TW - 1) / p.TW; p.tiles_h = (d->H + p.TH - 1) / p.TH; p.tiles_b = (d->B + p.TB - 1) / p.TB;
+    p.N = d->N; p.Nout = d->geglu ? d->N / 2 : d->N;
+    p.nseg = d->nseg;
+    p.total_kb = 0;
+    for (int s = 0; s < d->nseg; ++s) {
+        if (!(d->a[s] && d->w[s] && d->C[s] > 0 && d->C[s] % 64 == 0 && (d->ksize[s] == 1 || d->ksize[s] == 3))) {
+            delete g;
+            return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: segment %d needs C %% 64 == 0 and ksize 1|3 (C=%d k=%d)", s, d->C[s], d->ksize[s]);
+        }
+        p.seg_C[s] = d->C[s]; p.seg_ksize[s] = d->ksize[s];
+        p.seg_taps[s] = d->ksize[s] * d->ksize[s]; p.seg_kb[s] = d->C[s] / BK;
+        p.total_kb += p.seg_taps[s] * p.seg_kb[s];
+    }
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    // ---- N tile
+    int bn = d->block_n;
+    if (bn == 0) {
+        const int cand[4] = {256, 160, 128, 64};
+        const int sms = sdk_num_sms();
+        bn = 0;
+        for (int i = 0; i < 4; ++i) {
+            if (d->N % cand[i]) continue;
+            if (m_tiles * (d->N / cand[i]) >= (sms * 4) / 5) { bn = cand[i]; break; }
+        }
+        if (bn == 0) {
+            if (d->N % 128 == 0) bn = 128; else if (d->N % 160 == 0) bn = 160; else if (d->N % 64 == 0) bn = 64; else bn = (d->N <= 32 ? 32 : (d->N <= 64 ? 64 : 128));
+        }
+    }
+    if (!(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256)) { delete g; return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_create: block_n %d", bn); }
+    const int n_tiles = (d->N + bn - 1) / bn;
+    // ---- split-K
+    int splits = d->splits;
+    if (splits == 0) {
+        const int tiles = m_tiles * n_tiles, sms = sdk_num_sms();
+        splits = 1;
+        if (tiles * 2 <= sms) {
+            splits = (sms + tiles - 1) / tiles;
+            const int max_splits = p.total_kb / 4 > 0 ? p.total_kb / 4 : 1;
+            if (splits > max_splits) splits = max_splits;
+            if (splits > 32) splits = 32;
+        }
+    }
+    if (splits < 1) splits = 1;
+    if (splits > p.total_kb) splits = p.total_kb;
+    p.kb_per_split = (p.total_kb + splits - 1) / splits;
+    splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.splits = splits;
+    // ---- tensor maps
+    int rc = SDK_OK;
+    for (int s = 0; s < d->nseg && rc == SDK_OK; ++s) {
+        const uint64_t adims[4] = {(uint64_t)d->C[s], (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
+        rc = encode_bf16(&p.tmA[s], d->a[s], 4, adims, abox, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+        if (rc != SDK_OK) break;
+        const uint64_t bdims[2] = {(uint64_t)p.seg_taps[s] * d->C[s], (uint64_t)d->N};
+        const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)bn};
+        rc = encode_bf16(&p.tmB[s], d->w[s], 2, bdims, bbox, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    }
+    if (rc != SDK_OK) { delete g; return rc; }
+    p.bias = d->bias; p.tbias = d->tbias; p.tb_stride = d->tb_stride; p.residual = d->residual;
+    p.out = d->out; p.out_dtype = d->out_dtype; p.geglu = d->geglu; p.out_nchw = d->out_nchw;
+    g->block_n = bn;
+    g->grid = dim3(m_tiles, n_tiles, splits);
+    g->ws_bytes = splits > 1 ? (int64_t)m_tiles * n_tiles * splits * BM * bn * 4 + (int64_t)m_tiles * n_tiles * 4 + 256 : 0;
+    *handle = g;
+    return SDK_OK;
+}
+
+extern "C" int64_t sdk_tc_gemm_workspace_bytes(void* handle) { return handle ? ((TcGemm*)handle)->ws_bytes : 0; }
+
+// workspace layout: [counters (tiles u32, 256-aligned)] [partials]; must have been zeroed once.
+extern "C" int sdk_tc_gemm_set_workspace(void* handle, void* ws) {
+    SDK_CHECK_ARG(handle, "sdk_tc_gemm_set_workspace: null handle");
+    TcGemm* g = (TcGemm*)handle;
+    if (g->prm.splits > 1) {
+        SDK_CHECK_ARG(ws, "sdk_tc_gemm_set_workspace: split-K GEMM needs a workspace");
+        const size_t tiles = (size_t)g->grid.x * g->grid.y;
+        g->prm.counters = (unsigned int*)ws;
+        g->prm.partial = (float*)((char*)ws + ((tiles * 4 + 255) / 256) * 256);
+    }
+    return SDK_OK;
+}
+
+// out[0]=block_n out[1]=splits out[2]=grid.x out[3]=grid.y out[4]=TW out[5]=TH out[6]=TB out[7]=total k-blocks
+extern "C" int sdk_tc_gemm_info(void* handle, int* out, int n) {
+    SDK_CHECK_ARG(handle && out && n >= 8, "sdk_tc_gemm_info: bad args");
+    TcGemm* g = (TcGemm*)handle;
+    out[0] = g->block_n; out[1] = g->prm.splits; out[2] = g->grid.x; out[3] = g->grid.y;
+    out[4] = g->prm.TW; out[5] = g->prm.TH; out[6] = g->prm.TB; out[7] = g->prm.total_kb;
+    return SDK_OK;
+}
+
+extern "C" int sdk_tc_gemm_launch(void* handle, void* stream) {
+    SDK_CHECK_ARG(handle, "sdk_tc_gemm_launch: null handle");
+    TcGemm* g = (TcGemm*)handle;
+    SDK_CHECK_ARG(g->prm.splits == 1 || g->prm.partial, "sdk_tc_gemm_launch: workspace not set for split-K");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (g->block_n) {
+        case 32: return launch_cfg<32, 8>(g, s);
+        case 64: return launch_cfg<64, 8>(g, s);
+        case 128: return launch_cfg<128, 6>(g, s);
+        case 160: return launch_cfg<160, 6>(g, s);
+        case 256: return launch_cfg<256, 4>(g, s);
+    }
+    return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_launch: block_n %d", g->block_n);
+}
+
+extern "C" int sdk_tc_gemm_destroy(void* handle) {
+    delete (TcGemm*)handle;
+    return SDK_OK;
+}
+
+// ---- stride-2 3x3 conv support: gather fp32 NHWC -> bf16 [B*Ho*Wo][9*C] (k = tap*C + c), pad 1 ----
+namespace {
+__global__ void __launch_bounds__(256)
+im2col_s2_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C, int Ho, int Wo) {
+    const int nq = C >> 2;
+    const long long total = (long long)B * Ho * Wo * 9 * nq;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % nq);
+        long long r = i / nq;
+        const int tap = (int)(r % 9); r /= 9;
+        const int ox = (int)(r % Wo); r /= Wo;
+        const int oy = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const int iy = oy * 2 + tap / 3 - 1, ix = ox * 2 + tap % 3 - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * H + iy) * W + ix) * C) + q);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 u; u.x = *reinterpret_cast<unsigned*>(&lo); u.y = *reinterpret_cast<unsigned*>(&hi);
+        *reinterpret_cast<uint2*>(dst + (i << 2)) = u;
+    }
+}
+}  // namespace
+
+extern "C" int sdk_im2col_s2(const float* src, void* dst, int B, int H, int W, int C, void* stream) {
+    SDK_CHECK_ARG(src && dst && B > 0 && H > 0 && W > 0 && C % 4 == 0, "sdk_im2col_s2: bad args");
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long total = (long long)B * Ho * Wo * 9 * (C / 4);
+    long long blocks = (total + 255) / 256, cap = (long long)sdk_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    im2col_s2_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, B, H, W, C, Ho, Wo);
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}

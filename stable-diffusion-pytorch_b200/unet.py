@@ -25,7 +25,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._lib import BF16_T, F32_T, ConvParams
+from ._lib import BF16_T, F32_T, ConvParams, TcGemmDesc
 from .arch import BLOCK_OUT, Conv, ResBlock, Transformer, UNetArch, build_arch, param_spec
 
 _DT = {F32_T: torch.float32, BF16_T: torch.bfloat16}
@@ -99,7 +99,7 @@ class PackedWeights:
                 p = st.resample.prefix
                 t[f"{p}.w"], t[f"{p}.b"] = conv_w(f"{p}.weight"), dev(sd[f"{p}.bias"])
         t["out.gn.g"], t["out.gn.b"] = dev(sd["output.0.weight"]), dev(sd["output.0.bias"])
-        t["out.w"], t["out.b"] = conv_w("output.2.weight", torch.float32), dev(sd["output.2.bias"])
+        t["out.w"], t["out.b"] = conv_w("output.2.weight", wdt), dev(sd["output.2.bias"])
         self.t = t
 
     def ptr(self, name) -> int:
@@ -160,6 +160,7 @@ class StepProgram:
         self.keep = []           # ctypes structs / tensors that must outlive the launches
         self.pool = _Pool(dev)
         self.n_launch = 0
+        self.tc_handles = []
 
         f32 = torch.float32
         # static I/O staging (graph-stable addresses)
@@ -209,7 +210,20 @@ class StepProgram:
         return out, Hout, Wout
 
     def _emit_tc_conv(self, p, srcs, w, ctx):
-        raise RuntimeError("bf16 tensor-core path is not built into this library")
+        """tcgen05 implicit GEMM for a stride-1 conv / linear described by ConvParams ``p``."""
+        if len(srcs) != 1 or p.stride != 1 or p.upsample:
+            raise RuntimeError("tensor-core conv takes one pre-concatenated, pre-upsampled bf16 source at stride 1")
+        d = TcGemmDesc()
+        d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = p.src0, p.weight, p.C0, p.ksize, 1
+        d.B, d.H, d.W, d.N = p.B, p.Hin, p.Win, p.N
+        d.bias, d.tbias, d.tb_stride, d.residual, d.out = p.bias, p.tbias, p.tb_stride, p.residual, p.out
+        d.out_dtype, d.geglu, d.out_nchw = p.out_dtype, p.geglu, p.out_nchw
+        d.block_n, d.splits = self.net.tc_block_n, self.net.tc_splits
+        h = C.c_void_p()
+        _lib.check(self.lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
+        self.tc_handles.append(h)
+        self.keep.append(d)
+        self._emit(self.lib.sdk_tc_gemm_launch, h, ctx=ctx)
 
     def _gn(self, srcs, B, HW, g, b, eps, silu, want_raw=False):
         """GroupNorm(32)(+SiLU) over the concat of srcs -> operand-typed tensor [B*HW, C]."""
@@ -374,11 +388,17 @@ class StepProgram:
                 skips.append((x, xc, h, w))
                 shared.add(id(x))
             if st.resample is not None:
-                op, tmp = self._operand(x, B, h, w, xc)
-                y, h, w = self._conv([(op, xc)], t[f"{st.resample.prefix}.w"], t[f"{st.resample.prefix}.b"], B, h, w, xc,
-                                     k=3, stride=2)
-                if tmp:
-                    self.pool.put(op)
+                wn, bn_ = t[f"{st.resample.prefix}.w"], t[f"{st.resample.prefix}.b"]
+                if self.act == F32_T:
+                    y, h, w = self._conv([(x, xc)], wn, bn_, B, h, w, xc, k=3, stride=2)
+                else:
+                    # stride-2 3x3 (unet.py:236): gather the 9 taps into bf16 rows, then a 1-tap tensor-core GEMM
+                    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+                    col = self.pool.get(B * ho * wo, 9 * xc, BF16_T)
+                    self._emit(lib.sdk_im2col_s2, x.data_ptr(), col.data_ptr(), B, h, w, xc)
+                    y, _, _ = self._conv([(col, 9 * xc)], wn, bn_, 1, 1, B * ho * wo, xc, k=1)
+                    self.pool.put(col)
+                    h, w = ho, wo
                 x = y
                 skips.append((x, xc, h, w))
                 shared.add(id(x))
@@ -422,15 +442,32 @@ class StepProgram:
         # head (unet.py:398-401): GN + SiLU + conv 320 -> out_channels, written straight to NCHW
         ao, _ = self._gn([(x, xc)], B, h * w, t["out.gn.g"], t["out.gn.b"], a.eps, True)
         self.pool.put(x)
-        if self.act == F32_T:
-            self._conv([(ao, xc)], t["out.w"], t["out.b"], B, h, w, a.out_channels, k=3, out=self.out, out_nchw=True)
-        else:
-            self._emit_head_tc(ao, xc, B, h, w)
+        self._conv([(ao, xc)], t["out.w"], t["out.b"], B, h, w, a.out_channels, k=3, out=self.out, out_nchw=True)
         self.pool.put(ao)
         self.n_launch = len(self.ops)
+        self._finish_tc()
 
-    def _emit_head_tc(self, ao, xc, B, h, w):
-        raise RuntimeError("bf16 tensor-core path is not built into this library")
+    def _finish_tc(self):
+        """One zeroed split-K workspace shared by every tensor-core GEMM of the program (stream-ordered)."""
+        need = max([int(self.lib.sdk_tc_gemm_workspace_bytes(h)) for h in self.tc_handles] + [0])
+        self.tc_ws = torch.zeros(max(need, 256), dtype=torch.uint8, device=self.device)
+        for h in self.tc_handles:
+            _lib.check(self.lib.sdk_tc_gemm_set_workspace(h, self.tc_ws.data_ptr()))
+
+    def tc_info(self):
+        out = []
+        buf = (C.c_int * 8)()
+        for h in self.tc_handles:
+            _lib.check(self.lib.sdk_tc_gemm_info(h, buf, 8))
+            out.append(tuple(buf))
+        return out
+
+    def __del__(self):
+        try:
+            for h in getattr(self, "tc_handles", []):
+                self.lib.sdk_tc_gemm_destroy(h)
+        except Exception:
+            pass
 
     # ---- execution ----------------------------------------------------------------------
     def launch(self, ops):
@@ -470,6 +507,8 @@ class UNet(nn.Module):
         for name, shape in param_spec(self.arch):
             self._register(name, shape)
         self.precision = os.environ.get("SDB200_PRECISION", "bf16")
+        self.tc_block_n = int(os.environ.get("SDB200_TC_BLOCK_N", "0"))      # 0 = auto; tuning / test overrides
+        self.tc_splits = int(os.environ.get("SDB200_TC_SPLITS", "0"))
         self.use_cuda_graph = os.environ.get("SDB200_CUDA_GRAPH", "1") != "0"
         self._packed: Dict = {}
         self._plans: Dict = {}

@@ -1,0 +1,296 @@
+"""GPU kernel-level parity: every C-ABI kernel against a plain PyTorch fp32 reference of the same op
+(TF32 disabled) on seeded inputs.  Tolerances: fp32 kernels 2e-5 rel-L2; bf16-operand kernels are
+compared on bf16-ROUNDED inputs with fp32 reference math, so only accumulation order and the final
+output rounding differ (<= 4e-3 for bf16 outputs, <= 2e-5 for fp32 outputs)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as Fn
+
+from stable_diffusion_pytorch_b200 import _lib
+from stable_diffusion_pytorch_b200._lib import BF16_T, F32_T, ConvParams, TcGemmDesc
+
+pytestmark = pytest.mark.gpu
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gen(shape, seed, dev, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference for the implicit GEMM: NHWC in, torch conv2d in fp32
+# ------------------------------------------------------------------------------------------------
+def ref_conv(srcs, w_nkkc, bias, k, stride, up, tbias, residual, geglu):
+    x = torch.cat([s.float() for s in srcs], dim=-1)                   # [B,H,W,C]
+    x = x.permute(0, 3, 1, 2)
+    if up:
+        x = Fn.interpolate(x, scale_factor=2, mode="nearest")
+    N = w_nkkc.shape[0]
+    w = w_nkkc.float().view(N, k, k, -1).permute(0, 3, 1, 2)
+    y = Fn.conv2d(x, w, bias, stride=stride, padding=k // 2)           # [B,N,Ho,Wo]
+    if tbias is not None:
+        y = y + tbias[:, :, None, None]
+    y = y.permute(0, 2, 3, 1)
+    if geglu:
+        y = y[..., 0::2] * Fn.gelu(y[..., 1::2])
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+CONV_CASES = [
+    # B, H, W, (C0, C1), N, k, stride, up, tbias, residual, geglu
+    (2, 16, 16, (320, 0), 320, 3, 1, False, "per", True, False),
+    (2, 8, 8, (1280, 1280), 1280, 3, 1, False, "one", False, False),
+    (1, 16, 16, (640, 320), 640, 1, 1, False, None, False, False),
+    (2, 16, 16, (320, 0), 320, 3, 2, False, None, False, False),
+    (2, 8, 8, (640, 0), 640, 3, 1, True, None, False, False),
+    (1, 1, 300, (320, 0), 2560, 1, 1, False, None, False, True),
+    (1, 8, 16, (4, 0), 320, 3, 1, False, None, False, False),
+    (3, 5, 7, (32, 0), 20, 3, 1, False, None, True, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_gemm_f32(dev, case):
+    B, H, W, (C0, C1), N, k, stride, up, tbm, res, geglu = case
+    lib = _lib.lib()
+    s0 = gen((B, H, W, C0), 1, dev)
+    s1 = gen((B, H, W, C1), 2, dev) if C1 else None
+    Cin = C0 + C1
+    w = gen((N, k * k * Cin), 3, dev, 1.0 / math.sqrt(k * k * Cin))
+    bias = gen((N,), 4, dev, 0.1)
+    upf = 2 if up else 1
+    Ho = (H * upf + 2 * (k // 2) - k) // stride + 1
+    Wo = (W * upf + 2 * (k // 2) - k) // stride + 1
+    tb = None if tbm is None else gen((B if tbm == "per" else 1, N), 5, dev)
+    Nout = N // 2 if geglu else N
+    resid = gen((B, Ho, Wo, Nout), 6, dev) if res else None
+    out = torch.empty((B, Ho, Wo, Nout), device=dev)
+    p = ConvParams()
+    p.src0, p.src1, p.C0, p.C1 = s0.data_ptr(), (s1.data_ptr() if C1 else 0), C0, C1
+    p.weight, p.bias = w.data_ptr(), bias.data_ptr()
+    p.tbias, p.tb_stride = (tb.data_ptr() if tb is not None else 0), (N if tbm == "per" else 0)
+    p.residual, p.out = (resid.data_ptr() if res else 0), out.data_ptr()
+    p.B, p.Hin, p.Win, p.Hout, p.Wout = B, H, W, Ho, Wo
+    p.ksize, p.stride, p.upsample, p.N = k, stride, int(up), N
+    p.in_dtype, p.out_dtype, p.out_nchw, p.geglu = F32_T, F32_T, 0, int(geglu)
+    _lib.check(lib.sdk_conv_gemm_f32(C.byref(p), stream()))
+    tbe = None if tb is None else tb.expand(B, N)
+    want = ref_conv([s0] + ([s1] if C1 else []), w, bias, k, stride, up, tbe, resid, geglu)
+    assert rel_l2(out, want) < 2e-5
+
+
+TC_CASES = [
+    # name, B, H, W, C, N, k, tbias, residual, geglu, out_dtype, out_nchw, block_n, splits
+    ("lin_L0", 1, 1, 8192, 320, 320, 1, None, True, False, F32_T, 0, 0, 0),
+    ("lin_ragged_kv", 1, 1, 154, 768, 640, 1, None, False, False, BF16_T, 0, 0, 0),
+    ("conv_L0", 2, 64, 64, 320, 320, 3, "one", False, False, F32_T, 0, 0, 0),
+    ("conv_L1", 2, 32, 32, 640, 640, 3, "per", True, False, F32_T, 0, 0, 0),
+    ("conv_L3_splitk", 2, 8, 8, 1280, 1280, 3, None, True, False, F32_T, 0, 0, 0),
+    ("conv_L2_bn256", 2, 16, 16, 1280, 1280, 3, None, False, False, F32_T, 0, 256, 1),
+    ("conv_bn128", 2, 16, 16, 640, 1280, 3, None, False, False, BF16_T, 0, 128, 3),
+    ("conv_bn64", 1, 16, 16, 320, 320, 3, None, False, False, F32_T, 0, 64, 2),
+    ("geglu", 1, 1, 2048, 640, 5120, 1, None, False, True, BF16_T, 0, 0, 0),
+    ("geglu_small", 1, 1, 128, 1280, 10240, 1, None, False, True, BF16_T, 0, 0, 0),
+    ("head_nchw", 2, 32, 32, 320, 4, 3, None, False, False, F32_T, 1, 0, 0),
+    ("odd_hw", 3, 24, 24, 320, 640, 3, None, True, False, F32_T, 0, 0, 0),
+    ("tiny_hw", 2, 4, 4, 1280, 1280, 3, None, False, False, F32_T, 0, 0, 0),
+    ("conv1x1_sp", 2, 16, 16, 2560, 1280, 1, None, False, False, F32_T, 0, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_tc_gemm(dev, case):
+    name, B, H, W, Cc, N, k, tbm, res, geglu, odt, nchw, bn, splits = case
+    lib = _lib.lib()
+    a = gen((B, H, W, Cc), 11, dev).bfloat16()
+    w = gen((N, k * k * Cc), 12, dev, 1.0 / math.sqrt(k * k * Cc)).bfloat16()
+    bias = gen((N,), 13, dev, 0.1)
+    tb = None if tbm is None else gen((B if tbm == "per" else 1, N), 14, dev)
+    Nout = N // 2 if geglu else N
+    resid = gen((B, H, W, Nout), 15, dev) if res else None
+    odtype = torch.float32 if odt == F32_T else torch.bfloat16
+    out = torch.full((B, Nout, H, W) if nchw else (B, H, W, Nout), float("nan"), device=dev, dtype=odtype)
+    d = TcGemmDesc()
+    d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = a.data_ptr(), w.data_ptr(), Cc, k, 1
+    d.B, d.H, d.W, d.N = B, H, W, N
+    d.bias = bias.data_ptr()
+    d.tbias, d.tb_stride = (tb.data_ptr() if tb is not None else 0), (N if tbm == "per" else 0)
+    d.residual, d.out = (resid.data_ptr() if res else 0), out.data_ptr()
+    d.out_dtype, d.geglu, d.out_nchw, d.block_n, d.splits = odt, int(geglu), nchw, bn, splits
+    h = C.c_void_p()
+    _lib.check(lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
+    info = (C.c_int * 8)()
+    _lib.check(lib.sdk_tc_gemm_info(h, info, 8))
+    ws = torch.zeros(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=dev)
+    _lib.check(lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr()))
+    for _ in range(2):                                    # twice: split-K tickets must self-reset
+        _lib.check(lib.sdk_tc_gemm_launch(h, stream()))
+    torch.cuda.synchronize()
+    lib.sdk_tc_gemm_destroy(h)
+    tbe = None if tb is None else tb.expand(B, N)
+    want = ref_conv([a], w, bias, k, 1, False, tbe, resid, geglu)
+    if nchw:
+        want = want.permute(0, 3, 1, 2)
+    e = rel_l2(out.float(), want)
+    print(f"{name}: block_n={info[0]} splits={info[1]} grid=({info[2]},{info[3]}) tile=({info[4]},{info[5]},{info[6]}) kb={info[7]} rel-L2={e:.2e}")
+    assert not torch.isnan(out.float()).any()
+    assert e < (4e-3 if odt == BF16_T else 2e-5)
+
+
+def test_tc_gemm_two_segments(dev):
+    """conv_2 (3x3 over a2) + fused 1x1 shortcut over the raw concat input (unet.py:188-193)."""
+    lib = _lib.lib()
+    B, H, W, C2, Cs, N = 2, 16, 16, 640, 1920, 640
+    a2 = gen((B, H, W, C2), 21, dev).bfloat16()
+    raw = gen((B, H, W, Cs), 22, dev).bfloat16()
+    w2 = gen((N, 9 * C2), 23, dev, 1 / math.sqrt(9 * C2)).bfloat16()
+    ws_ = gen((N, Cs), 24, dev, 1 / math.sqrt(Cs)).bfloat16()
+    bias = gen((N,), 25, dev, 0.1)
+    out = torch.empty((B, H, W, N), device=dev)
+    d = TcGemmDesc()
+    d.a[0], d.w[0], d.C[0], d.ksize[0] = a2.data_ptr(), w2.data_ptr(), C2, 3
+    d.a[1], d.w[1], d.C[1], d.ksize[1] = raw.data_ptr(), ws_.data_ptr(), Cs, 1
+    d.nseg, d.B, d.H, d.W, d.N = 2, B, H, W, N
+    d.bias, d.out, d.out_dtype = bias.data_ptr(), out.data_ptr(), F32_T
+    h = C.c_void_p()
+    _lib.check(lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
+    ws = torch.zeros(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=dev)
+    _lib.check(lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr()))
+    _lib.check(lib.sdk_tc_gemm_launch(h, stream()))
+    torch.cuda.synchronize()
+    lib.sdk_tc_gemm_destroy(h)
+    want = ref_conv([a2], w2, bias, 3, 1, False, None, None, False) + ref_conv([raw], ws_, None, 1, 1, False, None, None, False)
+    assert rel_l2(out, want) < 2e-5
+
+
+ATT_CASES = [(2, 8, 1024, 1024, 40), (2, 8, 256, 256, 160), (1, 8, 1024, 77, 80), (2, 5, 576, 576, 64),
+             (2, 8, 64, 77, 160), (1, 8, 100, 77, 40), (2, 20, 144, 144, 64)]
+
+
+@pytest.mark.parametrize("case", ATT_CASES)
+@pytest.mark.parametrize("mode", ["f32", "bf16"])
+def test_attention(dev, case, mode):
+    B, Hh, Sq, Sk, D = case
+    lib = _lib.lib()
+    Cc = Hh * D
+    dt = torch.float32 if mode == "f32" else torch.bfloat16
+    self_attn = Sq == Sk
+    if self_attn:
+        qkv = gen((B, Sq, 3 * Cc), 31, dev).to(dt)
+        q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+        strides = (3 * Cc, Sq * 3 * Cc, 3 * Cc, Sk * 3 * Cc, 3 * Cc, Sk * 3 * Cc)
+    else:
+        q = gen((B, Sq, Cc), 32, dev).to(dt)
+        kv = gen((1, Sk, 2 * Cc), 33, dev).to(dt)                       # batch-broadcast context
+        k, v = kv[..., :Cc], kv[..., Cc:]
+        strides = (Cc, Sq * Cc, 2 * Cc, 0, 2 * Cc, 0)
+    out = torch.empty((B, Sq, Cc), device=dev, dtype=dt)
+    fn = lib.sdk_attention_f32 if mode == "f32" else lib.sdk_attention_bf16
+    _lib.check(fn(q.data_ptr(), strides[0], strides[1], k.data_ptr(), strides[2], strides[3], v.data_ptr(), strides[4], strides[5],
+                  out.data_ptr(), Cc, Sq * Cc, B, Hh, Sq, Sk, D, float(D ** -0.5), stream()))
+
+    def heads(t):
+        return t.float().expand(B, -1, -1).reshape(B, t.shape[1], Hh, D).permute(0, 2, 1, 3)
+
+    qh, kh, vh = heads(q), heads(k), heads(v)
+    w = torch.softmax((qh @ kh.transpose(-1, -2)) * D ** -0.5, dim=-1)
+    want = (w @ vh).permute(0, 2, 1, 3).reshape(B, Sq, Cc)
+    e = rel_l2(out.float(), want)
+    print(f"attention {mode} {case}: rel-L2 {e:.2e}")
+    assert e < (2e-5 if mode == "f32" else 6e-3)
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 320, 0), (2, 64, 1280, 640), (1, 4096, 640, 320), (3, 16, 2560, 0), (2, 1024, 960, 0)])
+@pytest.mark.parametrize("odt", [F32_T, BF16_T])
+def test_groupnorm(dev, shape, odt):
+    B, HW, C0, C1 = shape
+    lib = _lib.lib()
+    s0 = gen((B, HW, C0), 41, dev) * 2 + 0.5
+    s1 = gen((B, HW, C1), 42, dev) if C1 else None
+    Ct = C0 + C1
+    gamma, beta = gen((Ct,), 43, dev) * 0.1 + 1, gen((Ct,), 44, dev) * 0.1
+    stats = torch.empty((B, 32, 2), device=dev)
+    ws = torch.zeros(int(lib.sdk_groupnorm_workspace_bytes(B, HW)), dtype=torch.uint8, device=dev)
+    odtype = torch.float32 if odt == F32_T else torch.bfloat16
+    out = torch.empty((B, HW, Ct), device=dev, dtype=odtype)
+    raw = torch.empty((B, HW, Ct), device=dev, dtype=odtype)
+    for _ in range(2):
+        _lib.check(lib.sdk_groupnorm_stats(s0.data_ptr(), C0, s1.data_ptr() if C1 else 0, C1, B, HW, 1e-5, stats.data_ptr(), ws.data_ptr(), stream()))
+        _lib.check(lib.sdk_groupnorm_apply(s0.data_ptr(), C0, s1.data_ptr() if C1 else 0, C1, B, HW, stats.data_ptr(), gamma.data_ptr(),
+                                           beta.data_ptr(), 1, out.data_ptr(), raw.data_ptr(), odt, stream()))
+    x = torch.cat([s0] + ([s1] if C1 else []), -1)
+    want = Fn.silu(Fn.group_norm(x.permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
+    assert rel_l2(out.float(), want) < (2e-5 if odt == F32_T else 4e-3)
+    assert rel_l2(raw.float(), x) < (1e-7 if odt == F32_T else 4e-3)
+
+
+@pytest.mark.parametrize("C_", [320, 640, 1280, 768])
+def test_layernorm(dev, C_):
+    lib = _lib.lib()
+    x = gen((1000, C_), 51, dev) * 3 + 1
+    g, b = gen((C_,), 52, dev) * 0.1 + 1, gen((C_,), 53, dev) * 0.1
+    for odt, dt, tol in ((F32_T, torch.float32, 2e-6), (BF16_T, torch.bfloat16, 4e-3)):
+        out = torch.empty((1000, C_), device=dev, dtype=dt)
+        _lib.check(lib.sdk_layernorm(x.data_ptr(), g.data_ptr(), b.data_ptr(), 1e-5, out.data_ptr(), odt, 1000, C_, stream()))
+        assert rel_l2(out.float(), Fn.layer_norm(x, (C_,), g, b, 1e-5)) < tol
+
+
+def test_time_embedding_and_gemv(dev):
+    lib = _lib.lib()
+    t = torch.tensor([981, 1, 500], device=dev)
+    out = torch.empty((3, 320), device=dev)
+    _lib.check(lib.sdk_time_sinusoid(t.data_ptr(), 3, 320, out.data_ptr(), stream()))
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, 160, dtype=torch.float32, device=dev) / 160)
+    xx = t[:, None].float() * freqs[None]
+    want = torch.cat([torch.cos(xx), torch.sin(xx)], -1)
+    assert (out - want).abs().max() < 2e-4            # |arg| up to ~1e3: a few ulp of the argument
+    W = gen((2000, 1280), 61, dev, 0.03)
+    bias = gen((2000,), 62, dev)
+    x = gen((3, 1280), 63, dev)
+    for wdt, code, tol in ((torch.float32, F32_T, 2e-6), (torch.bfloat16, BF16_T, 2e-6)):
+        Wd = W.to(wdt)
+        y = torch.empty((3, 2000), device=dev)
+        _lib.check(lib.sdk_gemv(Wd.data_ptr(), code, bias.data_ptr(), x.data_ptr(), y.data_ptr(), 3, 2000, 1280, 1, 1, stream()))
+        want = Fn.silu(Fn.linear(Fn.silu(x), Wd.float(), bias))
+        assert rel_l2(y, want) < 1e-5
+
+
+def test_cast_upsample_im2col_nchw(dev):
+    lib = _lib.lib()
+    x = gen((2, 6, 10, 64), 71, dev)
+    up = torch.empty((2, 12, 20, 64), device=dev, dtype=torch.bfloat16)
+    _lib.check(lib.sdk_cast_upsample(x.data_ptr(), up.data_ptr(), BF16_T, 2, 6, 10, 64, 2, stream()))
+    want = Fn.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1).bfloat16()
+    assert torch.equal(up, want)
+    col = torch.empty((2 * 3 * 5, 9 * 64), device=dev, dtype=torch.bfloat16)
+    _lib.check(lib.sdk_im2col_s2(x.data_ptr(), col.data_ptr(), 2, 6, 10, 64, stream()))
+    unf = Fn.unfold(x.permute(0, 3, 1, 2), 3, padding=1, stride=2)           # [B, C*9, L], index c*9 + tap
+    want = unf.view(2, 64, 9, 15).permute(0, 3, 2, 1).reshape(30, 576).bfloat16()
+    assert torch.equal(col, want)
+    lat = gen((1, 4, 8, 8), 72, dev)
+    nhwc = torch.empty((2, 64, 4), device=dev)
+    _lib.check(lib.sdk_nchw_to_nhwc(lat.data_ptr(), nhwc.data_ptr(), 1, 2, 4, 64, stream()))
+    assert torch.equal(nhwc, lat.repeat(2, 1, 1, 1).permute(0, 2, 3, 1).reshape(2, 64, 4))
