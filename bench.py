@@ -1,0 +1,364 @@
+"""Benchmark of the denoising hot path (BASELINE.json metric: SD1.5 UNet ms/step & images/sec, 512^2,
+DDIM-50, CFG 7.5) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4]
+                    [--batch-per-gpu B] [--precision bf16|fp32] [--no-cpu-baseline]
+
+A "step" is one pass of the loop body of models/diffusion.py:223-236 over one batch of synthetic input:
+UNet forward on the CFG-doubled batch + guidance blend + DDIM update.  With N GPUs every rank runs its own
+shard (data parallel, no collective inside a step; one all-gather of the final latents after the timed
+region is checked but not timed).  Rank 0 prints ONE JSON line.  See DESIGN.md §Measurement.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# algorithmic GFLOP per UNet sample (2*MACs of conv/linear + 4*B*H*Sq*Sk*D attention)
+GFLOP_PER_SAMPLE = {("sd15", 64): 803.25, ("sd15", 32): 180.08, ("sd21", 64): 804.26, ("sd21", 96): 2149.08}
+# dense-contraction part executed by the tcgen05 implicit-GEMM kernel (conv3x3 + s2 + conv1x1 + q/k/v/out proj
+# + GEGLU-in + FFN-out), GFLOP per step at UNet batch 2, SD1.5 64x64 (SURVEY.md §8(d) breakdown)
+GEMM_GFLOP_B2_SD15_64 = 789.3 + 11.3 + 87.2 + 159.4 + 204.7 + 102.3
+
+CONFIGS = {
+    2: dict(arch="sd15", hw=64, steps=50, cfg=True, batch=1, ptype="epsilon", dctx=768,
+            name="SD1.5-arch UNet 512^2 (64x64 latent), DDIM-50, CFG 7.5, batch 1 per GPU"),
+    3: dict(arch="sd15", hw=64, steps=50, cfg=True, batch=8, ptype="epsilon", dctx=768,
+            name="SD1.5-arch UNet 512^2, DDIM-50, CFG 7.5, batch 64 over 8 GPUs (8 per GPU)"),
+    4: dict(arch="sd21", hw=96, steps=50, cfg=True, batch=2, ptype="v_prediction", dctx=1024,
+            name="SD2.1-arch UNet 768^2 (96x96 latent), DDIM-50, v-prediction, batch 16 over 8 GPUs (2 per GPU)"),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p["bf16_tflops"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def build_oracle_inputs(cfg, total_batch):
+    from oracle import unet_oracle as UO          # synthetic-input recipe + weights (checker infrastructure)
+    arch = UO.SD15 if cfg["arch"] == "sd15" else UO.SD21
+    sd = UO.make_state_dict(0 if cfg["arch"] == "sd15" else 1, **arch)
+    g = torch.Generator().manual_seed(1234)
+    latent = torch.randn((total_batch, 4, cfg["hw"], cfg["hw"]), generator=g)
+    ctx = torch.randn(((2 if cfg["cfg"] else 1) * total_batch, 77, cfg["dctx"]), generator=g)
+    return arch, sd, latent, ctx
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_loop_body_seconds(cfg, sd, arch, hw, n_timed, budget_s):
+    """Seconds per loop-body step of the ORACLE port on the host cores (UNet batch 2B=2 + CFG + DDIM)."""
+    from oracle import sampler_oracle as SO
+    from oracle import unet_oracle as UO
+    torch.set_num_threads(os.cpu_count())
+    g = torch.Generator().manual_seed(1234)
+    lat = torch.randn((1, 4, hw, hw), generator=g)
+    nctx = 2 if cfg["cfg"] else 1
+    ctx = torch.randn((nctx, 77, cfg["dctx"]), generator=g)
+    _, alphas, a_hat = SO.schedule_fp32()
+    ts = SO.ddim_timesteps(1000, 50)
+    times = []
+    t_start = time.time()
+    with torch.no_grad():
+        for i in range(n_timed + 1):                       # first iteration = warm-up
+            t0 = time.time()
+            t = int(ts[min(i, len(ts) - 1)])
+            out = UO.unet_forward(sd, lat.repeat(nctx, 1, 1, 1), torch.tensor([t]), ctx, **arch)
+            if cfg["cfg"]:
+                u, c = SO.cfg_blend(out.numpy())
+                eps = SO.cfg_combine(u, c, 7.5)
+            else:
+                eps = out.numpy()
+            lat = torch.from_numpy(SO.ddim_reverse(lat.numpy(), t, eps, alphas, a_hat, 1000, 50, cfg["ptype"]))
+            dt = time.time() - t0
+            if i > 0:
+                times.append(dt)
+            if time.time() - t_start > budget_s and len(times) >= 1:
+                break
+    return sum(times) / len(times), len(times)
+
+
+def run_reference_arm(args, cfg):
+    """--impl reference: the reference's CPU path (oracle port; the Python reference cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arch, sd, _, _ = build_oracle_inputs(cfg, 1)
+    total = args.steps + args.warmup
+    hw = cfg["hw"]
+    est_full = 6.0 * (GFLOP_PER_SAMPLE[(cfg["arch"], hw)] / 803.25)
+    sample = f"full loop-body steps at {hw}x{hw} latent, UNet batch {2 if cfg['cfg'] else 1}"
+    scale = 1.0
+    if total * est_full > 240 and (cfg["arch"], 32) in GFLOP_PER_SAMPLE:
+        scale = GFLOP_PER_SAMPLE[(cfg["arch"], hw)] / GFLOP_PER_SAMPLE[(cfg["arch"], 32)]
+        hw = 32
+        sample = f"loop-body steps on a 32x32 latent, time scaled x{scale:.2f} by algorithmic FLOPs to {cfg['hw']}x{cfg['hw']}"
+    torch.set_num_threads(os.cpu_count())
+    n = max(1, min(args.steps, int(240 / max(est_full / scale, 0.5))))
+    sec, used = cpu_loop_body_seconds(cfg, sd, arch, hw, n, budget_s=240)
+    sec *= scale
+    img_s = 1.0 / (cfg["steps"] * sec)
+    line = {"impl": "reference", "metric": "images_per_sec", "value": img_s, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "timed_steps": used},
+            "cpu_baseline": {"value": img_s, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": img_s, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+def time_gemm_family(loop, iters=5):
+    """Average device time of ALL tcgen05 implicit-GEMM launches of one step, replayed back to back as a graph."""
+    lib_launch = loop.prog.lib.sdk_tc_gemm_launch
+    ops = [(fn, a) for fn, a in loop.prog.ops if fn is lib_launch]
+    if not ops:
+        return None, 0
+    g = torch.cuda.CUDAGraph()
+    loop.prog.launch(ops)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        loop.prog.launch(ops)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, len(ops)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--batch-per-gpu", type=int, default=0)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.batch_per_gpu:
+        cfg["batch"] = args.batch_per_gpu
+    if args.impl == "reference":
+        return run_reference_arm(args, cfg)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from stable_diffusion_pytorch_b200 import DDIMSampler, UNet
+    from stable_diffusion_pytorch_b200.dist import gather_latents, shard_inputs
+    from stable_diffusion_pytorch_b200.pipeline import DenoiseLoop
+
+    B = cfg["batch"]
+    arch, sd, latent_all, ctx_all = build_oracle_inputs(cfg, B * world)
+    net = UNet(attention_head_dim=arch["attention_head_dim"], cross_attention_dim=arch["cross_attention_dim"])
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval().set_precision(args.precision)
+    lat, ctx = shard_inputs(latent_all, ctx_all, rank, world, do_cfg=cfg["cfg"])
+    lat_d, ctx_d = lat.to(dev), ctx.to(dev)
+    smp = DDIMSampler(prediction_type=cfg["ptype"])
+    smp._set_inference_steps(50)
+    loop = DenoiseLoop(net, smp, B, cfg["hw"], cfg["hw"], do_cfg=cfg["cfg"], cfg_scale=7.5, use_cuda_graph=not args.no_graph)
+    K, Wm = args.steps, args.warmup
+    n_grid = len(smp.timesteps)
+
+    def run_steps(n):
+        done = 0
+        while done < n:                                      # walk the 50-step grid; restart the walk when it ends
+            m = min(n - done, n_grid - int(loop_pos[0]))
+            for _ in range(m):
+                loop.step()
+            loop_pos[0] += m
+            done += m
+            if loop_pos[0] >= n_grid:
+                loop.counter.zero_()
+                loop_pos[0] = 0
+
+    loop_pos = [0]
+    with torch.no_grad():
+        loop.reset(lat_d, ctx_d)
+        run_steps(Wm)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        run_steps(K)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler.stop_flag = True
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        ms_step = ms_total / K
+        finite = bool(torch.isfinite(loop.latent).all().item())
+
+        # ---- e2e through the public drop-in API with HOST buffers (UNet.forward + sampler.reverse_process)
+        ub = 2 * B if cfg["cfg"] else B
+        lat_h = lat.clone().pin_memory()
+        ctx_h = ctx.clone().pin_memory()
+        res_h = torch.empty_like(lat_h).pin_memory()
+        ts_list = smp.timesteps.tolist()
+
+        def e2e_step(i):
+            x = lat_h.to(dev, non_blocking=True)
+            c = ctx_h.to(dev, non_blocking=True)
+            tt = torch.tensor([ts_list[i % n_grid]], dtype=torch.int64).to(dev, non_blocking=True)
+            xin = x.repeat(2, 1, 1, 1) if cfg["cfg"] else x
+            o = net(xin, tt, c)
+            y = smp.reverse_process(x, tt, o, cfg_scale=7.5) if cfg["cfg"] else smp.reverse_process(x, tt, o)
+            res_h.copy_(y, non_blocking=True)
+            torch.cuda.current_stream().synchronize()         # the caller reads the step's result on the host
+            lat_h.copy_(res_h)
+
+        for i in range(3):
+            e2e_step(i)
+        k2 = max(3, min(K, 20))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(k2):
+            e2e_step(3 + i)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / k2
+        t = torch.tensor([e2e_ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        h2d = lat_h.numel() * 4 + ctx_h.numel() * 4 + 8
+        d2h = res_h.numel() * 4
+
+        # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM), rank 0
+        gemm_ms, gemm_launches = (None, 0)
+        if rank == 0 and args.precision == "bf16":
+            gemm_ms, gemm_launches = time_gemm_family(loop)
+
+        # the path's only collective: gather final latents (not timed; checked)
+        final = gather_latents(loop.latent.clone(), B * world)
+        assert final.shape[0] == B * world
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, tf_burst, tf_sus, peak_src = peaks()
+    imgs_per_s = (B * world) / (cfg["steps"] * ms_step * 1e-3)
+    e2e_imgs = (B * world) / (cfg["steps"] * e2e_ms * 1e-3)
+    gf_sample = GFLOP_PER_SAMPLE[(cfg["arch"], cfg["hw"])]
+    step_gflop = gf_sample * ub
+    roof = None
+    if gemm_ms:
+        gemm_gflop = GEMM_GFLOP_B2_SD15_64 * (ub / 2.0) if (cfg["arch"], cfg["hw"]) == ("sd15", 64) else None
+        if gemm_gflop:
+            ach = gemm_gflop / gemm_ms            # GFLOP / ms == TFLOP/s
+            roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
+                    "kernel": "conv_gemm_tc_kernel (tcgen05 implicit GEMM), all launches of one step",
+                    "launches_per_step": gemm_launches, "ms_per_step_in_kernel": gemm_ms, "share_of_step": gemm_ms / ms_step,
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"}
+    line = {
+        "metric": "images_per_sec", "value": imgs_per_s, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": cfg["name"], "images_per_gpu": B, "unet_batch_per_gpu": ub, "latent": [cfg["hw"], cfg["hw"]],
+                   "sampler_steps_per_image": cfg["steps"], "cfg_scale": 7.5 if cfg["cfg"] else None,
+                   "l2_policy": "inputs larger than L2: each step streams 1.72 GB of bf16 weights (L2 = 126 MB)",
+                   "cuda_graph": not args.no_graph, "finite": finite},
+        "step_tflops": step_gflop / ms_step, "step_frac_of_peak": step_gflop / ms_step / tf_sus,
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_imgs, "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "UNet.forward + DDIMSampler.reverse_process, pinned host buffers in and out every step"},
+        "gpu_launches": loop.launches_per_step * K,
+        "roofline": roof,
+    }
+    if not args.no_cpu_baseline and world >= 1:
+        try:
+            sec, used = cpu_loop_body_seconds(cfg, sd, arch, cfg["hw"], 2, budget_s=45)
+            line["cpu_baseline"] = {"value": 1.0 / (cfg["steps"] * sec), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{used} loop-body steps (after 1 warm-up) of the oracle port at {cfg['hw']}x{cfg['hw']}, extrapolated x{cfg['steps']}",
+                                    "s_per_step": sec}
+        except Exception as ex:                               # the baseline must never take the bench line down
+            line["cpu_baseline"] = {"error": repr(ex)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,9 @@ int sdk_forward_process(const float* x0, const float* noise, float* out, int64_t
 /* models/diffusion.py:111-113 — one-step x0 = (x - sigma*eps)/alpha */
 int sdk_x0_from_eps(const float* x, const float* eps, float sigma, float alpha, float* out, int64_t n, void* stream);
 
+/* device-side walk of the (host-built) timestep grid: t_out[0] = table[counter[0]++]  (models/diffusion.py:223) */
+int sdk_next_timestep(const int64_t* table, int n, int* counter, int64_t* t_out, void* stream);
+
 /* ---- normalisation / layout (models/unet/unet.py:66,102-108,157,160,250,343,399) ------------- */
 int64_t sdk_groupnorm_workspace_bytes(int B, int HW);
 /* GroupNorm(32) statistics over the channel-concat [src0 | src1] (src1 may be NULL with C1 = 0);

@@ -62,8 +62,8 @@ __device__ __forceinline__ float ddpm_one(float x, float e, const Coef& k, float
 // MODE 0/1: DDIM eps / v ; MODE 2: DDPM
 template <int MODE>
 __global__ void __launch_bounds__(256)
-step_kernel(const float* __restrict__ x, const float* __restrict__ eu, const float* __restrict__ ec, float scale,
-            const float* __restrict__ noise, float* __restrict__ out, long long n,
+step_kernel(const float* x, const float* __restrict__ eu, const float* __restrict__ ec, float scale,
+            const float* __restrict__ noise, float* out, long long n,      // x and out may alias (in-place latent state)
             const float* __restrict__ table, int T, const long long* __restrict__ t_dev, long long t_host, int vec_ok) {
     Coef k;
     const bool ok = load_coef(table, T, t_dev, t_host, k);
@@ -71,7 +71,7 @@ step_kernel(const float* __restrict__ x, const float* __restrict__ eu, const flo
     const long long nvec = vec_ok ? (n >> 2) : 0;      // 16-byte path only when every pointer is 16-byte aligned
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+        float4 xv = reinterpret_cast<const float4*>(x)[i];
         float4 uv = __ldg(reinterpret_cast<const float4*>(eu) + i);
         float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (noise) zv = __ldg(reinterpret_cast<const float4*>(noise) + i);
@@ -182,6 +182,26 @@ extern "C" int sdk_x0_from_eps(const float* x, const float* eps, float sigma, fl
     SDK_CHECK_ARG(x && eps && out, "sdk_x0_from_eps: null pointer");
     if (n <= 0) return SDK_OK;
     x0_from_eps_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, eps, sigma, alpha, out, n);
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
+// ---- loop bookkeeping on the device: t_out[0] = table[counter[0]]; counter[0]++ -------------------
+// Lets a whole sampling step (UNet + CFG + scheduler update) be ONE CUDA-graph replay with no host
+// work in between: the timestep sequence (host-built, bit-exact) is uploaded once and walked here.
+namespace {
+__global__ void next_timestep_kernel(const long long* __restrict__ table, int n, int* __restrict__ counter, long long* __restrict__ t_out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int i = counter[0];
+        t_out[0] = (i >= 0 && i < n) ? table[i] : -1;     // -1 poisons the sampler update (NaN) instead of reading out of range
+        counter[0] = i + 1;
+    }
+}
+}  // namespace
+
+extern "C" int sdk_next_timestep(const int64_t* table, int n, int* counter, int64_t* t_out, void* stream) {
+    SDK_CHECK_ARG(table && counter && t_out && n > 0, "sdk_next_timestep: bad args");
+    next_timestep_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const long long*)table, n, counter, (long long*)t_out);
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }

@@ -1,0 +1,145 @@
+"""The denoising loop as ONE replayable device program — drop-in for the loop body of the
+reference's ``StableDiffusion.generate`` (models/diffusion.py:223-236) and for the one-step path
+(models/diffusion.py:106-113).
+
+Per step the reference does: ``latent.repeat(2,...)`` -> UNet -> ``chunk(2)`` -> ``u + s*(c-u)`` ->
+``sampler.reverse_process`` with three host syncs.  Here a step is a single CUDA-graph replay:
+
+    next_timestep (device walk of the host-built grid)  ->  UNet step program (batch 2B, the repeat is
+    folded into the NCHW->NHWC gather)  ->  fused CFG + DDIM/DDPM update, in place on the latent state
+
+so the host enqueues one graph launch per step and never synchronises.  The timestep grid, the
+coefficient tables and all index bookkeeping are the sampler's (bit-exact with the reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .scheduler import PRED_EPS, PRED_V, DDIMSampler, DDPMSampler, x0_from_eps
+from .unet import StepProgram, UNet
+
+
+class DenoiseLoop:
+    """Sampler loop for a fixed problem shape.
+
+    loop = DenoiseLoop(unet, sampler, batch=B, height=h, width=w, do_cfg=True, cfg_scale=7.5)
+    latent = loop.run(latent, context)          # context rows [uncond ; cond] when do_cfg
+    """
+
+    def __init__(self, unet: UNet, sampler, batch: int, height: int, width: int, *, do_cfg: bool = True,
+                 cfg_scale: float = 7.5, context_len: int = 77, context_batch: Optional[int] = None,
+                 device=None, use_cuda_graph: Optional[bool] = None):
+        if not isinstance(sampler, (DDIMSampler, DDPMSampler)):
+            raise TypeError("sampler must be a stable_diffusion_pytorch_b200 DDIMSampler/DDPMSampler")
+        self.unet, self.sampler = unet, sampler
+        self.device = torch.device(device) if device is not None else next(unet.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("DenoiseLoop needs the UNet on a CUDA device; there is no CPU fallback")
+        self.B, self.H, self.W = batch, height, width
+        self.do_cfg, self.cfg_scale = do_cfg, float(cfg_scale)
+        ub = 2 * batch if do_cfg else batch
+        bc = ub if context_batch is None else context_batch
+        self.lib = _lib.lib()
+        pw = unet._weights(self.device)
+        self.prog = StepProgram(unet, pw, ub, height, width, 1, bc, context_len, b_src=batch)
+        self.use_graph = unet.use_cuda_graph if use_cuda_graph is None else use_cuda_graph
+        self.graph = None
+        self.latent = self.prog.x_in                         # the loop state IS the UNet's input staging buffer
+        self.noise = torch.empty_like(self.latent) if isinstance(sampler, DDPMSampler) else None
+        self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.ts_table = None
+        self._grid_key = None
+        self._cond_ref, self._cond_version = None, -1
+        self.launches_per_step = len(self.prog.ops) + 2
+
+    # ---- one step = [next timestep] + UNet program + [CFG + scheduler update in place] -------------------
+    def _enqueue_step(self):
+        s, p, lib = self.sampler, self.prog, self.lib
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(lib.sdk_next_timestep(self.ts_table.data_ptr(), self.ts_table.numel(), self.counter.data_ptr(),
+                                         p.t_in.data_ptr(), stream))
+        p.launch(p.ops)
+        n = self.latent.numel()
+        out = p.out
+        eps_u = out.data_ptr()
+        eps_c = out.data_ptr() + 4 * n if self.do_cfg else 0
+        if isinstance(s, DDPMSampler):
+            _lib.check(lib.sdk_ddpm_step(self.latent.data_ptr(), eps_u, eps_c, self.cfg_scale, self.noise.data_ptr(),
+                                         self.latent.data_ptr(), n, self.coef.data_ptr(), s.noise_step, p.t_in.data_ptr(), 0, stream))
+        else:
+            pred = PRED_V if s.prediction_type == "v_prediction" else PRED_EPS
+            _lib.check(lib.sdk_ddim_step(self.latent.data_ptr(), eps_u, eps_c, self.cfg_scale, 0, self.latent.data_ptr(), n,
+                                         self.coef.data_ptr(), s.noise_step, p.t_in.data_ptr(), 0, pred, stream))
+
+    def _prepare(self, context: torch.Tensor):
+        s, p = self.sampler, self.prog
+        key = (tuple(s.timesteps.tolist()), s._stride())
+        if key != self._grid_key:
+            self.ts_table = s.timesteps.to(self.device, torch.int64).contiguous()
+            self.coef = s._coef_table(self.device, 0.0)
+            self._grid_key = key
+            self.graph = None                                  # tables are baked into the captured launches
+        if context is not self._cond_ref or context._version != self._cond_version:
+            if tuple(context.shape) != tuple(p.cond_in.shape):
+                raise RuntimeError(f"context shape {tuple(context.shape)} != {tuple(p.cond_in.shape)}")
+            p.cond_in.copy_(context, non_blocking=True)
+            p.launch(p.ctx_ops)                                # cross-attention K/V once per generation (loop-invariant)
+            self._cond_ref, self._cond_version = context, context._version
+
+    def step(self):
+        """Advance the latent state by one sampler step (device-side timestep walk)."""
+        if isinstance(self.sampler, DDPMSampler):
+            # same global-RNG draw as ddpm.py:80, outside the graph so torch's generator state advances normally
+            self.noise.copy_(torch.randn(self.latent.shape, dtype=self.latent.dtype, device=self.device))
+        if not self.use_graph:
+            self._enqueue_step()
+        elif self.graph is None:
+            if not getattr(self, "_warm", False):
+                self._enqueue_step()
+                self._warm = True
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_step()
+                self.graph = g
+                g.replay()
+        else:
+            self.graph.replay()
+
+    def reset(self, latent: torch.Tensor, context: torch.Tensor):
+        if tuple(latent.shape) != tuple(self.latent.shape):
+            raise RuntimeError(f"latent shape {tuple(latent.shape)} != {tuple(self.latent.shape)}")
+        self._prepare(context)
+        self.latent.copy_(latent, non_blocking=True)
+        self.counter.zero_()
+
+    def run(self, latent: torch.Tensor, context: torch.Tensor, steps: Optional[int] = None) -> torch.Tensor:
+        """Full loop over ``sampler.timesteps`` (or the first ``steps`` of them); returns the final latent."""
+        self.reset(latent, context)
+        n = len(self.sampler.timesteps) if steps is None else steps
+        for _ in range(n):
+            self.step()
+        return self.latent.clone()
+
+
+@torch.no_grad()
+def denoise(unet: UNet, sampler, latent: torch.Tensor, context: torch.Tensor, *, do_cfg: bool = True,
+            cfg_scale: float = 7.5) -> torch.Tensor:
+    """Functional form of the loop body of models/diffusion.py:223-236 (sampler._set_inference_steps first)."""
+    b, _, h, w = latent.shape
+    loop = DenoiseLoop(unet, sampler, b, h, w, do_cfg=do_cfg, cfg_scale=cfg_scale, context_len=context.shape[1],
+                       context_batch=context.shape[0], device=latent.device)
+    return loop.run(latent, context)
+
+
+@torch.no_grad()
+def one_step(unet: UNet, sampler, latent: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+    """SwiftBrush one-step generation (models/diffusion.py:106-113): t = sampler.timesteps[0], no CFG,
+    context batch 1 broadcast, x0 = (x - sigma_T*eps)/alpha_T."""
+    t = sampler.timesteps[0].to(latent.device).unsqueeze(0)
+    pred = unet(latent, t, context)
+    return x0_from_eps(latent, pred)

@@ -145,8 +145,9 @@ class _Pool:
 class StepProgram:
     """One UNet forward for fixed (B, H, W, n_timesteps, cond batch, Sk) as a flat launch list."""
 
-    def __init__(self, net: "UNet", pw: PackedWeights, B, H, W, nt, Bc, Sk):
+    def __init__(self, net: "UNet", pw: PackedWeights, B, H, W, nt, Bc, Sk, b_src=None):
         self.net, self.pw = net, pw
+        self.b_src = B if b_src is None else b_src     # latent rows actually stored: B == 2*b_src folds latent.repeat(2,...)
         self.B, self.H, self.W, self.nt, self.Bc, self.Sk = B, H, W, nt, Bc, Sk
         a: UNetArch = net.arch
         self.arch = a
@@ -164,7 +165,7 @@ class StepProgram:
 
         f32 = torch.float32
         # static I/O staging (graph-stable addresses)
-        self.x_in = torch.empty((B, a.in_channels, H, W), dtype=f32, device=dev)
+        self.x_in = torch.empty((self.b_src, a.in_channels, H, W), dtype=f32, device=dev)
         self.t_in = torch.zeros((nt,), dtype=torch.int64, device=dev)
         self.cond_in = torch.empty((Bc, Sk, a.dctx), dtype=f32, device=dev)
         self.out = torch.empty((B, a.out_channels, H, W), dtype=f32, device=dev)
@@ -363,7 +364,7 @@ class StepProgram:
 
         # conv_in (unet.py:256): NCHW latent -> NHWC, then 3x3 conv with Cin = 4 (FFMA kernel: K = 36)
         xin = self.pool.get(B * H * W, a.in_channels, F32_T)
-        self._emit(lib.sdk_nchw_to_nhwc, self.x_in.data_ptr(), xin.data_ptr(), B, B, a.in_channels, H * W)
+        self._emit(lib.sdk_nchw_to_nhwc, self.x_in.data_ptr(), xin.data_ptr(), self.b_src, B, a.in_channels, H * W)
         x, _, _ = self._conv([(xin, a.in_channels)], t["conv_in.w"], t["conv_in.b"], B, H, W, BLOCK_OUT[0], k=3,
                              in_code=F32_T, force_simt=True)
         self.pool.put(xin)

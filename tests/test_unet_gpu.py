@@ -117,3 +117,70 @@ def test_rejects_cpu_and_bad_shapes(sd15_fp32, dev):
         net(torch.zeros(1, 4, 12, 12, device=dev), torch.tensor([1], device=dev), torch.zeros(1, 77, 768, device=dev))
     with pytest.raises(RuntimeError):
         net(torch.zeros(2, 4, 8, 8, device=dev), torch.tensor([1, 2, 3], device=dev), torch.zeros(2, 77, 768, device=dev))
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 tensor-core mode (tcgen05 GEMMs, bf16 operands, fp32 accumulate / residual stream)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def sd15_bf16(dev):
+    return _make(UO.SD15, 0, dev, "bf16")
+
+
+def test_bf16_forward_golden(sd15_bf16, g15, dev):
+    net, _ = sd15_bf16
+    T = lambda k: torch.from_numpy(g15[k]).to(dev)
+    with torch.no_grad():
+        for t in (981, 1):
+            y = net(T("lat16").repeat(2, 1, 1, 1), torch.tensor([t], device=dev), T("ctx"))
+            e = rel_l2(y.cpu().numpy(), g15[f"out16_t{t}"])
+            print(f"bf16 out16 t={t}: rel-L2 {e:.3e}")
+            assert e < BF16_TOL
+        y2 = net(T("lat16").repeat(2, 1, 1, 1), torch.tensor([1], device=dev), T("ctx"))     # graph capture
+        y3 = net(T("lat16").repeat(2, 1, 1, 1), torch.tensor([1], device=dev), T("ctx"))     # graph replay
+        assert torch.equal(y2, y) and torch.equal(y3, y), "bf16 path must be run-to-run deterministic"
+        y = net(T("lat8").repeat(2, 1, 1, 1), torch.tensor([500, 20], device=dev), T("ctx8"))
+        assert rel_l2(y.cpu().numpy(), g15["out8_t500_20"]) < BF16_TOL
+        y = net(T("lat8").repeat(2, 1, 1, 1), torch.tensor([999], device=dev), T("ctx8")[:1])
+        assert rel_l2(y.cpu().numpy(), g15["out8_ctx1_t999"]) < BF16_TOL
+        y = net(T("lat8x16"), torch.tensor([301], device=dev), T("ctx8")[1:])
+        assert rel_l2(y.cpu().numpy(), g15["out8x16_t301"]) < BF16_TOL
+
+
+def test_bf16_ddim_loop_golden(sd15_bf16, g15, dev):
+    net, _ = sd15_bf16
+    latent = torch.from_numpy(g15["lat16"]).to(dev)
+    ctx = torch.from_numpy(g15["ctx"]).to(dev)
+    smp = DDIMSampler()
+    smp._set_inference_steps(10)
+    with torch.no_grad():
+        for i, ts in enumerate(smp.timesteps.to(dev)):
+            ts = ts.unsqueeze(0)
+            latent = smp.reverse_process(latent, ts, net(latent.repeat(2, 1, 1, 1), ts, ctx), cfg_scale=7.5)
+            if i == 0:
+                print(f"bf16 DDIM-10 step-1 latent rel-L2 {rel_l2(latent.cpu().numpy(), g15['loop16_ddim10_step1']):.3e}")
+    e = rel_l2(latent.cpu().numpy(), g15["loop16_ddim10_final"])
+    print(f"bf16 DDIM-10 loop final latent rel-L2 {e:.3e}")
+    assert e < BF16_TOL
+
+
+def test_bf16_sd21_golden(golden_dir, dev):
+    g = np.load(os.path.join(golden_dir, "unet_sd21_golden.npz"))
+    net, _ = _make(UO.SD21, 1, dev, "bf16")
+    T = lambda k: torch.from_numpy(g[k]).to(dev)
+    with torch.no_grad():
+        y = net(T("lat16").repeat(2, 1, 1, 1), torch.tensor([961], device=dev), T("ctx"))
+        e = rel_l2(y.cpu().numpy(), g["out16_t961"])
+        print(f"bf16 sd21 out16: rel-L2 {e:.3e}")
+        assert e < BF16_TOL
+        smp = DDIMSampler(prediction_type="v_prediction")
+        smp._set_inference_steps(5)
+        latent = T("lat16")
+        for ts in smp.timesteps.to(dev):
+            ts = ts.unsqueeze(0)
+            latent = smp.reverse_process(latent, ts, net(latent.repeat(2, 1, 1, 1), ts, T("ctx")), cfg_scale=7.5)
+        e = rel_l2(latent.cpu().numpy(), g["loop16_ddim5_v_final"])
+        print(f"bf16 sd21 v-pred DDIM-5 final: rel-L2 {e:.3e}")
+        assert e < BF16_TOL
+    del net
+    torch.cuda.empty_cache()
