@@ -119,7 +119,7 @@ int sdk_attention_bf16(const void* q, int64_t q_row, int64_t q_batch, const void
 /* ---- tcgen05 / TMEM / TMA implicit GEMM (bf16 operands, fp32 accumulate) -----------------------------
  * Same math as sdk_conv_gemm_f32 for stride-1 "same" convolutions (ksize 1|3) and linears, with up to two
  * (activation, weight) segments accumulated into one output (segment 1 = a fused 1x1 shortcut conv,
- * unet.py:192).  Activations: NHWC bf16 [B][H][W][C], C % 64 == 0; weights bf16 [N][ksize*ksize*C].
+ * unet.py:192).  Activations: NHWC bf16 [B][H][W][C], C % 64 == 0; weights bf16 [N][ksize*ksize*C] or k-block-major (w_kmajor).
  * A plan object holds the TMA descriptors; launches are async and graph-capturable.
  * Replaces nn.Conv2d/nn.Linear at unet.py:67,71,158,161,168,246,401; attention.py:19-25; activation_fn.py:14. */
 typedef struct SdkTcGemmDesc {
@@ -135,6 +135,7 @@ typedef struct SdkTcGemmDesc {
     int out_dtype, geglu, out_nchw;
     int block_n;        /* 0 = auto (32|64|128|160|256) */
     int splits;         /* 0 = auto split-K */
+    int w_kmajor;       /* 0: weights [N][K] row-major; 1: k-block-major [K/64][N][64] (contiguous B stages) */
 } SdkTcGemmDesc;
 int sdk_tc_gemm_create(const SdkTcGemmDesc* desc, void** handle);
 int64_t sdk_tc_gemm_workspace_bytes(void* handle);

@@ -13,8 +13,11 @@
 // * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner, warps 2..5 =
 //   epilogue (tcgen05.ld 32 lanes x 32 columns -> bias / time-bias / residual / GEGLU -> global).
 //   smem stages are recycled through full/empty mbarriers (tcgen05.commit releases a stage).
+// * Weights are stored k-block-major [K/64][N][64] so that a CTA's B stage is ONE contiguous BN*128-byte
+//   run of HBM (sequential DRAM pages) instead of BN 128-byte pieces 2*K bytes apart.
 // * Small-M layers (deep UNet levels at small batch) are weight-streaming bound: split-K over
-//   blockIdx.z with per-tile fp32 partials and a last-CTA fix-up in fixed split order (deterministic).
+//   blockIdx.z writes fp32 partials [split][row][N]; a second, fully parallel kernel sums the splits in
+//   fixed order (deterministic) and applies the epilogue.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/sdb200.h"
@@ -30,7 +33,7 @@ struct alignas(64) TcParams {
     CUtensorMap tmA[2];
     CUtensorMap tmB[2];
     int seg_taps[2], seg_kb[2], seg_ksize[2], seg_C[2];
-    int nseg;
+    int nseg, w_kmajor;
     int TW, TH, TB, rows;
     int W, H, B;
     int tiles_w, tiles_h, tiles_b;
@@ -38,7 +41,7 @@ struct alignas(64) TcParams {
     int total_kb, splits, kb_per_split;
     const float* bias; const float* tbias; long long tb_stride; const float* residual;
     void* out; int out_dtype, geglu, out_nchw;
-    float* partial; unsigned int* counters;
+    float* partial; long long M;
 };
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* v) {
@@ -125,7 +128,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, (STAGES <= 3 || (BN <= 64 && STAGES <= 4)) ? 2 : 1)
 conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int B_STAGE_BYTES = BN * BK * 2;
     constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
@@ -139,7 +142,6 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    uint32_t* last_flag = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -187,7 +189,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 ptx::mbar_wait(&empty[s], ph ^ 1u);
                 ptx::mbar_expect_tx(&full[s], stage_bytes);
                 ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 + dx, h0 + dy, b0);
-                ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, n0);
+                if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, tap * p.seg_kb[seg] + kb);
+                else ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -216,7 +219,6 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         const bool valid = r < p.rows && ox < p.W && oy < p.H && b < p.B;
         const long long grow = ((long long)b * p.H + oy) * p.W + ox;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
 
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
@@ -234,44 +236,22 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 }
             }
         } else {
-            float* mine = p.partial + (((size_t)tile_id * p.splits + blockIdx.z) * BM + r) * BN;
+            // split-K: raw fp32 partial sums, row-major [split][M][N]; reduced by splitk_reduce_kernel
+            float* mine = p.partial + ((size_t)blockIdx.z * p.M + (size_t)(valid ? grow : 0)) * p.N + n0;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t u[32];
                 ptx::tmem_ld32(taddr + c * 32, u);
                 ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    __stcg(reinterpret_cast<float4*>(mine + c * 32 + j),
-                           make_float4(__uint_as_float(u[j]), __uint_as_float(u[j + 1]), __uint_as_float(u[j + 2]), __uint_as_float(u[j + 3])));
-            }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) {
-                const unsigned prev = atomicAdd(&p.counters[tile_id], 1u);
-                const unsigned last = (prev == (unsigned)p.splits - 1u) ? 1u : 0u;
-                if (last) p.counters[tile_id] = 0u;      // self-reset for the next launch
-                *last_flag = last;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*last_flag) {
-                __threadfence();
                 if (valid) {
-                    const float* base = p.partial + (((size_t)tile_id * p.splits) * BM + r) * BN;
-#pragma unroll 1
-                    for (int c = 0; c < BN / 32; ++c) {
-                        float v[32];
+                    if (n0 + c * 32 + 32 <= p.N) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                        for (int s = 0; s < p.splits; ++s) {          // fixed order -> deterministic
-                            const float4* src = reinterpret_cast<const float4*>(base + (size_t)s * BM * BN + c * 32);
+                        for (int j = 0; j < 32; j += 4)
+                            __stcg(reinterpret_cast<float4*>(mine + c * 32 + j),
+                                   make_float4(__uint_as_float(u[j]), __uint_as_float(u[j + 1]), __uint_as_float(u[j + 2]), __uint_as_float(u[j + 3])));
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 x = __ldcg(src + j);
-                                v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-                            }
-                        }
-                        epilogue_chunk(p, v, n0 + c * 32, grow, b, oy, ox);
+                        for (int j = 0; j < 32; ++j) if (n0 + c * 32 + j < p.N) mine[c * 32 + j] = __uint_as_float(u[j]);
                     }
                 }
             }
@@ -282,6 +262,80 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// Split-K second pass: one thread = one output row x 4 columns; consecutive threads take consecutive float4s
+// of a row (coalesced 16-byte loads, splits unrolled for memory-level parallelism), sum the splits in index
+// order (deterministic) and run the epilogue.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const __grid_constant__ TcParams p) {
+    const int N = p.N, quads = (N + 3) >> 2;
+    const long long total = p.M * quads;
+    const size_t plane = (size_t)p.M * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int qd = (int)(i % quads);
+        const long long grow = i / quads;
+        const int n = qd << 2;
+        const float* src = p.partial + (size_t)grow * N + n;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (n + 4 <= N) {
+            int sp = 0;
+            for (; sp + 4 <= p.splits; sp += 4) {
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sp * plane));
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 1) * plane));
+                const float4 c = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 2) * plane));
+                const float4 d = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 3) * plane));
+                v[0] = (((v[0] + a.x) + b.x) + c.x) + d.x; v[1] = (((v[1] + a.y) + b.y) + c.y) + d.y;
+                v[2] = (((v[2] + a.z) + b.z) + c.z) + d.z; v[3] = (((v[3] + a.w) + b.w) + c.w) + d.w;
+            }
+            for (; sp < p.splits; ++sp) {
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sp * plane));
+                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            }
+        } else {
+            for (int sp = 0; sp < p.splits; ++sp)
+                for (int j = 0; j < 4; ++j) if (n + j < N) v[j] += __ldcg(src + (size_t)sp * plane + j);
+        }
+        const int ox = (int)(grow % p.W);
+        const long long t2 = grow / p.W;
+        const int oy = (int)(t2 % p.H), b = (int)(t2 / p.H);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (n + j < N) {
+                if (p.bias) v[j] += __ldg(p.bias + n + j);
+                if (p.tbias) v[j] += __ldg(p.tbias + (long long)b * p.tb_stride + n + j);
+            }
+        }
+        if (p.geglu) {
+            const long long off = grow * p.Nout + (n >> 1);
+            float o0 = v[0] * gelu_erf_f(v[1]), o1 = v[2] * gelu_erf_f(v[3]);
+            if (p.residual) { o0 += __ldg(p.residual + off); o1 += __ldg(p.residual + off + 1); }
+            if (p.out_dtype == SDK_BF16) *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)p.out + off) = __floats2bfloat162_rn(o0, o1);
+            else *reinterpret_cast<float2*>((float*)p.out + off) = make_float2(o0, o1);
+        } else if (p.out_nchw || n + 4 > N) {
+            for (int j = 0; j < 4; ++j) {
+                if (n + j >= N) break;
+                const long long o = p.out_nchw ? (((long long)b * N + n + j) * p.H + oy) * p.W + ox : grow * N + n + j;
+                float y = v[j];
+                if (p.residual) y += __ldg(p.residual + o);
+                if (p.out_dtype == SDK_BF16) ((__nv_bfloat16*)p.out)[o] = __float2bfloat16_rn(y);
+                else ((float*)p.out)[o] = y;
+            }
+        } else {
+            const long long off = grow * N + n;
+            if (p.residual) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+                v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+            }
+            if (p.out_dtype == SDK_BF16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+                uint2 u; u.x = *reinterpret_cast<unsigned*>(&lo); u.y = *reinterpret_cast<unsigned*>(&hi);
+                *reinterpret_cast<uint2*>((__nv_bfloat16*)p.out + off) = u;
+            } else {
+                *reinterpret_cast<float4*>((float*)p.out + off) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
     }
 }
 
@@ -304,6 +358,7 @@ EncodeTiledFn get_encode() {
 }
 
 int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, CUtensorMapL2promotion promo) {
+    // densely packed tensor, innermost dimension first
     EncodeTiledFn enc = get_encode();
     if (!enc) return sdk_fail(SDK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[4]; cuuint64_t gstride[3]; cuuint32_t bdim[4]; cuuint32_t estr[4];
@@ -323,6 +378,7 @@ int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims,
 struct TcGemm {
     TcParams prm;
     int block_n, stages, smem_bytes;
+    bool co_resident;
     dim3 grid;
     int64_t ws_bytes;
 };
@@ -337,6 +393,13 @@ int launch_cfg(const TcGemm* g, cudaStream_t s) {
     }
     conv_gemm_tc_kernel<BN, STAGES><<<g->grid, TC_THREADS, smem, s>>>(g->prm);
     SDK_LAUNCH_CHECK();
+    if (g->prm.splits > 1) {
+        const long long items = g->prm.M * ((g->prm.N + 3) / 4);
+        long long blocks = (items + 255) / 256, cap = (long long)sdk_num_sms() * 8;
+        if (blocks > cap) blocks = cap;
+        splitk_reduce_kernel<<<(int)blocks, 256, 0, s>>>(g->prm);
+        SDK_LAUNCH_CHECK();
+    }
     return SDK_OK;
 }
 
@@ -386,34 +449,53 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         p.total_kb += p.seg_taps[s] * p.seg_kb[s];
     }
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-    // ---- N tile
-    int bn = d->block_n;
-    if (bn == 0) {
-        const int cand[4] = {256, 160, 128, 64};
-        const int sms = sdk_num_sms();
-        bn = 0;
-        for (int i = 0; i < 4; ++i) {
-            if (d->N % cand[i]) continue;
-            if (m_tiles * (d->N / cand[i]) >= (sms * 4) / 5) { bn = cand[i]; break; }
+    p.M = (long long)d->B * d->H * d->W;
+    p.w_kmajor = d->w_kmajor;
+    // ---- N tile and split-K: pick the (block_n, splits) pair with the lowest modelled time.
+    // Model (SM clocks): a CTA's k-block is bound by the L2->smem feed of its A (16 KiB) + B (block_n*128 B)
+    // stage at ~42 B/clk/SM when all SMs pull (LTS cap ~6300 B/clk), by the MMA issue (2*block_n clk), and the
+    // whole launch by streaming the weights from HBM once; split-K adds the partial round trip.
+    const int sms = sdk_num_sms();
+    int bn = d->block_n, splits = d->splits;
+    {
+        const int cands[5] = {256, 160, 128, 64, 32};
+        double best = 1e30;
+        int best_bn = 0, best_sp = 1;
+        for (int i = 0; i < 5; ++i) {
+            const int c = cands[i];
+            if (d->block_n && c != d->block_n) continue;
+            if (!d->block_n) {
+                if (c >= 64 && d->N % c != 0 && d->N > c) continue;       // exact tilings only (all UNet widths are multiples of 160)
+                if (c > 32 && d->N <= c / 2) continue;                      // do not waste most of a tile on padding
+            }
+            const int n_t = (d->N + c - 1) / c;
+            const int tiles = m_tiles * n_t;
+            const int max_sp = d->splits ? d->splits : (p.total_kb / 4 > 0 ? (p.total_kb / 4 < 32 ? p.total_kb / 4 : 32) : 1);
+            for (int sp = (d->splits ? d->splits : 1); sp <= max_sp; ++sp) {
+                const int kb_cta = (p.total_kb + sp - 1) / sp;
+                const int real_sp = (p.total_kb + kb_cta - 1) / kb_cta;
+                if (real_sp != sp && !d->splits) continue;
+                const long long ctas = (long long)tiles * real_sp;
+                const long long waves = (ctas + sms - 1) / sms;
+                const double active = (double)(ctas < sms ? ctas : sms);
+                double feed = 6300.0 / active; if (feed > 110.0) feed = 110.0;      // B/clk per SM
+                const double stage_bytes = 16384.0 + c * 128.0;
+                double t_kb = stage_bytes / feed;
+                if (t_kb < 2.0 * c) t_kb = 2.0 * c;
+                const double t_epi = c * (d->geglu ? 24.0 : 8.0) * (real_sp > 1 ? 0.5 : 1.0);
+                double t = waves * (kb_cta * t_kb + 2500.0 + t_epi);
+                const double w_bytes = (double)p.total_kb * 64.0 * d->N * 2.0;
+                const double t_hbm = w_bytes / 3400.0 * 1.0;                         // ~6.5 TB/s at ~1.9 GHz = 3400 B/clk
+                if (t < t_hbm) t = t_hbm;
+                if (real_sp > 1) t += 4000.0 + (double)real_sp * p.M * d->N * 8.0 / 2500.0;
+                if (t < best) { best = t; best_bn = c; best_sp = real_sp; }
+                if (d->splits) break;
+            }
         }
-        if (bn == 0) {
-            if (d->N % 128 == 0) bn = 128; else if (d->N % 160 == 0) bn = 160; else if (d->N % 64 == 0) bn = 64; else bn = (d->N <= 32 ? 32 : (d->N <= 64 ? 64 : 128));
-        }
+        if (best_bn == 0) { delete g; return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_create: no tile for N=%d block_n=%d", d->N, d->block_n); }
+        bn = best_bn; splits = best_sp;
     }
-    if (!(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 256)) { delete g; return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_create: block_n %d", bn); }
     const int n_tiles = (d->N + bn - 1) / bn;
-    // ---- split-K
-    int splits = d->splits;
-    if (splits == 0) {
-        const int tiles = m_tiles * n_tiles, sms = sdk_num_sms();
-        splits = 1;
-        if (tiles * 2 <= sms) {
-            splits = (sms + tiles - 1) / tiles;
-            const int max_splits = p.total_kb / 4 > 0 ? p.total_kb / 4 : 1;
-            if (splits > max_splits) splits = max_splits;
-            if (splits > 32) splits = 32;
-        }
-    }
     if (splits < 1) splits = 1;
     if (splits > p.total_kb) splits = p.total_kb;
     p.kb_per_split = (p.total_kb + splits - 1) / splits;
@@ -426,31 +508,38 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
         rc = encode_bf16(&p.tmA[s], d->a[s], 4, adims, abox, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
         if (rc != SDK_OK) break;
-        const uint64_t bdims[2] = {(uint64_t)p.seg_taps[s] * d->C[s], (uint64_t)d->N};
-        const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)bn};
-        rc = encode_bf16(&p.tmB[s], d->w[s], 2, bdims, bbox, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (d->w_kmajor) {
+            const uint64_t bdims[3] = {(uint64_t)BK, (uint64_t)d->N, (uint64_t)p.seg_taps[s] * p.seg_kb[s]};
+            const uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)bn, 1u};
+            rc = encode_bf16(&p.tmB[s], d->w[s], 3, bdims, bbox, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        } else {
+            const uint64_t bdims[2] = {(uint64_t)p.seg_taps[s] * d->C[s], (uint64_t)d->N};
+            const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)bn};
+            rc = encode_bf16(&p.tmB[s], d->w[s], 2, bdims, bbox, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        }
     }
     if (rc != SDK_OK) { delete g; return rc; }
     p.bias = d->bias; p.tbias = d->tbias; p.tb_stride = d->tb_stride; p.residual = d->residual;
     p.out = d->out; p.out_dtype = d->out_dtype; p.geglu = d->geglu; p.out_nchw = d->out_nchw;
     g->block_n = bn;
     g->grid = dim3(m_tiles, n_tiles, splits);
-    g->ws_bytes = splits > 1 ? (int64_t)m_tiles * n_tiles * splits * BM * bn * 4 + (int64_t)m_tiles * n_tiles * 4 + 256 : 0;
+    // short K per CTA: the fixed prologue/epilogue cost dominates -> shallow pipeline so that 2 CTAs share an SM and
+    // one CTA's epilogue overlaps the other's main loop
+    g->co_resident = p.kb_per_split <= 12;
+    g->ws_bytes = splits > 1 ? (int64_t)splits * p.M * d->N * 4 + 256 : 0;
     *handle = g;
     return SDK_OK;
 }
 
 extern "C" int64_t sdk_tc_gemm_workspace_bytes(void* handle) { return handle ? ((TcGemm*)handle)->ws_bytes : 0; }
 
-// workspace layout: [counters (tiles u32, 256-aligned)] [partials]; must have been zeroed once.
+// workspace: fp32 split-K partials [splits][M][N]; may be shared by all GEMMs launched on one stream.
 extern "C" int sdk_tc_gemm_set_workspace(void* handle, void* ws) {
     SDK_CHECK_ARG(handle, "sdk_tc_gemm_set_workspace: null handle");
     TcGemm* g = (TcGemm*)handle;
     if (g->prm.splits > 1) {
-        SDK_CHECK_ARG(ws, "sdk_tc_gemm_set_workspace: split-K GEMM needs a workspace");
-        const size_t tiles = (size_t)g->grid.x * g->grid.y;
-        g->prm.counters = (unsigned int*)ws;
-        g->prm.partial = (float*)((char*)ws + ((tiles * 4 + 255) / 256) * 256);
+        SDK_CHECK_ARG(ws && ((uintptr_t)ws & 15) == 0, "sdk_tc_gemm_set_workspace: split-K GEMM needs a 16-byte aligned workspace");
+        g->prm.partial = (float*)ws;
     }
     return SDK_OK;
 }
@@ -469,6 +558,15 @@ extern "C" int sdk_tc_gemm_launch(void* handle, void* stream) {
     TcGemm* g = (TcGemm*)handle;
     SDK_CHECK_ARG(g->prm.splits == 1 || g->prm.partial, "sdk_tc_gemm_launch: workspace not set for split-K");
     cudaStream_t s = (cudaStream_t)stream;
+    if (g->co_resident) {
+        switch (g->block_n) {
+            case 32: return launch_cfg<32, 4>(g, s);
+            case 64: return launch_cfg<64, 4>(g, s);
+            case 128: return launch_cfg<128, 3>(g, s);
+            case 160: return launch_cfg<160, 3>(g, s);
+            case 256: return launch_cfg<256, 2>(g, s);
+        }
+    }
     switch (g->block_n) {
         case 32: return launch_cfg<32, 8>(g, s);
         case 64: return launch_cfg<64, 8>(g, s);

@@ -56,8 +56,15 @@ class PackedWeights:
         sd = {k: v.detach() for k, v in net.named_parameters()}
         t: Dict[str, torch.Tensor] = {}
 
+        kmajor = precision != "fp32"
+
         def dev(x, dt=torch.float32):
-            return x.to(device=device, dtype=dt).contiguous()
+            x = x.to(device=device, dtype=dt)
+            if kmajor and dt == torch.bfloat16 and x.dim() == 2 and x.shape[1] % 64 == 0:
+                # tensor-core operand: k-block-major [K/64][N][64] -> every B stage is one contiguous run of HBM
+                n, k = x.shape
+                x = x.view(n, k // 64, 64).permute(1, 0, 2)
+            return x.contiguous()
 
         def conv_w(name, dt=wdt):
             w = sd[name]                                  # [N, Cin, kh, kw]
@@ -66,7 +73,7 @@ class PackedWeights:
         for k in ("time_embedding.ffn.0.weight", "time_embedding.ffn.0.bias",
                   "time_embedding.ffn.2.weight", "time_embedding.ffn.2.bias"):
             t[k] = dev(sd[k])
-        t["tb.w"] = dev(torch.cat([sd[f"{r.prefix}.t_embed.weight"] for r in a.res_blocks], 0), wdt)
+        t["tb.w"] = torch.cat([sd[f"{r.prefix}.t_embed.weight"] for r in a.res_blocks], 0).to(device=device, dtype=wdt).contiguous()
         t["tb.b"] = dev(torch.cat([sd[f"{r.prefix}.t_embed.bias"] for r in a.res_blocks], 0))
         t["conv_in.w"] = conv_w("encoder.conv_in.weight", torch.float32)
         t["conv_in.b"] = dev(sd["encoder.conv_in.bias"])
@@ -219,7 +226,7 @@ class StepProgram:
         d.B, d.H, d.W, d.N = p.B, p.Hin, p.Win, p.N
         d.bias, d.tbias, d.tb_stride, d.residual, d.out = p.bias, p.tbias, p.tb_stride, p.residual, p.out
         d.out_dtype, d.geglu, d.out_nchw = p.out_dtype, p.geglu, p.out_nchw
-        d.block_n, d.splits = self.net.tc_block_n, self.net.tc_splits
+        d.block_n, d.splits, d.w_kmajor = self.net.tc_block_n, self.net.tc_splits, 1
         h = C.c_void_p()
         _lib.check(self.lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
         self.tc_handles.append(h)

@@ -121,8 +121,14 @@ TC_CASES = [
 ]
 
 
+def kmajor(w):
+    n, k = w.shape
+    return w.view(n, k // 64, 64).permute(1, 0, 2).contiguous()
+
+
+@pytest.mark.parametrize("wk", [1, 0], ids=["kmajor", "rowmajor"])
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
-def test_tc_gemm(dev, case):
+def test_tc_gemm(dev, case, wk):
     name, B, H, W, Cc, N, k, tbm, res, geglu, odt, nchw, bn, splits = case
     lib = _lib.lib()
     a = gen((B, H, W, Cc), 11, dev).bfloat16()
@@ -134,7 +140,9 @@ def test_tc_gemm(dev, case):
     odtype = torch.float32 if odt == F32_T else torch.bfloat16
     out = torch.full((B, Nout, H, W) if nchw else (B, H, W, Nout), float("nan"), device=dev, dtype=odtype)
     d = TcGemmDesc()
-    d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = a.data_ptr(), w.data_ptr(), Cc, k, 1
+    wp = kmajor(w) if wk else w
+    d.w_kmajor = wk
+    d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = a.data_ptr(), wp.data_ptr(), Cc, k, 1
     d.B, d.H, d.W, d.N = B, H, W, N
     d.bias = bias.data_ptr()
     d.tbias, d.tb_stride = (tb.data_ptr() if tb is not None else 0), (N if tbm == "per" else 0)
@@ -171,8 +179,10 @@ def test_tc_gemm_two_segments(dev):
     bias = gen((N,), 25, dev, 0.1)
     out = torch.empty((B, H, W, N), device=dev)
     d = TcGemmDesc()
-    d.a[0], d.w[0], d.C[0], d.ksize[0] = a2.data_ptr(), w2.data_ptr(), C2, 3
-    d.a[1], d.w[1], d.C[1], d.ksize[1] = raw.data_ptr(), ws_.data_ptr(), Cs, 1
+    w2k, wsk = kmajor(w2), kmajor(ws_)
+    d.w_kmajor = 1
+    d.a[0], d.w[0], d.C[0], d.ksize[0] = a2.data_ptr(), w2k.data_ptr(), C2, 3
+    d.a[1], d.w[1], d.C[1], d.ksize[1] = raw.data_ptr(), wsk.data_ptr(), Cs, 1
     d.nseg, d.B, d.H, d.W, d.N = 2, B, H, W, N
     d.bias, d.out, d.out_dtype = bias.data_ptr(), out.data_ptr(), F32_T
     h = C.c_void_p()
