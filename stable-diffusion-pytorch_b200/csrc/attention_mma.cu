@@ -38,6 +38,11 @@ __device__ __forceinline__ void mma_bf16(float* c, unsigned a0, unsigned a1, uns
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float fast_exp2(float x) {          // MUFU.EX2, flush-to-zero; exp2(-inf) = 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<unsigned*>(&v);
@@ -150,7 +155,7 @@ attention_bf16_kernel(const __nv_bfloat16* __restrict__ q, long long q_row, long
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
             const float m_new = fmaxf(m_run[r], mx[r]);           // finite: each tile has >= 1 valid key
-            corr[r] = exp2f((m_run[r] - m_new) * scale_log2);
+            corr[r] = fast_exp2((m_run[r] - m_new) * scale_log2);
             m_run[r] = m_new;
             msc[r] = m_new * scale_log2;
         }
@@ -158,10 +163,10 @@ attention_bf16_kernel(const __nv_bfloat16* __restrict__ q, long long q_row, long
         unsigned pa[4][4];                                      // P as bf16 A fragments: 4 k16 steps over 64 keys
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
-            const float p0 = exp2f(s[nb][0] * scale_log2 - msc[0]);
-            const float p1 = exp2f(s[nb][1] * scale_log2 - msc[0]);
-            const float p2 = exp2f(s[nb][2] * scale_log2 - msc[1]);
-            const float p3 = exp2f(s[nb][3] * scale_log2 - msc[1]);
+            const float p0 = fast_exp2(s[nb][0] * scale_log2 - msc[0]);
+            const float p1 = fast_exp2(s[nb][1] * scale_log2 - msc[0]);
+            const float p2 = fast_exp2(s[nb][2] * scale_log2 - msc[1]);
+            const float p3 = fast_exp2(s[nb][3] * scale_log2 - msc[1]);
             ps[0] += p0 + p1; ps[1] += p2 + p3;
             pa[nb >> 1][(nb & 1) * 2] = pack_bf16(p0, p1);
             pa[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16(p2, p3);

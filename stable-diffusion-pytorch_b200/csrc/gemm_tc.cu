@@ -452,9 +452,10 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     p.M = (long long)d->B * d->H * d->W;
     p.w_kmajor = d->w_kmajor;
     // ---- N tile and split-K: pick the (block_n, splits) pair with the lowest modelled time.
-    // Model (SM clocks): a CTA's k-block is bound by the L2->smem feed of its A (16 KiB) + B (block_n*128 B)
-    // stage at ~42 B/clk/SM when all SMs pull (LTS cap ~6300 B/clk), by the MMA issue (2*block_n clk), and the
-    // whole launch by streaming the weights from HBM once; split-K adds the partial round trip.
+    // Model (SM clocks), constants measured on B200 (profiles/): a CTA's k-block is bound by the L2->smem feed of
+    // its A (16 KiB) + B (block_n*128 B) stage at ~46 B/clk per SM (chip-wide LTS cap ~6300 B/clk), by the MMA
+    // issue (2*block_n clk), and the whole launch by streaming the weights from HBM once; split-K adds the
+    // partial round trip through the second (reduce) kernel.
     const int sms = sdk_num_sms();
     int bn = d->block_n, splits = d->splits;
     {
@@ -478,7 +479,7 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
                 const long long ctas = (long long)tiles * real_sp;
                 const long long waves = (ctas + sms - 1) / sms;
                 const double active = (double)(ctas < sms ? ctas : sms);
-                double feed = 6300.0 / active; if (feed > 110.0) feed = 110.0;      // B/clk per SM
+                double feed = 6300.0 / active; if (feed > 46.0) feed = 46.0;        // B/clk per SM
                 const double stage_bytes = 16384.0 + c * 128.0;
                 double t_kb = stage_bytes / feed;
                 if (t_kb < 2.0 * c) t_kb = 2.0 * c;
@@ -487,7 +488,7 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
                 const double w_bytes = (double)p.total_kb * 64.0 * d->N * 2.0;
                 const double t_hbm = w_bytes / 3400.0 * 1.0;                         // ~6.5 TB/s at ~1.9 GHz = 3400 B/clk
                 if (t < t_hbm) t = t_hbm;
-                if (real_sp > 1) t += 4000.0 + (double)real_sp * p.M * d->N * 8.0 / 2500.0;
+                if (real_sp > 1) t += 9000.0 + (double)real_sp * p.M * d->N * 8.0 / 2500.0;
                 if (t < best) { best = t; best_bn = c; best_sp = real_sp; }
                 if (d->splits) break;
             }

@@ -18,14 +18,16 @@ constexpr int GROUPS = 32;
 constexpr int GN_THREADS = 256;
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm statistics.  grid = (chunks, B).  Thread t owns channel quads {t, t+256, ...}; for each
-// quad it walks the chunk's pixels (coalesced across the CTA), keeping fp32 partial sums per channel
-// which are folded into per-group double sums.  The last CTA of a sample (atomic ticket) adds the
-// per-chunk partials in fixed chunk order -> deterministic mean / rstd.
+// GroupNorm statistics.  grid = (chunks, B), ~2 CTAs per SM over the whole batch.  A CTA owns a run of
+// pixels; its 256 threads are laid out as (pixel lanes) x (channel quads) so that a warp reads
+// consecutive 16-byte quads of one pixel row (coalesced) and each thread keeps 4-deep loads in flight.
+// Per-thread fp32 partials (a few dozen values each) go to shared memory; one thread per group folds
+// them in a fixed order in double; the last CTA of a sample (atomic ticket) folds the per-chunk
+// partials in chunk order -> deterministic mean / rstd with no fp32 cancellation issue.
 // ---------------------------------------------------------------------------------------------
 struct GNStatsArgs {
     const float* src0; const float* src1;
-    int C0, C1, HW, chunks, pix_per_chunk;
+    int C0, C1, HW, chunks, pix_per_chunk, px_lanes, q_iters;
     double* partial;        // [B][chunks][GROUPS][2]
     unsigned int* ticket;   // [B], zero on entry, self-resetting
     float* stats;           // [B][GROUPS][2] = mean, rstd
@@ -34,60 +36,92 @@ struct GNStatsArgs {
 
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(GNStatsArgs a) {
-    __shared__ double s_sum[GROUPS], s_sq[GROUPS];
+    extern __shared__ float s_part[];            // [nq][px_lanes][8] : 4 sums + 4 sums of squares per (quad, pixel lane)
     __shared__ bool s_last;
     const int b = blockIdx.y, chunk = blockIdx.x;
-    const int C = a.C0 + a.C1, cpg = C / GROUPS;
-    if (threadIdx.x < GROUPS) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
-    __syncthreads();
+    const int C = a.C0 + a.C1, cpg = C / GROUPS, nq = C >> 2;
     const int p0 = chunk * a.pix_per_chunk;
     const int p1 = min(a.HW, p0 + a.pix_per_chunk);
-    const int nquads = C >> 2;
-    for (int q = threadIdx.x; q < nquads; q += GN_THREADS) {
-        const int c = q << 2;
-        const float* base; int cs, cl;
-        if (c < a.C0) { base = a.src0; cs = a.C0; cl = c; } else { base = a.src1; cs = a.C1; cl = c - a.C0; }
-        const float* p = base + ((size_t)b * a.HW + p0) * cs + cl;
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-        double ds[4] = {0, 0, 0, 0}, dss[4] = {0, 0, 0, 0};
-        int cnt = 0;
-        for (int pix = p0; pix < p1; ++pix, p += cs) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p));
-            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-            ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
-            if (++cnt == 32) {            // bound fp32 accumulation length, then promote
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dss[j] += ss[j]; s[j] = 0.f; ss[j] = 0.f; }
-                cnt = 0;
+    const int qlanes = GN_THREADS / a.px_lanes;          // threads along the channel-quad axis
+    const int pl = threadIdx.x / qlanes, ql = threadIdx.x - pl * qlanes;
+    if (pl < a.px_lanes) {
+        for (int it = 0; it < a.q_iters; ++it) {
+            const int q = ql + it * qlanes;
+            if (q >= nq) break;
+            const int c = q << 2;
+            const float* base; int cs, cl;
+            if (c < a.C0) { base = a.src0; cs = a.C0; cl = c; } else { base = a.src1; cs = a.C1; cl = c - a.C0; }
+            const float* p = base + ((size_t)b * a.HW) * cs + cl;
+            float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+            int pix = p0 + pl;
+            const int stride = a.px_lanes;
+            for (; pix + 3 * stride < p1; pix += 4 * stride) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + (size_t)pix * cs));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + stride) * cs));
+                const float4 v2 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + 2 * stride) * cs));
+                const float4 v3 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + 3 * stride) * cs));
+                s[0] += (v0.x + v1.x) + (v2.x + v3.x); s[1] += (v0.y + v1.y) + (v2.y + v3.y);
+                s[2] += (v0.z + v1.z) + (v2.z + v3.z); s[3] += (v0.w + v1.w) + (v2.w + v3.w);
+                ss[0] += (v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x);
+                ss[1] += (v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y);
+                ss[2] += (v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z);
+                ss[3] += (v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w);
             }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            ds[j] += s[j]; dss[j] += ss[j];
-            const int g = (c + j) / cpg;
-            atomicAdd(&s_sum[g], ds[j]);
-            atomicAdd(&s_sq[g], dss[j]);
+            for (; pix < p1; pix += stride) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)pix * cs));
+                s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+                ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+            }
+            float* dst = s_part + ((size_t)q * a.px_lanes + pl) * 8;
+            *reinterpret_cast<float4*>(dst) = make_float4(s[0], s[1], s[2], s[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(ss[0], ss[1], ss[2], ss[3]);
         }
     }
     __syncthreads();
     double* part = a.partial + ((size_t)b * a.chunks + chunk) * GROUPS * 2;
-    if (threadIdx.x < GROUPS) { part[threadIdx.x * 2] = s_sum[threadIdx.x]; part[threadIdx.x * 2 + 1] = s_sq[threadIdx.x]; }
+    if (threadIdx.x < GROUPS) {
+        const int g = threadIdx.x;
+        double sum = 0.0, sq = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const float* src = s_part + (size_t)(c >> 2) * a.px_lanes * 8 + (c & 3);
+            for (int l = 0; l < a.px_lanes; ++l) { sum += (double)src[l * 8]; sq += (double)src[l * 8 + 4]; }
+        }
+        part[g * 2] = sum; part[g * 2 + 1] = sq;
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&a.ticket[b], 1u) == (unsigned)a.chunks - 1u);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x < GROUPS) {
+    {
+        // last CTA of the sample: 8 slices x 32 groups fold the per-chunk partials (fixed assignment and order)
+        __shared__ double s_red[8][GROUPS][2];
+        const int g = threadIdx.x & 31, sl = threadIdx.x >> 5;
+        const double* pp = a.partial + (size_t)b * a.chunks * GROUPS * 2 + g * 2;
         double sum = 0.0, sq = 0.0;
-        const double* pp = a.partial + (size_t)b * a.chunks * GROUPS * 2 + threadIdx.x * 2;
-        for (int k = 0; k < a.chunks; ++k) { sum += __ldcg(pp + (size_t)k * GROUPS * 2); sq += __ldcg(pp + (size_t)k * GROUPS * 2 + 1); }
-        const double n = (double)cpg * (double)a.HW;
-        const double mean = sum / n;
-        double var = sq / n - mean * mean;      // biased variance (nn.GroupNorm)
-        if (var < 0.0) var = 0.0;
-        a.stats[((size_t)b * GROUPS + threadIdx.x) * 2] = (float)mean;
-        a.stats[((size_t)b * GROUPS + threadIdx.x) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
+        int k = sl;
+        for (; k + 24 < a.chunks; k += 32) {
+            const double a0 = __ldcg(pp + (size_t)k * GROUPS * 2), b0 = __ldcg(pp + (size_t)k * GROUPS * 2 + 1);
+            const double a1 = __ldcg(pp + (size_t)(k + 8) * GROUPS * 2), b1 = __ldcg(pp + (size_t)(k + 8) * GROUPS * 2 + 1);
+            const double a2 = __ldcg(pp + (size_t)(k + 16) * GROUPS * 2), b2 = __ldcg(pp + (size_t)(k + 16) * GROUPS * 2 + 1);
+            const double a3 = __ldcg(pp + (size_t)(k + 24) * GROUPS * 2), b3 = __ldcg(pp + (size_t)(k + 24) * GROUPS * 2 + 1);
+            sum = (((sum + a0) + a1) + a2) + a3; sq = (((sq + b0) + b1) + b2) + b3;
+        }
+        for (; k < a.chunks; k += 8) { sum += __ldcg(pp + (size_t)k * GROUPS * 2); sq += __ldcg(pp + (size_t)k * GROUPS * 2 + 1); }
+        s_red[sl][g][0] = sum; s_red[sl][g][1] = sq;
+        __syncthreads();
+        if (threadIdx.x < GROUPS) {
+            sum = 0.0; sq = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sum += s_red[i][g][0]; sq += s_red[i][g][1]; }
+            const double n = (double)cpg * (double)a.HW;
+            const double mean = sum / n;
+            double var = sq / n - mean * mean;      // biased variance (nn.GroupNorm)
+            if (var < 0.0) var = 0.0;
+            a.stats[((size_t)b * GROUPS + g) * 2] = (float)mean;
+            a.stats[((size_t)b * GROUPS + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
+        }
     }
     if (threadIdx.x == 0) a.ticket[b] = 0u;
 }
@@ -223,9 +257,11 @@ inline int grid_for(long long items, int threads) {
 
 }  // namespace
 
+constexpr int GN_MAX_CHUNKS = 512;
+
 extern "C" int64_t sdk_groupnorm_workspace_bytes(int B, int HW) {
-    // partial sums [B][chunks<=64][32][2] doubles + tickets [B]
-    return (int64_t)B * 64 * GROUPS * 2 * sizeof(double) + (int64_t)B * sizeof(unsigned int) + 256;
+    // tickets [B] (256-byte aligned) + partial sums [B][chunks <= 512][32][2] doubles
+    return (((int64_t)B * sizeof(unsigned int) + 255) / 256) * 256 + (int64_t)B * GN_MAX_CHUNKS * GROUPS * 2 * sizeof(double);
 }
 
 // stats [B][32][2] fp32 (mean, rstd).  workspace must be zero-initialised ONCE (tickets self-reset).
@@ -236,18 +272,28 @@ extern "C" int sdk_groupnorm_stats(const float* src0, int C0, const float* src1,
     SDK_CHECK_ARG(C0 > 0 && C1 >= 0 && (C1 == 0 || src1), "sdk_groupnorm_stats: bad sources");
     SDK_CHECK_ARG(C % GROUPS == 0 && C0 % 4 == 0 && C1 % 4 == 0, "sdk_groupnorm_stats: C=%d+%d must be a multiple of 32 (quads of 4)", C0, C1);
     SDK_CHECK_ARG(B > 0 && B < 65536 && HW > 0, "sdk_groupnorm_stats: bad B/HW");
+    const int nq = C / 4;
+    SDK_CHECK_ARG(nq * 32 <= 48 * 1024 / 1 && nq <= 4096, "sdk_groupnorm_stats: C too large");
     int chunks = (sdk_num_sms() * 2 + B - 1) / B;      // ~2 CTAs per SM over the whole batch
-    if (chunks > 64) chunks = 64;
+    if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
     if (chunks > HW) chunks = HW;
     if (chunks < 1) chunks = 1;
     const int ppc = (HW + chunks - 1) / chunks;
     chunks = (HW + ppc - 1) / ppc;
+    // thread layout: as many pixel lanes as fit beside the quad axis (never more than the chunk has pixels)
+    int px_lanes = GN_THREADS / (nq < GN_THREADS ? nq : GN_THREADS);
+    if (px_lanes > ppc) px_lanes = ppc;
+    if (px_lanes < 1) px_lanes = 1;
+    const int qlanes = GN_THREADS / px_lanes;
     GNStatsArgs a;
     a.src0 = src0; a.src1 = src1; a.C0 = C0; a.C1 = C1; a.HW = HW; a.chunks = chunks; a.pix_per_chunk = ppc;
+    a.px_lanes = px_lanes; a.q_iters = (nq + qlanes - 1) / qlanes;
     a.ticket = reinterpret_cast<unsigned int*>(workspace);
     a.partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + (((size_t)B * sizeof(unsigned int) + 255) / 256) * 256);
     a.stats = stats; a.eps = eps;
-    gn_stats_kernel<<<dim3(chunks, B), GN_THREADS, 0, (cudaStream_t)stream>>>(a);
+    const size_t smem = (size_t)nq * px_lanes * 8 * sizeof(float);
+    SDK_CHECK_ARG(smem <= 48 * 1024, "sdk_groupnorm_stats: shared memory %zu too large", smem);
+    gn_stats_kernel<<<dim3(chunks, B), GN_THREADS, smem, (cudaStream_t)stream>>>(a);
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
