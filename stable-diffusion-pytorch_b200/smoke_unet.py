@@ -1,0 +1,32 @@
+"""smoke(): one small UNet step on cuda:0 (both precision modes) checked against the oracle."""
+import numpy as np
+import torch
+
+
+def run():
+    from oracle import unet_oracle as UO                       # checker only
+    from stable_diffusion_pytorch_b200 import DDIMSampler, UNet
+    from stable_diffusion_pytorch_b200.pipeline import DenoiseLoop
+
+    dev = torch.device("cuda:0")
+    sd = UO.make_state_dict(0, **UO.SD15)
+    lat, ctx = UO.synthetic_inputs(1, 8, 8, 768, seed=3)
+    t = torch.tensor([981])
+    with torch.no_grad():
+        want = UO.unet_forward(sd, lat.repeat(2, 1, 1, 1), t, ctx, **UO.SD15).numpy()
+    net = UNet()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    for precision, tol in (("fp32", 1e-4), ("bf16", 1e-2)):
+        net.set_precision(precision)
+        with torch.no_grad():
+            got = net(lat.repeat(2, 1, 1, 1).to(dev), t.to(dev), ctx.to(dev)).cpu().numpy()
+        e = float(np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want))
+        assert e < tol, f"UNet {precision} forward rel-L2 {e:.3e} vs oracle"
+        print(f"smoke: UNet forward ({precision}) on cuda:0 rel-L2 {e:.2e} vs oracle")
+    smp = DDIMSampler()
+    smp._set_inference_steps(10)
+    with torch.no_grad():
+        out = DenoiseLoop(net, smp, 1, 8, 8).run(lat.to(dev), ctx.to(dev), steps=2)
+    assert torch.isfinite(out).all()
+    print("smoke: 2 graph-replayed DDIM steps (tcgen05 GEMMs + flash attention + fused CFG/DDIM) finite")

@@ -1,0 +1,69 @@
+"""CPU suite, part 3: the C-ABI boundary.  The built library must load and export every symbol that
+include/sdb200.h declares, and the ctypes binding table must cover exactly that set (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sdb200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"typedef struct.*?}\s*\w+;", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdk_\w+)\s*\(", src)))
+
+
+def test_header_declares_entry_points():
+    names = declared_functions()
+    for must in ("sdk_ddim_step", "sdk_ddpm_step", "sdk_tc_gemm_launch", "sdk_attention_bf16", "sdk_groupnorm_stats",
+                 "sdk_layernorm", "sdk_conv_gemm_f32", "sdk_last_error"):
+        assert must in names
+    assert len(names) >= 25
+
+
+def test_library_exports_every_declared_symbol():
+    from stable_diffusion_pytorch_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in declared_functions() if not hasattr(h, n)]
+    assert not missing, f"declared in sdb200.h but not exported: {missing}"
+
+
+def test_binding_table_matches_header():
+    from stable_diffusion_pytorch_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_functions()
+    lib = _lib.lib()                       # resolves every symbol with its argtypes
+    assert lib.sdk_version() >= 100
+    assert lib.sdk_last_error() is not None
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors of the two parameter structs have the field order of the header."""
+    from stable_diffusion_pytorch_b200 import _lib
+    src = open(HEADER).read()
+    for cname, mirror in (("SdkConvParams", _lib.ConvParams), ("SdkTcGemmDesc", _lib.TcGemmDesc)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(None, 1)[1] if not decl.startswith("const") else decl.split(None, 2)[2]
+            for n in names.split(","):
+                fields.append(n.replace("*", "").strip().split("[")[0])
+        assert fields == [f[0] for f in mirror._fields_], (cname, fields)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from stable_diffusion_pytorch_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.ExtensionMissing, match="no CPU/PyTorch fallback"):
+        _lib.lib()

@@ -91,3 +91,58 @@ def test_one_step_sd21(golden_dir, dev):
     assert rel_l2(x0.cpu().numpy(), g["onestep_x0"]) < 1e-4
     del net
     torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs at FULL size: golden trajectories from the unmodified reference
+# (tests/golden/make_golden_fullsize.py; 50 DDIM steps, CFG 7.5).
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_config2_sd15_512_ddim50_full(net15, golden_dir, dev, precision, tol):
+    """BASELINE config 2: SD1.5-arch, 64x64 latent, DDIM-50, CFG 7.5, batch 1."""
+    g = np.load(os.path.join(golden_dir, "loop_sd15_full.npz"))
+    net15.set_precision(precision)
+    smp = DDIMSampler()
+    smp._set_inference_steps(50)
+    assert np.array_equal(smp.timesteps.numpy(), g["timesteps"])            # bookkeeping: bit-exact
+    lat, ctx = torch.from_numpy(g["lat"]).to(dev), torch.from_numpy(g["ctx"]).to(dev)
+    loop = DenoiseLoop(net15, smp, 1, 64, 64)
+    with torch.no_grad():
+        loop.reset(lat, ctx)
+        errs = {}
+        for i in range(50):
+            loop.step()
+            if i + 1 in (1, 10, 25, 50):
+                errs[i + 1] = rel_l2(loop.latent.cpu().numpy(), g[f"latent_step{i + 1}"])
+    print(f"config 2 ({precision}) latent rel-L2 after steps 1/10/25/50: " + " ".join(f"{errs[k]:.3e}" for k in (1, 10, 25, 50)))
+    assert errs[50] < tol
+    net15.set_precision("bf16")
+
+
+def test_config4_sd21_768_ddim50_vpred_full(golden_dir, dev):
+    """BASELINE config 4 at batch 1: SD2.1-arch, 96x96 latent, DDIM-50, v-prediction, CFG 7.5."""
+    g = np.load(os.path.join(golden_dir, "loop_sd21_full.npz"))
+    net = UNet(attention_head_dim=[5, 10, 20, 20], cross_attention_dim=1024)
+    net.load_state_dict(UO.make_state_dict(1, **UO.SD21), strict=True)
+    net = net.to(dev).eval()
+    lat, ctx = torch.from_numpy(g["lat"]).to(dev), torch.from_numpy(g["ctx"]).to(dev)
+    res = {}
+    for precision in ("bf16", "fp32"):
+        net.set_precision(precision)
+        smp = DDIMSampler(prediction_type="v_prediction")
+        smp._set_inference_steps(50)
+        loop = DenoiseLoop(net, smp, 1, 96, 96)
+        with torch.no_grad():
+            loop.reset(lat, ctx)
+            for i in range(50):
+                loop.step()
+                if i + 1 in (1, 10, 25, 50):
+                    res[(precision, i + 1)] = rel_l2(loop.latent.cpu().numpy(), g[f"latent_step{i + 1}"])
+        print(f"config 4 ({precision}) latent rel-L2 after steps 1/10/25/50: " + " ".join(f"{res[(precision, k)]:.3e}" for k in (1, 10, 25, 50)))
+        del loop
+        net.invalidate()
+        torch.cuda.empty_cache()
+    assert res[("fp32", 50)] < 1e-4
+    assert res[("bf16", 50)] < 1e-2
+    del net
+    torch.cuda.empty_cache()
