@@ -33,6 +33,8 @@ const char* sdk_last_error(void);
 int sdk_version(void);
 /* out[0]=SM count, out[1..2]=compute capability, out[3]=max opt-in shared memory per block */
 int sdk_device_info(int* out, int n);
+/* programmatic dependent launch for all kernels (1 = on; default off): kernel N+1's prologue overlaps kernel N's tail */
+int sdk_set_pdl(int enabled);
 
 /* ---- sampler: fused CFG blend + scheduler update (models/diffusion.py:233-236) ------------------
  * coef_table: [T][8] fp32 per-timestep scalars built by the host sampler; the timestep is read from

@@ -56,6 +56,7 @@ SIGNATURES = {
     "sdk_im2col_s2": [P, P, I32, I32, I32, I32, P],
     # --- misc
     "sdk_device_info": [P, I32],
+    "sdk_set_pdl": [I32],
 }
 
 
@@ -102,6 +103,7 @@ def lib():
                 fn = getattr(h, name)          # AttributeError here == header/library drift
                 fn.argtypes = argtypes
                 fn.restype = RESTYPES.get(name, C.c_int)
+            h.sdk_set_pdl(1 if os.environ.get("SDB200_PDL", "0") == "1" else 0)
             _lib = h
     return _lib
 

@@ -55,6 +55,8 @@ attention_bf16_kernel(const __nv_bfloat16* __restrict__ q, long long q_row, long
                       const __nv_bfloat16* __restrict__ v, long long v_row, long long v_batch,
                       __nv_bfloat16* __restrict__ out, long long o_row, long long o_batch,
                       int heads, int Sq, int Sk, float scale_log2) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int DP = (D + 15) / 16 * 16;          // QK^T reduction length (zero padded)
     constexpr int LD = DP + 8;                      // smem row pitch in elements (+16 B: conflict-free ldmatrix)
     constexpr int KSTEPS = DP / 16;                 // k16 steps of QK^T
@@ -224,8 +226,8 @@ int launch(const __nv_bfloat16* q, long long q_row, long long q_batch, const __n
         configured = true;
     }
     dim3 grid((Sq + BQ - 1) / BQ, B * heads);
-    attention_bf16_kernel<D><<<grid, THREADS, smem, s>>>(q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch, out, o_row, o_batch,
-                                                         heads, Sq, Sk, scale * 1.4426950408889634f);
+    SDK_CUDA(sdk_launch(attention_bf16_kernel<D>, dim3(grid), dim3(THREADS), (size_t)(smem), s, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch, out, o_row, o_batch,
+                                                         heads, Sq, Sk, scale * 1.4426950408889634f));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }

@@ -17,6 +17,8 @@ attention_f32_kernel(const float* __restrict__ q, long long q_row, long long q_b
                      const float* __restrict__ v, long long v_row, long long v_batch,
                      float* __restrict__ out, long long o_row, long long o_batch,
                      int heads, int Sq, int Sk, float scale) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int DQ = D / 4;                    // output columns per thread
     extern __shared__ float smem[];
     float (*Qs)[D + 1] = reinterpret_cast<float (*)[D + 1]>(smem);
@@ -108,8 +110,8 @@ int launch(const float* q, long long q_row, long long q_batch, const float* k, l
         configured = true;
     }
     dim3 grid((Sq + BQ - 1) / BQ, B * heads);
-    attention_f32_kernel<D><<<grid, THREADS, smem, s>>>(q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch,
-                                                        out, o_row, o_batch, heads, Sq, Sk, scale);
+    SDK_CUDA(sdk_launch(attention_f32_kernel<D>, dim3(grid), dim3(THREADS), (size_t)(smem), s, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch,
+                                                        out, o_row, o_batch, heads, Sq, Sk, scale));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }

@@ -13,6 +13,11 @@ int sdk_fail(int code, const char* fmt, ...) {
     return code;
 }
 
+static int g_pdl = 0;   // measured on B200 inside CUDA graphs: -3.5 % with early triggers -> off by default
+bool sdk_pdl_enabled() { return g_pdl != 0; }
+// enable (1) / disable (0, default) programmatic dependent launch for all subsequent launches
+extern "C" int sdk_set_pdl(int enabled) { g_pdl = enabled ? 1 : 0; return SDK_OK; }
+
 extern "C" const char* sdk_last_error() { return g_err; }
 extern "C" int sdk_version() { return 100; }
 

@@ -59,6 +59,27 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// ---- programmatic dependent launch (PDL): every kernel of the step program is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, calls pdl_trigger() first (lets the NEXT kernel's
+// CTAs be scheduled as soon as this grid has fully started) and pdl_wait() before its first access to global
+// memory (blocks until the PREVIOUS grid has completed and flushed).  Prologues (smem carve-up, mbarrier
+// init, TMEM alloc, descriptor prefetch) and launch latency of kernel N+1 thereby overlap kernel N's tail.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool sdk_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t sdk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = sdk_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // dtype codes used across the C ABI
 #define SDK_F32 0
 #define SDK_BF16 1

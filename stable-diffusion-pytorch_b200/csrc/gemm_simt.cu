@@ -63,6 +63,8 @@ __device__ __forceinline__ float4 load_b_quad(const float* __restrict__ w, int n
 
 __global__ void __launch_bounds__(THREADS)
 conv_gemm_f32_kernel(const SdkConvParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float As[2][BK][BM + PADM];
     __shared__ __align__(16) float Bs[2][BK][BN + PADM];
 
@@ -205,7 +207,7 @@ extern "C" int sdk_conv_gemm_f32(const SdkConvParams* p, void* stream) {
     const int M = p->B * p->Hout * p->Wout;
     dim3 grid((M + BM - 1) / BM, (p->N + BN - 1) / BN);
     SDK_CHECK_ARG(grid.y < 65536, "sdk_conv_gemm_f32: N too large");
-    conv_gemm_f32_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(*p);
+    SDK_CUDA(sdk_launch(conv_gemm_f32_kernel, dim3(grid), dim3(THREADS), (size_t)(0), (cudaStream_t)stream, *p));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }

@@ -130,6 +130,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, (STAGES <= 3 || (BN <= 64 && STAGES <= 4)) ? 2 : 1)
 conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
+    pdl_trigger();
     constexpr int B_STAGE_BYTES = BN * BK * 2;
     constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM, BN);
@@ -172,6 +173,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -270,6 +272,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
 // order (deterministic) and run the epilogue.
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const __grid_constant__ TcParams p) {
+    pdl_trigger();
+    pdl_wait();
     const int N = p.N, quads = (N + 3) >> 2;
     const long long total = p.M * quads;
     const size_t plane = (size_t)p.M * N;
@@ -391,13 +395,13 @@ int launch_cfg(const TcGemm* g, cudaStream_t s) {
         SDK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    conv_gemm_tc_kernel<BN, STAGES><<<g->grid, TC_THREADS, smem, s>>>(g->prm);
+    SDK_CUDA(sdk_launch(conv_gemm_tc_kernel<BN, STAGES>, dim3(g->grid), dim3(TC_THREADS), (size_t)(smem), s, g->prm));
     SDK_LAUNCH_CHECK();
     if (g->prm.splits > 1) {
         const long long items = g->prm.M * ((g->prm.N + 3) / 4);
         long long blocks = (items + 255) / 256, cap = (long long)sdk_num_sms() * 8;
         if (blocks > cap) blocks = cap;
-        splitk_reduce_kernel<<<(int)blocks, 256, 0, s>>>(g->prm);
+        SDK_CUDA(sdk_launch(splitk_reduce_kernel, dim3((int)blocks), dim3(256), (size_t)(0), s, g->prm));
         SDK_LAUNCH_CHECK();
     }
     return SDK_OK;
@@ -587,6 +591,8 @@ extern "C" int sdk_tc_gemm_destroy(void* handle) {
 namespace {
 __global__ void __launch_bounds__(256)
 im2col_s2_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C, int Ho, int Wo) {
+    pdl_trigger();
+    pdl_wait();
     const int nq = C >> 2;
     const long long total = (long long)B * Ho * Wo * 9 * nq;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -612,7 +618,7 @@ extern "C" int sdk_im2col_s2(const float* src, void* dst, int B, int H, int W, i
     const long long total = (long long)B * Ho * Wo * 9 * (C / 4);
     long long blocks = (total + 255) / 256, cap = (long long)sdk_num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    im2col_s2_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, B, H, W, C, Ho, Wo);
+    SDK_CUDA(sdk_launch(im2col_s2_kernel, dim3((int)blocks), dim3(256), (size_t)(0), (cudaStream_t)stream, src, (__nv_bfloat16*)dst, B, H, W, C, Ho, Wo));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }

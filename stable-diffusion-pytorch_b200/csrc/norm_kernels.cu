@@ -36,6 +36,8 @@ struct GNStatsArgs {
 
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(GNStatsArgs a) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float s_part[];            // [nq][px_lanes][8] : 4 sums + 4 sums of squares per (quad, pixel lane)
     __shared__ bool s_last;
     const int b = blockIdx.y, chunk = blockIdx.x;
@@ -149,6 +151,8 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
 template <typename TOut>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(GNApplyArgs a) {
+    pdl_trigger();
+    pdl_wait();
     const int C = a.C0 + a.C1, cpg = C / GROUPS, nquads = C >> 2;
     const long long total = (long long)a.B * a.HW * nquads;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -181,6 +185,8 @@ template <typename TOut, int MAXQ>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, TOut* __restrict__ out, int C, long long rows) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -223,6 +229,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 template <typename TOut>
 __global__ void __launch_bounds__(256)
 cast_upsample_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int B, int H, int W, int C, int up) {
+    pdl_trigger();
+    pdl_wait();
     const int Ho = H * up, Wo = W * up, nquads = C >> 2;
     const long long total = (long long)B * Ho * Wo * nquads;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -238,6 +246,8 @@ cast_upsample_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int 
 
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B_src, int B_dst, int C, int HW) {
+    pdl_trigger();
+    pdl_wait();
     // dst[b][p][c] = src[b % B_src][c][p]   (b % B_src implements latent.repeat(2,1,1,1), diffusion.py:228)
     const long long total = (long long)B_dst * HW * C;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -293,7 +303,7 @@ extern "C" int sdk_groupnorm_stats(const float* src0, int C0, const float* src1,
     a.stats = stats; a.eps = eps;
     const size_t smem = (size_t)nq * px_lanes * 8 * sizeof(float);
     SDK_CHECK_ARG(smem <= 48 * 1024, "sdk_groupnorm_stats: shared memory %zu too large", smem);
-    gn_stats_kernel<<<dim3(chunks, B), GN_THREADS, smem, (cudaStream_t)stream>>>(a);
+    SDK_CUDA(sdk_launch(gn_stats_kernel, dim3(dim3(chunks, B)), dim3(GN_THREADS), (size_t)(smem), (cudaStream_t)stream, a));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
@@ -308,8 +318,8 @@ extern "C" int sdk_groupnorm_apply(const float* src0, int C0, const float* src1,
     a.src0 = src0; a.src1 = src1; a.C0 = C0; a.C1 = C1; a.HW = HW; a.B = B;
     a.stats = stats; a.gamma = gamma; a.beta = beta; a.out = out; a.raw_out = raw_out; a.silu = silu;
     const int grid = grid_for((long long)B * HW * (C / 4), 256);
-    if (out_dtype == SDK_F32) gn_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
-    else if (out_dtype == SDK_BF16) gn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    if (out_dtype == SDK_F32) SDK_CUDA(sdk_launch(gn_apply_kernel<float>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, a));
+    else if (out_dtype == SDK_BF16) SDK_CUDA(sdk_launch(gn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, a));
     else return sdk_fail(SDK_ERR_ARG, "sdk_groupnorm_apply: out_dtype %d", out_dtype);
     SDK_LAUNCH_CHECK();
     return SDK_OK;
@@ -322,7 +332,7 @@ extern "C" int sdk_layernorm(const float* x, const float* gamma, const float* be
     if (rows <= 0) return SDK_OK;
     const int grid = grid_for(rows * 32, 256);
     cudaStream_t s = (cudaStream_t)stream;
-#define LN_LAUNCH(T, MAXQ) layernorm_kernel<T, MAXQ><<<grid, 256, 0, s>>>(x, gamma, beta, eps, reinterpret_cast<T*>(out), C, rows)
+#define LN_LAUNCH(T, MAXQ) SDK_CUDA(sdk_launch(layernorm_kernel<T, MAXQ>, dim3(grid), dim3(256), 0, s, x, gamma, beta, eps, reinterpret_cast<T*>(out), C, rows))
     const int nq = (C / 4 + 31) / 32;
     if (out_dtype == SDK_F32) {
         if (nq <= 3) LN_LAUNCH(float, 3); else if (nq <= 5) LN_LAUNCH(float, 5); else if (nq <= 10) LN_LAUNCH(float, 10); else LN_LAUNCH(float, 16);
@@ -339,8 +349,8 @@ extern "C" int sdk_cast_upsample(const float* src, void* dst, int out_dtype, int
     const long long total = (long long)B * H * up * W * up * (C / 4);
     if (total <= 0) return SDK_OK;
     const int grid = grid_for(total, 256);
-    if (out_dtype == SDK_F32) cast_upsample_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(src, (float*)dst, B, H, W, C, up);
-    else if (out_dtype == SDK_BF16) cast_upsample_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, B, H, W, C, up);
+    if (out_dtype == SDK_F32) SDK_CUDA(sdk_launch(cast_upsample_kernel<float>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, src, (float*)dst, B, H, W, C, up));
+    else if (out_dtype == SDK_BF16) SDK_CUDA(sdk_launch(cast_upsample_kernel<__nv_bfloat16>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, src, (__nv_bfloat16*)dst, B, H, W, C, up));
     else return sdk_fail(SDK_ERR_ARG, "sdk_cast_upsample: out_dtype %d", out_dtype);
     SDK_LAUNCH_CHECK();
     return SDK_OK;
@@ -348,7 +358,7 @@ extern "C" int sdk_cast_upsample(const float* src, void* dst, int out_dtype, int
 
 extern "C" int sdk_nchw_to_nhwc(const float* src, float* dst, int B_src, int B_dst, int C, int HW, void* stream) {
     SDK_CHECK_ARG(src && dst && B_src > 0 && B_dst > 0 && C > 0 && HW > 0, "sdk_nchw_to_nhwc: bad args");
-    nchw_to_nhwc_kernel<<<grid_for((long long)B_dst * HW * C, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, B_src, B_dst, C, HW);
+    SDK_CUDA(sdk_launch(nchw_to_nhwc_kernel, dim3(grid_for((long long)B_dst * HW * C, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, src, dst, B_src, B_dst, C, HW));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }

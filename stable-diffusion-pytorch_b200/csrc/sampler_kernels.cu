@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(256)
 step_kernel(const float* x, const float* __restrict__ eu, const float* __restrict__ ec, float scale,
             const float* __restrict__ noise, float* out, long long n,      // x and out may alias (in-place latent state)
             const float* __restrict__ table, int T, const long long* __restrict__ t_dev, long long t_host, int vec_ok) {
+    pdl_trigger();
+    pdl_wait();
     Coef k;
     const bool ok = load_coef(table, T, t_dev, t_host, k);
     const float qnan = __int_as_float(0x7fc00000);
@@ -105,6 +107,8 @@ step_kernel(const float* x, const float* __restrict__ eu, const float* __restric
 __global__ void __launch_bounds__(256)
 forward_process_kernel(const float* __restrict__ x0, const float* __restrict__ noise, float* __restrict__ out,
                        long long per_sample, const float* __restrict__ table, int T, const long long* __restrict__ t) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
     long long tb = t[b];
     const bool ok = tb >= 0 && tb < T;
@@ -120,6 +124,8 @@ forward_process_kernel(const float* __restrict__ x0, const float* __restrict__ n
 __global__ void __launch_bounds__(256)
 x0_from_eps_kernel(const float* __restrict__ x, const float* __restrict__ e, float sigma, float alpha,
                    float* __restrict__ out, long long n) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(sigma, e[i])), alpha);
 }
@@ -147,9 +153,9 @@ extern "C" int sdk_ddim_step(const float* x, const float* eps_u, const float* ep
     int grid = grid_for((n + 3) / 4, 256);
     cudaStream_t s = (cudaStream_t)stream;
     if (prediction_type == 0)
-        step_kernel<0><<<grid, 256, 0, s>>>(x, eps_u, eps_c, cfg_scale, noise, out, n, coef_table, T, (const long long*)t_dev, t_host, vec_ok);
+        SDK_CUDA(sdk_launch(step_kernel<0>, dim3(grid), dim3(256), (size_t)(0), s, x, eps_u, eps_c, cfg_scale, noise, out, n, coef_table, T, (const long long*)t_dev, t_host, vec_ok));
     else
-        step_kernel<1><<<grid, 256, 0, s>>>(x, eps_u, eps_c, cfg_scale, noise, out, n, coef_table, T, (const long long*)t_dev, t_host, vec_ok);
+        SDK_CUDA(sdk_launch(step_kernel<1>, dim3(grid), dim3(256), (size_t)(0), s, x, eps_u, eps_c, cfg_scale, noise, out, n, coef_table, T, (const long long*)t_dev, t_host, vec_ok));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
@@ -161,8 +167,8 @@ extern "C" int sdk_ddpm_step(const float* x, const float* eps_u, const float* ep
     SDK_CHECK_ARG(n >= 0 && T > 0, "sdk_ddpm_step: bad sizes");
     const int vec_ok = aligned16(x) && aligned16(eps_u) && aligned16(out) && aligned16(noise) && (!eps_c || aligned16(eps_c));
     if (n == 0) return SDK_OK;
-    step_kernel<2><<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-        x, eps_u, eps_c, cfg_scale, noise, out, n, coef_table, T, (const long long*)t_dev, t_host, vec_ok);
+    SDK_CUDA(sdk_launch(step_kernel<2>, dim3(grid_for((n + 3) / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
+        x, eps_u, eps_c, cfg_scale, noise, out, n, coef_table, T, (const long long*)t_dev, t_host, vec_ok));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
@@ -173,7 +179,7 @@ extern "C" int sdk_forward_process(const float* x0, const float* noise, float* o
     SDK_CHECK_ARG(batch >= 0 && batch < 65536 && per_sample >= 0, "sdk_forward_process: bad sizes");
     if (batch == 0 || per_sample == 0) return SDK_OK;
     dim3 grid(grid_for(per_sample, 256), (unsigned)batch);
-    forward_process_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, noise, out, per_sample, coef_table, T, (const long long*)t_dev);
+    SDK_CUDA(sdk_launch(forward_process_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, x0, noise, out, per_sample, coef_table, T, (const long long*)t_dev));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
@@ -181,7 +187,7 @@ extern "C" int sdk_forward_process(const float* x0, const float* noise, float* o
 extern "C" int sdk_x0_from_eps(const float* x, const float* eps, float sigma, float alpha, float* out, int64_t n, void* stream) {
     SDK_CHECK_ARG(x && eps && out, "sdk_x0_from_eps: null pointer");
     if (n <= 0) return SDK_OK;
-    x0_from_eps_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, eps, sigma, alpha, out, n);
+    SDK_CUDA(sdk_launch(x0_from_eps_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, x, eps, sigma, alpha, out, n));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
@@ -191,6 +197,8 @@ extern "C" int sdk_x0_from_eps(const float* x, const float* eps, float sigma, fl
 // work in between: the timestep sequence (host-built, bit-exact) is uploaded once and walked here.
 namespace {
 __global__ void next_timestep_kernel(const long long* __restrict__ table, int n, int* __restrict__ counter, long long* __restrict__ t_out) {
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int i = counter[0];
         t_out[0] = (i >= 0 && i < n) ? table[i] : -1;     // -1 poisons the sampler update (NaN) instead of reading out of range
@@ -201,7 +209,7 @@ __global__ void next_timestep_kernel(const long long* __restrict__ table, int n,
 
 extern "C" int sdk_next_timestep(const int64_t* table, int n, int* counter, int64_t* t_out, void* stream) {
     SDK_CHECK_ARG(table && counter && t_out && n > 0, "sdk_next_timestep: bad args");
-    next_timestep_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const long long*)table, n, counter, (long long*)t_out);
+    SDK_CUDA(sdk_launch(next_timestep_kernel, dim3(1), dim3(32), (size_t)(0), (cudaStream_t)stream, (const long long*)table, n, counter, (long long*)t_out));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }

@@ -9,6 +9,8 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 time_sinusoid_kernel(const long long* __restrict__ t, int n, int dim, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int half = dim >> 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * half) return;
@@ -44,6 +46,8 @@ template <typename TW, int NB>
 __global__ void __launch_bounds__(256)
 gemv_kernel(const TW* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x, float* __restrict__ y,
             int n, int R, int K, int act_in, int act_out) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int V = WVec<TW>::N;
     const int lane = threadIdx.x & 31;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -78,7 +82,7 @@ gemv_kernel(const TW* __restrict__ W, const float* __restrict__ bias, const floa
 extern "C" int sdk_time_sinusoid(const int64_t* t_dev, int n, int dim, float* out, void* stream) {
     SDK_CHECK_ARG(t_dev && out && n > 0 && dim > 0 && dim % 2 == 0, "sdk_time_sinusoid: bad args");
     const int total = n * (dim / 2);
-    time_sinusoid_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const long long*)t_dev, n, dim, out);
+    SDK_CUDA(sdk_launch(time_sinusoid_kernel, dim3((total + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, (const long long*)t_dev, n, dim, out));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
@@ -90,11 +94,11 @@ extern "C" int sdk_gemv(const void* W, int w_dtype, const float* bias, const flo
     const int grid = (R * 32 + 255) / 256;
     cudaStream_t s = (cudaStream_t)stream;
     if (w_dtype == SDK_F32) {
-        if (n == 1) gemv_kernel<float, 1><<<grid, 256, 0, s>>>((const float*)W, bias, x, y, n, R, K, act_in, act_out);
-        else gemv_kernel<float, 4><<<grid, 256, 0, s>>>((const float*)W, bias, x, y, n, R, K, act_in, act_out);
+        if (n == 1) SDK_CUDA(sdk_launch(gemv_kernel<float, 1>, dim3(grid), dim3(256), (size_t)(0), s, (const float*)W, bias, x, y, n, R, K, act_in, act_out));
+        else SDK_CUDA(sdk_launch(gemv_kernel<float, 4>, dim3(grid), dim3(256), (size_t)(0), s, (const float*)W, bias, x, y, n, R, K, act_in, act_out));
     } else if (w_dtype == SDK_BF16) {
-        if (n == 1) gemv_kernel<__nv_bfloat16, 1><<<grid, 256, 0, s>>>((const __nv_bfloat16*)W, bias, x, y, n, R, K, act_in, act_out);
-        else gemv_kernel<__nv_bfloat16, 4><<<grid, 256, 0, s>>>((const __nv_bfloat16*)W, bias, x, y, n, R, K, act_in, act_out);
+        if (n == 1) SDK_CUDA(sdk_launch(gemv_kernel<__nv_bfloat16, 1>, dim3(grid), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)W, bias, x, y, n, R, K, act_in, act_out));
+        else SDK_CUDA(sdk_launch(gemv_kernel<__nv_bfloat16, 4>, dim3(grid), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)W, bias, x, y, n, R, K, act_in, act_out));
     } else return sdk_fail(SDK_ERR_ARG, "sdk_gemv: w_dtype %d", w_dtype);
     SDK_LAUNCH_CHECK();
     return SDK_OK;

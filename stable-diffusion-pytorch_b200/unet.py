@@ -85,6 +85,7 @@ class PackedWeights:
                 t[f"{p}.{n}.w"], t[f"{p}.{n}.b"] = conv_w(f"{p}.{n}.weight"), dev(sd[f"{p}.{n}.bias"])
             if r.has_proj:
                 t[f"{p}.proj.w"], t[f"{p}.proj.b"] = conv_w(f"{p}.proj_input.weight"), dev(sd[f"{p}.proj_input.bias"])
+                t[f"{p}.conv2_proj.b"] = dev(sd[f"{p}.conv_2.bias"].float() + sd[f"{p}.proj_input.bias"].float())
         for tr in a.transformers:
             p, b, c = tr.prefix, f"{tr.prefix}.transformer_block", tr.c
             t[f"{p}.gn.g"], t[f"{p}.gn.b"] = dev(sd[f"{p}.groupnorm.weight"]), dev(sd[f"{p}.groupnorm.bias"])
@@ -187,7 +188,7 @@ class StepProgram:
 
     def _conv(self, srcs, w, bias, B, Hin, Win, N, *, k=1, stride=1, up=False, tbias=0, tb_stride=0,
               residual=None, geglu=False, out_code=F32_T, out=None, out_nchw=False, in_code=None, ctx=False,
-              force_simt=False):
+              force_simt=False, seg2=None):
         """srcs: [(tensor[rows, C], C)] (1 or 2).  Returns the output tensor [M, N or N/2]."""
         upf = 2 if up else 1
         pad = k // 2
@@ -214,15 +215,17 @@ class StepProgram:
         if p.in_dtype == F32_T or force_simt:
             self._emit(self.lib.sdk_conv_gemm_f32, C.byref(p), ctx=ctx)
         else:
-            self._emit_tc_conv(p, srcs, w, ctx)
+            self._emit_tc_conv(p, srcs, w, ctx, seg2)
         return out, Hout, Wout
 
-    def _emit_tc_conv(self, p, srcs, w, ctx):
+    def _emit_tc_conv(self, p, srcs, w, ctx, seg2=None):
         """tcgen05 implicit GEMM for a stride-1 conv / linear described by ConvParams ``p``."""
         if len(srcs) != 1 or p.stride != 1 or p.upsample:
             raise RuntimeError("tensor-core conv takes one pre-concatenated, pre-upsampled bf16 source at stride 1")
         d = TcGemmDesc()
         d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = p.src0, p.weight, p.C0, p.ksize, 1
+        if seg2 is not None:                                   # (activation [rows, C2] bf16, C2, 1x1 weights)
+            d.a[1], d.C[1], d.w[1], d.ksize[1], d.nseg = seg2[0].data_ptr(), seg2[1], seg2[2].data_ptr(), 1, 2
         d.B, d.H, d.W, d.N = p.B, p.Hin, p.Win, p.N
         d.bias, d.tbias, d.tb_stride, d.residual, d.out = p.bias, p.tbias, p.tb_stride, p.residual, p.out
         d.out_dtype, d.geglu, d.out_nchw = p.out_dtype, p.geglu, p.out_nchw
@@ -276,11 +279,14 @@ class StepProgram:
         if r.has_proj:
             if self.act == F32_T:
                 sc, _, _ = self._conv(srcs, t[f"{p}.proj.w"], t[f"{p}.proj.b"], B, H, W, r.cout, k=1)
+                out, _, _ = self._conv([(a2, r.cout)], t[f"{p}.conv_2.w"], t[f"{p}.conv_2.b"], B, H, W, r.cout, k=3, residual=sc)
+                self.pool.put(sc)
             else:
-                sc, _, _ = self._conv([(raw, r.cin_total)], t[f"{p}.proj.w"], t[f"{p}.proj.b"], B, H, W, r.cout, k=1)
+                # 1x1 shortcut conv (unet.py:192) as a second K segment of conv_2's GEMM: same TMEM accumulator,
+                # no fp32 round trip of the shortcut tensor; bias = conv_2.bias + proj_input.bias (packed)
+                out, _, _ = self._conv([(a2, r.cout)], t[f"{p}.conv_2.w"], t[f"{p}.conv2_proj.b"], B, H, W, r.cout, k=3,
+                                       seg2=(raw, r.cin_total, t[f"{p}.proj.w"]))
                 self.pool.put(raw)
-            out, _, _ = self._conv([(a2, r.cout)], t[f"{p}.conv_2.w"], t[f"{p}.conv_2.b"], B, H, W, r.cout, k=3, residual=sc)
-            self.pool.put(sc)
         else:
             out, _, _ = self._conv([(a2, r.cout)], t[f"{p}.conv_2.w"], t[f"{p}.conv_2.b"], B, H, W, r.cout, k=3,
                                    residual=srcs[0][0])
