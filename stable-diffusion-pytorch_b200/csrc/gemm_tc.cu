@@ -57,14 +57,33 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* v) {
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int n, long long grow, int b, int oy, int ox) {
     const int N = p.N;
     if (n >= N) return;
-    if (p.bias) {
+    if (n + 32 <= N) {
+        // full chunk: 16-byte loads, all issued before the first add (one scoreboard wait instead of 32)
+        if (p.bias) {
+            float4 bv[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(p.bias + n + j);
-    }
-    if (p.tbias) {
-        const float* tb = p.tbias + (long long)b * p.tb_stride + n;
+            for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(tb + j);
+            for (int j = 0; j < 8; ++j) { v[4 * j] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w; }
+        }
+        if (p.tbias) {
+            const float4* tb = reinterpret_cast<const float4*>(p.tbias + (long long)b * p.tb_stride + n);
+            float4 tv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tv[j] = __ldg(tb + j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[4 * j] += tv[j].x; v[4 * j + 1] += tv[j].y; v[4 * j + 2] += tv[j].z; v[4 * j + 3] += tv[j].w; }
+        }
+    } else {
+        if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(p.bias + n + j);
+        }
+        if (p.tbias) {
+            const float* tb = p.tbias + (long long)b * p.tb_stride + n;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(tb + j);
+        }
     }
     if (p.geglu) {
         // (value, gate) column pairs -> 16 outputs   (models/activation_fn.py:17-20)
@@ -101,11 +120,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
     const long long off = grow * N + n;
     if (n + 32 <= N) {
         if (p.residual) {
+            float4 rv[8];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + off + j));
-                v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
-            }
+            for (int j = 0; j < 8; ++j) rv[j] = __ldg(reinterpret_cast<const float4*>(p.residual + off) + j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[4 * j] += rv[j].x; v[4 * j + 1] += rv[j].y; v[4 * j + 2] += rv[j].z; v[4 * j + 3] += rv[j].w; }
         }
         if (p.out_dtype == SDK_BF16) {
 #pragma unroll

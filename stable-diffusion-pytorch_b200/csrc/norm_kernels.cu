@@ -16,6 +16,7 @@ namespace {
 
 constexpr int GROUPS = 32;
 constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_CHUNKS = 160;
 
 // ---------------------------------------------------------------------------------------------
 // GroupNorm statistics.  grid = (chunks, B), ~2 CTAs per SM over the whole batch.  A CTA owns a run of
@@ -101,16 +102,21 @@ gn_stats_kernel(GNStatsArgs a) {
         __shared__ double s_red[8][GROUPS][2];
         const int g = threadIdx.x & 31, sl = threadIdx.x >> 5;
         const double* pp = a.partial + (size_t)b * a.chunks * GROUPS * 2 + g * 2;
-        double sum = 0.0, sq = 0.0;
-        int k = sl;
-        for (; k + 24 < a.chunks; k += 32) {
-            const double a0 = __ldcg(pp + (size_t)k * GROUPS * 2), b0 = __ldcg(pp + (size_t)k * GROUPS * 2 + 1);
-            const double a1 = __ldcg(pp + (size_t)(k + 8) * GROUPS * 2), b1 = __ldcg(pp + (size_t)(k + 8) * GROUPS * 2 + 1);
-            const double a2 = __ldcg(pp + (size_t)(k + 16) * GROUPS * 2), b2 = __ldcg(pp + (size_t)(k + 16) * GROUPS * 2 + 1);
-            const double a3 = __ldcg(pp + (size_t)(k + 24) * GROUPS * 2), b3 = __ldcg(pp + (size_t)(k + 24) * GROUPS * 2 + 1);
-            sum = (((sum + a0) + a1) + a2) + a3; sq = (((sq + b0) + b1) + b2) + b3;
+        // all loads of this thread are issued before the first add (one L2 round trip, not chunks/8 of them);
+        // the additions still run in index order
+        constexpr int MAXL = GN_MAX_CHUNKS / 8;
+        double va[MAXL], vb[MAXL];
+        const int nl = (a.chunks - sl + 7) / 8;
+#pragma unroll
+        for (int i = 0; i < MAXL; ++i) {
+            if (i < nl) {
+                const double2 t = __ldcg(reinterpret_cast<const double2*>(pp + (size_t)(sl + 8 * i) * GROUPS * 2));
+                va[i] = t.x; vb[i] = t.y;
+            }
         }
-        for (; k < a.chunks; k += 8) { sum += __ldcg(pp + (size_t)k * GROUPS * 2); sq += __ldcg(pp + (size_t)k * GROUPS * 2 + 1); }
+        double sum = 0.0, sq = 0.0;
+#pragma unroll
+        for (int i = 0; i < MAXL; ++i) if (i < nl) { sum += va[i]; sq += vb[i]; }
         s_red[sl][g][0] = sum; s_red[sl][g][1] = sq;
         __syncthreads();
         if (threadIdx.x < GROUPS) {
@@ -266,8 +272,6 @@ inline int grid_for(long long items, int threads) {
 }
 
 }  // namespace
-
-constexpr int GN_MAX_CHUNKS = 512;
 
 extern "C" int64_t sdk_groupnorm_workspace_bytes(int B, int HW) {
     // tickets [B] (256-byte aligned) + partial sums [B][chunks <= 512][32][2] doubles

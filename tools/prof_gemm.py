@@ -37,12 +37,18 @@ def main():
     ap.add_argument("--splits", type=int, default=0)
     ap.add_argument("--only", default="")
     ap.add_argument("--rowmajor", action="store_true")
+    ap.add_argument("--warm", action="store_true", help="no L2 flush between launches; time 20 back-to-back launches")
+    ap.add_argument("--shape", default="", help="custom: name,B,H,W,C,N,k")
     args = ap.parse_args()
     lib = _lib.lib()
     dev = torch.device("cuda:0")
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for name, B, H, W, Cc, N, k in SHAPES:
+    shapes = SHAPES
+    if args.shape:
+        f = args.shape.split(",")
+        shapes = [(f[0],) + tuple(int(x) for x in f[1:])]
+    for name, B, H, W, Cc, N, k in shapes:
         if args.only and args.only not in name:
             continue
         a = torch.randn((B, H, W, Cc), device=dev).bfloat16()
@@ -67,7 +73,15 @@ def main():
         _lib.check(lib.sdk_tc_gemm_launch(h, stream))
         torch.cuda.synchronize()
         ts = []
-        for _ in range(args.iters):
+        if args.warm:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                _lib.check(lib.sdk_tc_gemm_launch(h, stream))
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3 / 20)
+        for _ in range(0 if args.warm else args.iters):
             flush.zero_()                                   # evict L2 between timed launches
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
