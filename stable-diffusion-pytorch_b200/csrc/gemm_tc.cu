@@ -149,7 +149,6 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, (STAGES <= 3 || (BN <= 64 && STAGES <= 4)) ? 2 : 1)
 conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
-    pdl_trigger();
     constexpr int B_STAGE_BYTES = BN * BK * 2;
     constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM, BN);
@@ -243,6 +242,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
 
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
+        pdl_trigger();       // main loop done: let the next kernel's CTAs launch and run their prologue under our epilogue
         if (p.splits == 1) {
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
@@ -291,7 +291,6 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
 // order (deterministic) and run the epilogue.
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const __grid_constant__ TcParams p) {
-    pdl_trigger();
     pdl_wait();
     const int N = p.N, quads = (N + 3) >> 2;
     const long long total = p.M * quads;
@@ -610,7 +609,6 @@ extern "C" int sdk_tc_gemm_destroy(void* handle) {
 namespace {
 __global__ void __launch_bounds__(256)
 im2col_s2_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C, int Ho, int Wo) {
-    pdl_trigger();
     pdl_wait();
     const int nq = C >> 2;
     const long long total = (long long)B * Ho * Wo * 9 * nq;

@@ -11,6 +11,7 @@
 //   cast (+ nearest 2x upsample)                                                 (unet.py:250)
 //   NCHW -> NHWC for the 4-channel latent                                        (unet.py:256 input)
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -37,7 +38,6 @@ struct GNStatsArgs {
 
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(GNStatsArgs a) {
-    pdl_trigger();
     pdl_wait();
     extern __shared__ float s_part[];            // [nq][px_lanes][8] : 4 sums + 4 sums of squares per (quad, pixel lane)
     __shared__ bool s_last;
@@ -157,7 +157,6 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
 template <typename TOut>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(GNApplyArgs a) {
-    pdl_trigger();
     pdl_wait();
     const int C = a.C0 + a.C1, cpg = C / GROUPS, nquads = C >> 2;
     const long long total = (long long)a.B * a.HW * nquads;
@@ -185,13 +184,151 @@ gn_apply_kernel(GNApplyArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused GroupNorm: statistics + apply in ONE cooperative launch (one grid barrier), deterministic.
+//   phase 1: work item (sample, chunk<=32) -> per-group (sum, sumsq) partials in double, as gn_stats_kernel
+//   grid barrier (cooperative groups)
+//   phase 2: every CTA folds the <=32 partials of the sample(s) it touches in fixed order (16 KiB of L2
+//            reads) and normalises its share of rows.  Saves a launch and the serialized "last CTA" tail.
+// ---------------------------------------------------------------------------------------------
+struct GNFusedArgs {
+    const float* src0; const float* src1;
+    int C0, C1, HW, B, chunks, pix_per_chunk, px_lanes, q_iters;
+    double* partial;        // [B][chunks][GROUPS][2]
+    const float* gamma; const float* beta;
+    void* out; void* raw_out;
+    float eps; int silu;
+};
+
+template <typename TOut>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_fused_kernel(GNFusedArgs a) {
+    pdl_wait();
+    extern __shared__ float s_part[];            // phase 1: [nq][px_lanes][8]; phase 2: stats [GROUPS][2]
+    const int C = a.C0 + a.C1, cpg = C / GROUPS, nq = C >> 2;
+    const int qlanes = GN_THREADS / a.px_lanes;
+    const int pl = threadIdx.x / qlanes, ql = threadIdx.x - pl * qlanes;
+    // ---------------- phase 1
+    for (int w = blockIdx.x; w < a.B * a.chunks; w += gridDim.x) {
+        const int b = w / a.chunks, chunk = w - b * a.chunks;
+        const int p0 = chunk * a.pix_per_chunk;
+        const int p1 = min(a.HW, p0 + a.pix_per_chunk);
+        if (pl < a.px_lanes) {
+            for (int it = 0; it < a.q_iters; ++it) {
+                const int q = ql + it * qlanes;
+                if (q >= nq) break;
+                const int c = q << 2;
+                const float* base; int cs, cl;
+                if (c < a.C0) { base = a.src0; cs = a.C0; cl = c; } else { base = a.src1; cs = a.C1; cl = c - a.C0; }
+                const float* p = base + ((size_t)b * a.HW) * cs + cl;
+                float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+                int pix = p0 + pl;
+                const int stride = a.px_lanes;
+                for (; pix + 3 * stride < p1; pix += 4 * stride) {
+                    const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + (size_t)pix * cs));
+                    const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + stride) * cs));
+                    const float4 v2 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + 2 * stride) * cs));
+                    const float4 v3 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + 3 * stride) * cs));
+                    s[0] += (v0.x + v1.x) + (v2.x + v3.x); s[1] += (v0.y + v1.y) + (v2.y + v3.y);
+                    s[2] += (v0.z + v1.z) + (v2.z + v3.z); s[3] += (v0.w + v1.w) + (v2.w + v3.w);
+                    ss[0] += (v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x);
+                    ss[1] += (v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y);
+                    ss[2] += (v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z);
+                    ss[3] += (v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w);
+                }
+                for (; pix < p1; pix += stride) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)pix * cs));
+                    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+                    ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+                }
+                float* dst = s_part + ((size_t)q * a.px_lanes + pl) * 8;
+                *reinterpret_cast<float4*>(dst) = make_float4(s[0], s[1], s[2], s[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < GROUPS) {
+            const int g = threadIdx.x;
+            double sum = 0.0, sq = 0.0;
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+                const float* src = s_part + (size_t)(c >> 2) * a.px_lanes * 8 + (c & 3);
+                for (int l = 0; l < a.px_lanes; ++l) { sum += (double)src[l * 8]; sq += (double)src[l * 8 + 4]; }
+            }
+            double* part = a.partial + ((size_t)b * a.chunks + chunk) * GROUPS * 2;
+            part[g * 2] = sum; part[g * 2 + 1] = sq;
+        }
+        __syncthreads();
+    }
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    // ---------------- phase 2
+    float2* s_stats = reinterpret_cast<float2*>(s_part);          // [GROUPS] (mean, rstd) of the cached sample
+    const long long rows = (long long)a.B * a.HW;
+    const long long r_lo = rows * blockIdx.x / gridDim.x, r_hi = rows * (blockIdx.x + 1) / gridDim.x;
+    int cached_b = -1;
+    for (long long r0 = r_lo; r0 < r_hi;) {
+        const int b = (int)(r0 / a.HW);
+        const long long r1 = min(r_hi, (long long)(b + 1) * a.HW);
+        if (b != cached_b) {
+            __syncthreads();
+            {
+                // 8 slices x 32 groups: each thread loads <= 4 partials (one L2 round trip), then a fixed-order fold
+                double* s_red = reinterpret_cast<double*>(s_part) + 64;          // [8][GROUPS][2] after the stats slots
+                const int g = threadIdx.x & 31, sl = threadIdx.x >> 5;
+                const double* pp = a.partial + (size_t)b * a.chunks * GROUPS * 2 + g * 2;
+                double2 t[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = sl + 8 * i;
+                    t[i] = k < a.chunks ? __ldcg(reinterpret_cast<const double2*>(pp + (size_t)k * GROUPS * 2)) : make_double2(0.0, 0.0);
+                }
+                s_red[(sl * GROUPS + g) * 2] = ((t[0].x + t[1].x) + t[2].x) + t[3].x;
+                s_red[(sl * GROUPS + g) * 2 + 1] = ((t[0].y + t[1].y) + t[2].y) + t[3].y;
+                __syncthreads();
+                if (threadIdx.x < GROUPS) {
+                    double sum = 0.0, sq = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { sum += s_red[(i * GROUPS + g) * 2]; sq += s_red[(i * GROUPS + g) * 2 + 1]; }
+                    const double n = (double)cpg * (double)a.HW;
+                    const double mean = sum / n;
+                    double var = sq / n - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    s_stats[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+                }
+            }
+            __syncthreads();
+            cached_b = b;
+        }
+        const long long items = (r1 - r0) * nq;
+        for (long long i = threadIdx.x; i < items; i += GN_THREADS) {
+            const int q = (int)(i % nq);
+            const long long row = r0 + i / nq;
+            const int c = q << 2;
+            const float* p = (c < a.C0) ? a.src0 + row * a.C0 + c : a.src1 + row * a.C1 + (c - a.C0);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+            const float xs[4] = {v.x, v.y, v.z, v.w}, gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 st = s_stats[(c + j) / cpg];
+                const float y = (xs[j] - st.x) * st.y * gs[j] + bs[j];
+                o[j] = a.silu ? silu_f(y) : y;
+            }
+            store4<TOut>(reinterpret_cast<TOut*>(a.out) + row * C + c, o[0], o[1], o[2], o[3]);
+            if (a.raw_out) store4<TOut>(reinterpret_cast<TOut*>(a.raw_out) + row * C + c, xs[0], xs[1], xs[2], xs[3]);
+        }
+        r0 = r1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row lives in registers (C <= 2048), exact two-pass statistics.
 // ---------------------------------------------------------------------------------------------
 template <typename TOut, int MAXQ>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, TOut* __restrict__ out, int C, long long rows) {
-    pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -235,7 +372,6 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 template <typename TOut>
 __global__ void __launch_bounds__(256)
 cast_upsample_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int B, int H, int W, int C, int up) {
-    pdl_trigger();
     pdl_wait();
     const int Ho = H * up, Wo = W * up, nquads = C >> 2;
     const long long total = (long long)B * Ho * Wo * nquads;
@@ -252,7 +388,6 @@ cast_upsample_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int 
 
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B_src, int B_dst, int C, int HW) {
-    pdl_trigger();
     pdl_wait();
     // dst[b][p][c] = src[b % B_src][c][p]   (b % B_src implements latent.repeat(2,1,1,1), diffusion.py:228)
     const long long total = (long long)B_dst * HW * C;
@@ -326,6 +461,47 @@ extern "C" int sdk_groupnorm_apply(const float* src0, int C0, const float* src1,
     else if (out_dtype == SDK_BF16) SDK_CUDA(sdk_launch(gn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, a));
     else return sdk_fail(SDK_ERR_ARG, "sdk_groupnorm_apply: out_dtype %d", out_dtype);
     SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
+
+// GroupNorm statistics + apply (+SiLU) (+raw cast copy) in one cooperative launch; workspace as for sdk_groupnorm_stats
+extern "C" int sdk_groupnorm_fused(const float* src0, int C0, const float* src1, int C1, int B, int HW, float eps,
+                                   const float* gamma, const float* beta, int silu, void* out, void* raw_out, int out_dtype,
+                                   void* workspace, void* stream) {
+    SDK_CHECK_ARG(src0 && gamma && beta && out && workspace, "sdk_groupnorm_fused: null pointer");
+    const int C = C0 + C1;
+    SDK_CHECK_ARG(C0 > 0 && C1 >= 0 && (C1 == 0 || src1), "sdk_groupnorm_fused: bad sources");
+    SDK_CHECK_ARG(C % GROUPS == 0 && C0 % 4 == 0 && C1 % 4 == 0, "sdk_groupnorm_fused: C=%d+%d must be a multiple of 32 (quads of 4)", C0, C1);
+    SDK_CHECK_ARG(B > 0 && HW > 0 && (out_dtype == SDK_F32 || out_dtype == SDK_BF16), "sdk_groupnorm_fused: bad args");
+    const int nq = C / 4;
+    int chunks = HW < 32 ? HW : 32;
+    const int ppc = (HW + chunks - 1) / chunks;
+    chunks = (HW + ppc - 1) / ppc;
+    int px_lanes = GN_THREADS / (nq < GN_THREADS ? nq : GN_THREADS);
+    if (px_lanes > ppc) px_lanes = ppc;
+    if (px_lanes < 1) px_lanes = 1;
+    const int qlanes = GN_THREADS / px_lanes;
+    GNFusedArgs a;
+    a.src0 = src0; a.src1 = src1; a.C0 = C0; a.C1 = C1; a.HW = HW; a.B = B; a.chunks = chunks; a.pix_per_chunk = ppc;
+    a.px_lanes = px_lanes; a.q_iters = (nq + qlanes - 1) / qlanes;
+    a.partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + (((size_t)B * sizeof(unsigned int) + 255) / 256) * 256);
+    a.gamma = gamma; a.beta = beta; a.out = out; a.raw_out = raw_out; a.eps = eps; a.silu = silu;
+    size_t smem = (size_t)nq * px_lanes * 8 * sizeof(float);
+    if (smem < 512 + 8 * GROUPS * 2 * sizeof(double)) smem = 512 + 8 * GROUPS * 2 * sizeof(double);   // phase 2: stats + fold scratch
+    SDK_CHECK_ARG(smem <= 48 * 1024, "sdk_groupnorm_fused: shared memory %zu too large", smem);
+    // grid: every CTA must be co-resident (cooperative launch): 2 CTAs of 256 threads per SM, no more than there is work
+    long long want = (long long)B * HW * nq / (GN_THREADS * 4);
+    if (want < (long long)B * chunks) want = (long long)B * chunks;
+    const void* fn = out_dtype == SDK_F32 ? (const void*)gn_fused_kernel<float> : (const void*)gn_fused_kernel<__nv_bfloat16>;
+    int occ = 0;
+    SDK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, GN_THREADS, smem));
+    SDK_CHECK_ARG(occ >= 1, "sdk_groupnorm_fused: kernel does not fit on an SM");
+    if (occ > 4) occ = 4;
+    int grid = sdk_num_sms() * occ;
+    if (want < grid) grid = (int)(want < 1 ? 1 : want);
+    void* kargs[] = {&a};
+    SDK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(GN_THREADS), kargs, smem, (cudaStream_t)stream));
     return SDK_OK;
 }
 

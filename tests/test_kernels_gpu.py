@@ -255,6 +255,13 @@ def test_groupnorm(dev, shape, odt):
     want = Fn.silu(Fn.group_norm(x.permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
     assert rel_l2(out.float(), want) < (2e-5 if odt == F32_T else 4e-3)
     assert rel_l2(raw.float(), x) < (1e-7 if odt == F32_T else 4e-3)
+    # fused (single cooperative launch) variant used by the step program: same answer, run-to-run identical
+    out2, raw2 = torch.empty_like(out), torch.empty_like(raw)
+    for dst in (out2, out):
+        _lib.check(lib.sdk_groupnorm_fused(s0.data_ptr(), C0, s1.data_ptr() if C1 else 0, C1, B, HW, 1e-5, gamma.data_ptr(), beta.data_ptr(), 1,
+                                           dst.data_ptr(), raw2.data_ptr(), odt, ws.data_ptr(), stream()))
+    assert rel_l2(out2.float(), want) < (2e-5 if odt == F32_T else 4e-3)
+    assert torch.equal(out2, out) and torch.equal(raw2, raw)
 
 
 @pytest.mark.parametrize("C_", [320, 640, 1280, 768])
