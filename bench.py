@@ -160,10 +160,12 @@ def run_reference_arm(args, cfg):
 
 
 # --------------------------------------------------------------------------------------------------
-def time_gemm_family(loop, iters=5):
+def time_gemm_family(loop, iters=5, fns=None):
     """Average device time of ALL tcgen05 implicit-GEMM launches of one step, replayed back to back as a graph."""
-    lib_launch = loop.prog.lib.sdk_tc_gemm_launch
-    ops = [(fn, a) for fn, a in loop.prog.ops if fn is lib_launch]
+    lib = loop.prog.lib
+    names = fns or ["sdk_tc_gemm_launch"]
+    targets = [getattr(lib, n) for n in names]
+    ops = [(fn, a) for fn, a in loop.prog.ops if any(fn is t for t in targets)]
     if not ops:
         return None, 0
     g = torch.cuda.CUDAGraph()
@@ -193,6 +195,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="also time each kernel class of one step as its own graph")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch_per_gpu:
@@ -304,8 +307,17 @@ def main():
 
         # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM), rank 0
         gemm_ms, gemm_launches = (None, 0)
+        breakdown = None
         if rank == 0 and args.precision == "bf16":
             gemm_ms, gemm_launches = time_gemm_family(loop)
+            if args.breakdown:
+                breakdown = {}
+                for label, fns in (("tc_gemm", ["sdk_tc_gemm_launch"]), ("attention", ["sdk_attention_bf16"]),
+                                   ("groupnorm", ["sdk_groupnorm_stats", "sdk_groupnorm_apply", "sdk_groupnorm_fused"]),
+                                   ("layernorm", ["sdk_layernorm"]),
+                                   ("other", ["sdk_cast_upsample", "sdk_im2col_s2", "sdk_nchw_to_nhwc", "sdk_gemv", "sdk_time_sinusoid", "sdk_conv_gemm_f32"])):
+                    ms, n = time_gemm_family(loop, fns=fns)
+                    breakdown[label] = {"ms": ms, "launches": n}
 
         # the path's only collective: gather final latents (not timed; checked)
         final = gather_latents(loop.latent.clone(), B * world)
@@ -347,6 +359,8 @@ def main():
         "gpu_launches": loop.launches_per_step * K,
         "roofline": roof,
     }
+    if breakdown:
+        line["breakdown_ms_per_step"] = breakdown
     if not args.no_cpu_baseline and world >= 1:
         try:
             sec, used = cpu_loop_body_seconds(cfg, sd, arch, cfg["hw"], 2, budget_s=45)

@@ -423,7 +423,10 @@ extern "C" int sdk_groupnorm_stats(const float* src0, int C0, const float* src1,
     SDK_CHECK_ARG(B > 0 && B < 65536 && HW > 0, "sdk_groupnorm_stats: bad B/HW");
     const int nq = C / 4;
     SDK_CHECK_ARG(nq * 32 <= 48 * 1024 / 1 && nq <= 4096, "sdk_groupnorm_stats: C too large");
-    int chunks = (sdk_num_sms() * 2 + B - 1) / B;      // ~2 CTAs per SM over the whole batch
+    int chunks = (sdk_num_sms() * 2 + B - 1) / B;      // ~2 CTAs per SM over the whole batch ...
+    const long long bytes_per_sample = (long long)HW * C * 4;
+    const int by_bytes = (int)((bytes_per_sample + 49151) / 49152);   // ... but >= 48 KiB of input per CTA: small tensors are
+    if (chunks > by_bytes) chunks = by_bytes;                          // latency-bound and every extra partial lengthens the final fold
     if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
     if (chunks > HW) chunks = HW;
     if (chunks < 1) chunks = 1;
