@@ -71,6 +71,10 @@ int sdk_groupnorm_apply(const float* src0, int C0, const float* src1, int C1, in
 int sdk_groupnorm_fused(const float* src0, int C0, const float* src1, int C1, int B, int HW, float eps,
                         const float* gamma, const float* beta, int silu, void* out, void* raw_out, int out_dtype,
                         void* workspace, void* stream);
+/* statistics + apply in ONE launch, one thread-block cluster per sample, DSMEM reduction (default of the step program) */
+int sdk_groupnorm_cluster(const float* src0, int C0, const float* src1, int C1, int B, int HW, float eps,
+                          const float* gamma, const float* beta, int silu, void* out, void* raw_out, int out_dtype,
+                          void* stream);
 int sdk_layernorm(const float* x, const float* gamma, const float* beta, float eps, void* out,
                   int out_dtype, int64_t rows, int C, void* stream);
 /* fp32 NHWC -> out_dtype NHWC, nearest upsample by `up` (1 or 2)  (unet.py:250) */

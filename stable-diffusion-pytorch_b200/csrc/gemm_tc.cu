@@ -28,6 +28,7 @@ namespace {
 
 constexpr int BM = 128, BK = 64, TC_THREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 2;           // 16 KiB
+constexpr int ADD_ROWS = 4;                          // samples per tile whose (bias + time-bias) row is staged in smem
 
 struct alignas(64) TcParams {
     CUtensorMap tmA[2];
@@ -54,10 +55,16 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* v) {
 }
 
 // Epilogue for one thread = one output row, 32 consecutive GEMM columns starting at n (absolute).
-__device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int n, long long grow, int b, int oy, int ox) {
+// `sadd` (shared memory, may be null) holds bias[n..n+32) + tbias[sample][n..n+32) already summed; `rpre` (may be null)
+// holds the row's residual values for this chunk, prefetched one chunk ahead by the caller.
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int n, long long grow, int b, int oy, int ox,
+                                               const float* sadd = nullptr, const float4* rpre = nullptr) {
     const int N = p.N;
     if (n >= N) return;
-    if (n + 32 <= N) {
+    if (sadd) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += sadd[j];       // same address across the warp: shared-memory broadcast
+    } else if (n + 32 <= N) {
         // full chunk: 16-byte loads, all issued before the first add (one scoreboard wait instead of 32)
         if (p.bias) {
             float4 bv[8];
@@ -119,7 +126,10 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
     }
     const long long off = grow * N + n;
     if (n + 32 <= N) {
-        if (p.residual) {
+        if (rpre) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[4 * j] += rpre[j].x; v[4 * j + 1] += rpre[j].y; v[4 * j + 2] += rpre[j].z; v[4 * j + 3] += rpre[j].w; }
+        } else if (p.residual) {
             float4 rv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) rv[j] = __ldg(reinterpret_cast<const float4*>(p.residual + off) + j);
@@ -161,6 +171,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* s_add = reinterpret_cast<float*>(tmem_slot + 4);        // [ADD_ROWS][BN]: bias + time-bias of the tile's samples
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -240,20 +251,52 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         const long long grow = ((long long)b * p.H + oy) * p.W + ox;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
 
+        // While the main loop runs, stage the additive epilogue terms of this tile in shared memory:
+        // s_add[tb][j] = bias[n0+j] + tbias[b0+tb][n0+j]  (one row per sample the tile touches, <= ADD_ROWS)
+        const bool staged = p.splits == 1 && p.TB <= ADD_ROWS && (p.bias || p.tbias);
+        if (staged) {
+            const int et = threadIdx.x - 64;                  // 0..127 within the epilogue warps
+            for (int i = et; i < p.TB * BN; i += 128) {
+                const int tbi = i / BN, j = i - tbi * BN;
+                float x = 0.f;
+                if (n0 + j < p.N) {
+                    if (p.bias) x = __ldg(p.bias + n0 + j);
+                    if (p.tbias && b0 + tbi < p.B) x += __ldg(p.tbias + (long long)(b0 + tbi) * p.tb_stride + n0 + j);
+                }
+                s_add[i] = x;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        const float* my_add = staged ? s_add + tb_i * BN : nullptr;
+        // residual prefetch (plain NHWC epilogue, full chunks): chunk c+1 is in flight while chunk c is finished
+        const bool rpf = p.splits == 1 && p.residual && valid && !p.geglu && !p.out_nchw && (n0 + BN <= p.N);
+        float4 rcur[8], rnext[8];
+        if (rpf) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rcur[j] = __ldg(reinterpret_cast<const float4*>(p.residual + grow * p.N + n0) + j);
+        }
+
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
-        pdl_trigger();       // main loop done: let the next kernel's CTAs launch and run their prologue under our epilogue
         if (p.splits == 1) {
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t u[32];
                 ptx::tmem_ld32(taddr + c * 32, u);
+                if (rpf && c + 1 < BN / 32) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rnext[j] = __ldg(reinterpret_cast<const float4*>(p.residual + grow * p.N + n0 + (c + 1) * 32) + j);
+                }
                 ptx::tmem_ld_wait();
                 if (valid) {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
-                    epilogue_chunk(p, v, n0 + c * 32, grow, b, oy, ox);
+                    epilogue_chunk(p, v, n0 + c * 32, grow, b, oy, ox, my_add ? my_add + c * 32 : nullptr, rpf ? rcur : nullptr);
+                }
+                if (rpf) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
                 }
             }
         } else {
@@ -407,7 +450,7 @@ struct TcGemm {
 
 template <int BN, int STAGES>
 int launch_cfg(const TcGemm* g, cudaStream_t s) {
-    constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256;
+    constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + ADD_ROWS * BN * 4;
     static bool configured = false;
     if (!configured) {
         SDK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

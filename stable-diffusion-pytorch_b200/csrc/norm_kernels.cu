@@ -154,32 +154,57 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
     *reinterpret_cast<uint2*>(p) = u;
 }
 
+// grid = (pixel chunks, B).  Threads are laid out (pixel lanes) x (channel quads) as in the statistics kernel; a thread
+// keeps gamma/beta and the (mean, rstd) of its 4 channels in registers and walks its pixels with 4 loads in flight --
+// no integer division and no table lookups in the inner loop.
 template <typename TOut>
-__global__ void __launch_bounds__(256)
-gn_apply_kernel(GNApplyArgs a) {
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(GNApplyArgs a, int pix_per_chunk, int px_lanes, int q_iters) {
     pdl_wait();
-    const int C = a.C0 + a.C1, cpg = C / GROUPS, nquads = C >> 2;
-    const long long total = (long long)a.B * a.HW * nquads;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int q = (int)(i % nquads);
-        const long long row = i / nquads;
-        const int b = (int)(row / a.HW);
+    const int b = blockIdx.y;
+    const int C = a.C0 + a.C1, cpg = C / GROUPS, nq = C >> 2;
+    const int p0 = blockIdx.x * pix_per_chunk;
+    const int p1 = min(a.HW, p0 + pix_per_chunk);
+    const int qlanes = GN_THREADS / px_lanes;
+    const int pl = threadIdx.x / qlanes, ql = threadIdx.x - pl * qlanes;
+    if (pl >= px_lanes) return;
+    TOut* out = reinterpret_cast<TOut*>(a.out) + (size_t)b * a.HW * C;
+    TOut* raw = a.raw_out ? reinterpret_cast<TOut*>(a.raw_out) + (size_t)b * a.HW * C : nullptr;
+    for (int it = 0; it < q_iters; ++it) {
+        const int q = ql + it * qlanes;
+        if (q >= nq) break;
         const int c = q << 2;
-        const float* p = (c < a.C0) ? a.src0 + row * a.C0 + c : a.src1 + row * a.C1 + (c - a.C0);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        const float* base; int cs, cl;
+        if (c < a.C0) { base = a.src0; cs = a.C0; cl = c; } else { base = a.src1; cs = a.C1; cl = c - a.C0; }
+        const float* p = base + ((size_t)b * a.HW) * cs + cl;
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
-        const float xs[4] = {v.x, v.y, v.z, v.w}, gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
-        float r[4];
+        float sc[4], sh[4];                                  // y = x * sc + sh
+        {
+            const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int g = (c + j) / cpg;
-            const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats) + (size_t)b * GROUPS + g);
-            float y = (xs[j] - st.x) * st.y * gs[j] + bs[j];
-            r[j] = a.silu ? silu_f(y) : y;
+            for (int j = 0; j < 4; ++j) {
+                const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats) + (size_t)b * GROUPS + (c + j) / cpg);
+                sc[j] = st.y * gs[j];
+                sh[j] = bs[j] - st.x * sc[j];
+            }
         }
-        store4<TOut>(reinterpret_cast<TOut*>(a.out) + row * C + c, r[0], r[1], r[2], r[3]);
-        if (a.raw_out) store4<TOut>(reinterpret_cast<TOut*>(a.raw_out) + row * C + c, xs[0], xs[1], xs[2], xs[3]);
+        auto emit = [&](int pix, const float4& v) {
+            float y0 = fmaf(v.x, sc[0], sh[0]), y1 = fmaf(v.y, sc[1], sh[1]), y2 = fmaf(v.z, sc[2], sh[2]), y3 = fmaf(v.w, sc[3], sh[3]);
+            if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+            store4<TOut>(out + (size_t)pix * C + c, y0, y1, y2, y3);
+            if (raw) store4<TOut>(raw + (size_t)pix * C + c, v.x, v.y, v.z, v.w);
+        };
+        int pix = p0 + pl;
+        const int stride = px_lanes;
+        for (; pix + 3 * stride < p1; pix += 4 * stride) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + (size_t)pix * cs));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + stride) * cs));
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + 2 * stride) * cs));
+            const float4 v3 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + 3 * stride) * cs));
+            emit(pix, v0); emit(pix + stride, v1); emit(pix + 2 * stride, v2); emit(pix + 3 * stride, v3);
+        }
+        for (; pix < p1; pix += stride) emit(pix, __ldg(reinterpret_cast<const float4*>(p + (size_t)pix * cs)));
     }
 }
 
@@ -323,6 +348,141 @@ gn_fused_kernel(GNFusedArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// GroupNorm in ONE launch with a thread-block cluster per sample (the default in the step program).
+//   grid = (CS, B), cluster = (CS,1,1), 1024 threads per CTA.  CTA r owns a contiguous run of the sample's pixels.
+//   pass 1: per-group (sum, sumsq) of the CTA's pixels -> 32 doubles x 2 in its shared memory
+//   cluster barrier; every CTA reads all CS partials through distributed shared memory in rank order
+//   (deterministic), derives mean / rstd, then pass 2 normalises its own pixels (second read hits L2).
+// No global atomics, tickets, fences or second launch: at UNet batch 2 a GroupNorm is latency-, not
+// bandwidth-bound, and this removes a launch plus the serialized last-CTA tail of the two-kernel form.
+// ---------------------------------------------------------------------------------------------
+constexpr int GNC_THREADS = 1024;
+
+__device__ __forceinline__ double dsmem_ld_f64(const double* local, unsigned rank) {
+    unsigned laddr = (unsigned)__cvta_generic_to_shared(local), raddr;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(raddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <typename TOut>
+__global__ void __launch_bounds__(GNC_THREADS, 1)
+gn_cluster_kernel(GNApplyArgs a, float eps, int CS, int px_lanes, int q_iters) {
+    pdl_wait();
+    extern __shared__ float s_part[];                       // [nq][px_lanes][8]
+    __shared__ double s_cl[GROUPS][2];                      // this CTA's per-group partial (read by the whole cluster)
+    __shared__ float2 s_stats[GROUPS];
+    const int b = blockIdx.y, rank = blockIdx.x;            // cluster spans blockIdx.x
+    const int C = a.C0 + a.C1, cpg = C / GROUPS, nq = C >> 2;
+    const int ppc = (a.HW + CS - 1) / CS;
+    const int p0 = rank * ppc, p1 = min(a.HW, p0 + ppc);
+    const int qlanes = GNC_THREADS / px_lanes;
+    const int pl = threadIdx.x / qlanes, ql = threadIdx.x - pl * qlanes;
+    const bool active = pl < px_lanes;
+    // ---- pass 1
+    if (active) {
+        for (int it = 0; it < q_iters; ++it) {
+            const int q = ql + it * qlanes;
+            if (q >= nq) break;
+            const int c = q << 2;
+            const float* base; int cs, cl;
+            if (c < a.C0) { base = a.src0; cs = a.C0; cl = c; } else { base = a.src1; cs = a.C1; cl = c - a.C0; }
+            const float* p = base + ((size_t)b * a.HW) * cs + cl;
+            float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+            int pix = p0 + pl;
+            const int stride = px_lanes;
+            for (; pix + 3 * stride < p1; pix += 4 * stride) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + (size_t)pix * cs));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + stride) * cs));
+                const float4 v2 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + 2 * stride) * cs));
+                const float4 v3 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + 3 * stride) * cs));
+                s[0] += (v0.x + v1.x) + (v2.x + v3.x); s[1] += (v0.y + v1.y) + (v2.y + v3.y);
+                s[2] += (v0.z + v1.z) + (v2.z + v3.z); s[3] += (v0.w + v1.w) + (v2.w + v3.w);
+                ss[0] += (v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x);
+                ss[1] += (v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y);
+                ss[2] += (v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z);
+                ss[3] += (v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w);
+            }
+            for (; pix < p1; pix += stride) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)pix * cs));
+                s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+                ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+            }
+            float* dst = s_part + ((size_t)q * px_lanes + pl) * 8;
+            *reinterpret_cast<float4*>(dst) = make_float4(s[0], s[1], s[2], s[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < GROUPS) {
+        const int g = threadIdx.x;
+        double sum = 0.0, sq = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const float* src = s_part + (size_t)(c >> 2) * px_lanes * 8 + (c & 3);
+            for (int l = 0; l < px_lanes; ++l) { sum += (double)src[l * 8]; sq += (double)src[l * 8 + 4]; }
+        }
+        s_cl[g][0] = sum; s_cl[g][1] = sq;
+    }
+    cluster_arrive();
+    cluster_wait();
+    if (threadIdx.x < GROUPS) {
+        const int g = threadIdx.x;
+        double sum = 0.0, sq = 0.0;
+        for (int r = 0; r < CS; ++r) { sum += dsmem_ld_f64(&s_cl[g][0], r); sq += dsmem_ld_f64(&s_cl[g][1], r); }
+        const double n = (double)cpg * (double)a.HW;
+        const double mean = sum / n;
+        double var = sq / n - mean * mean;                  // biased variance (nn.GroupNorm)
+        if (var < 0.0) var = 0.0;
+        s_stats[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+    cluster_arrive();                                       // our remote reads are done; waited on just before exit
+    __syncthreads();
+    // ---- pass 2
+    if (active) {
+        TOut* out = reinterpret_cast<TOut*>(a.out) + (size_t)b * a.HW * C;
+        TOut* raw = a.raw_out ? reinterpret_cast<TOut*>(a.raw_out) + (size_t)b * a.HW * C : nullptr;
+        for (int it = 0; it < q_iters; ++it) {
+            const int q = ql + it * qlanes;
+            if (q >= nq) break;
+            const int c = q << 2;
+            const float* base; int cs, cl;
+            if (c < a.C0) { base = a.src0; cs = a.C0; cl = c; } else { base = a.src1; cs = a.C1; cl = c - a.C0; }
+            const float* p = base + ((size_t)b * a.HW) * cs + cl;
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+            const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
+            float sc[4], sh[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 st = s_stats[(c + j) / cpg];
+                sc[j] = st.y * gs[j];
+                sh[j] = bs[j] - st.x * sc[j];
+            }
+            auto emit = [&](int pix, const float4& v) {
+                float y0 = fmaf(v.x, sc[0], sh[0]), y1 = fmaf(v.y, sc[1], sh[1]), y2 = fmaf(v.z, sc[2], sh[2]), y3 = fmaf(v.w, sc[3], sh[3]);
+                if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+                store4<TOut>(out + (size_t)pix * C + c, y0, y1, y2, y3);
+                if (raw) store4<TOut>(raw + (size_t)pix * C + c, v.x, v.y, v.z, v.w);
+            };
+            int pix = p0 + pl;
+            const int stride = px_lanes;
+            for (; pix + 3 * stride < p1; pix += 4 * stride) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + (size_t)pix * cs));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + stride) * cs));
+                const float4 v2 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + 2 * stride) * cs));
+                const float4 v3 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(pix + 3 * stride) * cs));
+                emit(pix, v0); emit(pix + stride, v1); emit(pix + 2 * stride, v2); emit(pix + 3 * stride, v3);
+            }
+            for (; pix < p1; pix += stride) emit(pix, __ldg(reinterpret_cast<const float4*>(p + (size_t)pix * cs)));
+        }
+    }
+    cluster_wait();                                         // nobody may exit while a peer still reads its s_cl
+}
+
+// ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row lives in registers (C <= 2048), exact two-pass statistics.
 // ---------------------------------------------------------------------------------------------
 template <typename TOut, int MAXQ>
@@ -459,9 +619,21 @@ extern "C" int sdk_groupnorm_apply(const float* src0, int C0, const float* src1,
     GNApplyArgs a;
     a.src0 = src0; a.src1 = src1; a.C0 = C0; a.C1 = C1; a.HW = HW; a.B = B;
     a.stats = stats; a.gamma = gamma; a.beta = beta; a.out = out; a.raw_out = raw_out; a.silu = silu;
-    const int grid = grid_for((long long)B * HW * (C / 4), 256);
-    if (out_dtype == SDK_F32) SDK_CUDA(sdk_launch(gn_apply_kernel<float>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, a));
-    else if (out_dtype == SDK_BF16) SDK_CUDA(sdk_launch(gn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, a));
+    const int nq = C / 4;
+    int px_lanes = GN_THREADS / (nq < GN_THREADS ? nq : GN_THREADS);
+    if (px_lanes > HW) px_lanes = HW;
+    if (px_lanes < 1) px_lanes = 1;
+    const int qlanes = GN_THREADS / px_lanes;
+    const int q_iters = (nq + qlanes - 1) / qlanes;
+    // ~8 pixels per thread, but never fewer CTAs than ~2 per SM when the tensor is large enough
+    int ppc = 8 * px_lanes;
+    int chunks = (HW + ppc - 1) / ppc;
+    const int want = (sdk_num_sms() * 2 + B - 1) / B;
+    if (chunks < want) { chunks = want < HW ? want : HW; ppc = (HW + chunks - 1) / chunks; }
+    chunks = (HW + ppc - 1) / ppc;
+    SDK_CHECK_ARG(B < 65536, "sdk_groupnorm_apply: batch too large");
+    if (out_dtype == SDK_F32) SDK_CUDA(sdk_launch(gn_apply_kernel<float>, dim3(chunks, B), dim3(GN_THREADS), (size_t)0, (cudaStream_t)stream, a, ppc, px_lanes, q_iters));
+    else if (out_dtype == SDK_BF16) SDK_CUDA(sdk_launch(gn_apply_kernel<__nv_bfloat16>, dim3(chunks, B), dim3(GN_THREADS), (size_t)0, (cudaStream_t)stream, a, ppc, px_lanes, q_iters));
     else return sdk_fail(SDK_ERR_ARG, "sdk_groupnorm_apply: out_dtype %d", out_dtype);
     SDK_LAUNCH_CHECK();
     return SDK_OK;
@@ -505,6 +677,46 @@ extern "C" int sdk_groupnorm_fused(const float* src0, int C0, const float* src1,
     if (want < grid) grid = (int)(want < 1 ? 1 : want);
     void* kargs[] = {&a};
     SDK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(GN_THREADS), kargs, smem, (cudaStream_t)stream));
+    return SDK_OK;
+}
+
+// GroupNorm (+SiLU, +raw copy) in one launch, one thread-block cluster per sample (see gn_cluster_kernel)
+extern "C" int sdk_groupnorm_cluster(const float* src0, int C0, const float* src1, int C1, int B, int HW, float eps,
+                                     const float* gamma, const float* beta, int silu, void* out, void* raw_out, int out_dtype,
+                                     void* stream) {
+    SDK_CHECK_ARG(src0 && gamma && beta && out, "sdk_groupnorm_cluster: null pointer");
+    const int C = C0 + C1;
+    SDK_CHECK_ARG(C0 > 0 && C1 >= 0 && (C1 == 0 || src1), "sdk_groupnorm_cluster: bad sources");
+    SDK_CHECK_ARG(C % GROUPS == 0 && C0 % 4 == 0 && C1 % 4 == 0, "sdk_groupnorm_cluster: C=%d+%d must be a multiple of 32 (quads of 4)", C0, C1);
+    SDK_CHECK_ARG(B > 0 && B < 65536 && HW > 0 && (out_dtype == SDK_F32 || out_dtype == SDK_BF16), "sdk_groupnorm_cluster: bad args");
+    const int nq = C / 4;
+    SDK_CHECK_ARG(nq <= 4096, "sdk_groupnorm_cluster: C too large");
+    int CS = 8;
+    while (CS > 1 && CS > HW) CS >>= 1;
+    const int ppc = (HW + CS - 1) / CS;
+    int px_lanes = GNC_THREADS / (nq < GNC_THREADS ? nq : GNC_THREADS);
+    if (px_lanes > ppc) px_lanes = ppc;
+    if (px_lanes < 1) px_lanes = 1;
+    const int qlanes = GNC_THREADS / px_lanes;
+    const int q_iters = (nq + qlanes - 1) / qlanes;
+    const size_t smem = (size_t)nq * px_lanes * 8 * sizeof(float);
+    SDK_CHECK_ARG(smem <= 160 * 1024, "sdk_groupnorm_cluster: shared memory %zu too large", smem);
+    GNApplyArgs a;
+    a.src0 = src0; a.src1 = src1; a.C0 = C0; a.C1 = C1; a.HW = HW; a.B = B;
+    a.stats = nullptr; a.gamma = gamma; a.beta = beta; a.out = out; a.raw_out = raw_out; a.silu = silu;
+    void (*fn)(GNApplyArgs, float, int, int, int) = out_dtype == SDK_F32 ? gn_cluster_kernel<float> : gn_cluster_kernel<__nv_bfloat16>;
+    static bool configured[2] = {false, false};
+    if (!configured[out_dtype]) {
+        SDK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured[out_dtype] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS, B); cfg.blockDim = dim3(GNC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SDK_CUDA(cudaLaunchKernelEx(&cfg, fn, a, eps, CS, px_lanes, q_iters));
     return SDK_OK;
 }
 

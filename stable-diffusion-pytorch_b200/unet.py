@@ -245,7 +245,15 @@ class StepProgram:
         raw = self.pool.get(B * HW, Ct, self.act) if want_raw else None
         s1p = s1.data_ptr() if s1 is not None else 0
         rawp = raw.data_ptr() if raw is not None else 0
-        if self.net.gn_fused:
+        mode = self.net.gn_mode
+        if mode == "auto":
+            # small tensors are latency-bound: one cluster launch (DSMEM reduce) beats two launches + ticketed tail;
+            # large ones are bandwidth-bound and need the whole chip (measured on B200)
+            mode = "cluster" if B * HW * Ct * 4 <= self.net.gn_cluster_max_bytes else "split"
+        if mode == "cluster":
+            self._emit(self.lib.sdk_groupnorm_cluster, s0.data_ptr(), c0, s1p, c1, B, HW, float(eps), g.data_ptr(), b.data_ptr(),
+                       int(silu), out.data_ptr(), rawp, self.act)
+        elif mode == "coop":
             # one cooperative launch (statistics, grid barrier, apply).  Measured on B200 inside the step graph:
             # 6.36 ms/step vs 6.15 ms/step for the two-kernel form below, so it is not the default.
             self._emit(self.lib.sdk_groupnorm_fused, s0.data_ptr(), c0, s1p, c1, B, HW, float(eps), g.data_ptr(), b.data_ptr(),
@@ -530,7 +538,8 @@ class UNet(nn.Module):
         self.precision = os.environ.get("SDB200_PRECISION", "bf16")
         self.tc_block_n = int(os.environ.get("SDB200_TC_BLOCK_N", "0"))      # 0 = auto; tuning / test overrides
         self.tc_splits = int(os.environ.get("SDB200_TC_SPLITS", "0"))
-        self.gn_fused = os.environ.get("SDB200_GN_FUSED", "0") == "1"
+        self.gn_mode = os.environ.get("SDB200_GN_MODE", "split")           # split (stats+apply kernels, fastest measured) | cluster | coop | auto
+        self.gn_cluster_max_bytes = int(os.environ.get("SDB200_GN_CLUSTER_MAX_BYTES", str(3 << 20)))
         self.use_cuda_graph = os.environ.get("SDB200_CUDA_GRAPH", "1") != "0"
         self._packed: Dict = {}
         self._plans: Dict = {}

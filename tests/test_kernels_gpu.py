@@ -262,6 +262,13 @@ def test_groupnorm(dev, shape, odt):
                                            dst.data_ptr(), raw2.data_ptr(), odt, ws.data_ptr(), stream()))
     assert rel_l2(out2.float(), want) < (2e-5 if odt == F32_T else 4e-3)
     assert torch.equal(out2, out) and torch.equal(raw2, raw)
+    # cluster / DSMEM variant (the step program's default)
+    out3, raw3 = torch.full_like(out, float("nan")), torch.full_like(raw, float("nan"))
+    for dst in (out3, out2):
+        _lib.check(lib.sdk_groupnorm_cluster(s0.data_ptr(), C0, s1.data_ptr() if C1 else 0, C1, B, HW, 1e-5, gamma.data_ptr(), beta.data_ptr(), 1,
+                                             dst.data_ptr(), raw3.data_ptr(), odt, stream()))
+    assert rel_l2(out3.float(), want) < (2e-5 if odt == F32_T else 4e-3)
+    assert torch.equal(out3, out2) and rel_l2(raw3.float(), x) < (1e-7 if odt == F32_T else 4e-3)
 
 
 @pytest.mark.parametrize("C_", [320, 640, 1280, 768])
