@@ -146,11 +146,12 @@ typedef struct SdkTcGemmDesc {
     int block_n;        /* 0 = auto (32|64|128|160|256) */
     int splits;         /* 0 = auto split-K */
     int w_kmajor;       /* 0: weights [N][K] row-major; 1: k-block-major [K/64][N][64] (contiguous B stages) */
+    int two_cta;        /* 0 = auto, 1 = never, 2 = always (when the number of m-tiles is even): tcgen05 cta_group::2 CTA pairs */
 } SdkTcGemmDesc;
 int sdk_tc_gemm_create(const SdkTcGemmDesc* desc, void** handle);
 int64_t sdk_tc_gemm_workspace_bytes(void* handle);
 int sdk_tc_gemm_set_workspace(void* handle, void* workspace);   /* zeroed once by the caller; shared across plans run on one stream */
-int sdk_tc_gemm_info(void* handle, int* out, int n);            /* block_n, splits, grid.x, grid.y, TW, TH, TB, k-blocks */
+int sdk_tc_gemm_info(void* handle, int* out, int n);            /* block_n, splits, grid.x, grid.y, TW, TH, TB, k-blocks [, cta group size if n >= 9] */
 int sdk_tc_gemm_launch(void* handle, void* stream);
 int sdk_tc_gemm_destroy(void* handle);
 /* stride-2 3x3 conv (unet.py:236): gather fp32 NHWC -> bf16 [B*Ho*Wo][9*C] rows, then a 1-tap sdk_tc_gemm */

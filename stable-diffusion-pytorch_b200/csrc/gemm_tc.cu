@@ -156,12 +156,20 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
     }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, (STAGES <= 3 || (BN <= 64 && STAGES <= 4)) ? 2 : 1)
+// TWO = cta_group::2: a CTA pair (cluster of 2 consecutive m-tiles) runs ONE 256 x BN MMA per K step.  Each CTA loads its
+// own 128 rows of A and HALF of the B tile (BN/2 rows), so a k-block costs 16 KiB + BN*64 B of L2->smem traffic per SM
+// instead of 16 KiB + BN*128 B; accumulator rows of each half live in that CTA's own TMEM.  Only the leader (rank 0)
+// issues MMAs; TMA completions of both CTAs are counted on the leader's "full" barrier, stage release and
+// accumulator-ready are multicast to both CTAs by tcgen05.commit.
+template <int BN, int STAGES, bool TWO>
+__global__ void __launch_bounds__(TC_THREADS, (!TWO && (STAGES <= 3 || (BN <= 64 && STAGES <= 4))) ? 2 : 1)
 conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
-    constexpr int B_STAGE_BYTES = BN * BK * 2;
+    constexpr int B_ROWS = TWO ? BN / 2 : BN;
+    constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
     constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM, BN);
+    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TWO ? 2 * BM : BM, BN);
+    const uint32_t rank = TWO ? ptx::cluster_ctarank() : 0u;
+    if (TWO) ptx::cluster_sync_all();                  // both CTAs resident before the paired TMEM allocation
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -187,7 +195,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     const int n_it = kb_end - kb_begin;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], TWO ? 2 : 1); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(tmem_full, 1);
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmA[0]);
@@ -195,11 +203,11 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         if (p.nseg > 1) { ptx::prefetch_tmap(&p.tmA[1]); ptx::prefetch_tmap(&p.tmB[1]); }
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (TWO) { ptx::tmem_alloc2(tmem_slot, TMEM_COLS); ptx::tmem_relinquish2(); }
+        else { ptx::tmem_alloc(tmem_slot, TMEM_COLS); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (TWO) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();          // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
@@ -218,6 +226,15 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 int dx = 0, dy = 0;
                 if (p.seg_ksize[seg] == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
                 ptx::mbar_wait(&empty[s], ph ^ 1u);
+                if (TWO) {
+                    const int nb = n0 + (int)rank * B_ROWS;              // this CTA's half of the B tile
+                    ptx::tma2_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 + dx, h0 + dy, b0);
+                    if (p.w_kmajor) ptx::tma2_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, nb, tap * p.seg_kb[seg] + kb);
+                    else ptx::tma2_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, nb);
+                    if (rank == 0) ptx::mbar_expect_tx(&full[s], 2u * stage_bytes);   // bytes of BOTH CTAs land on the leader's barrier
+                    else ptx::mbar_arrive_remote(&full[s], 0);
+                    continue;
+                }
                 ptx::mbar_expect_tx(&full[s], stage_bytes);
                 ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 + dx, h0 + dy, b0);
                 if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, tap * p.seg_kb[seg] + kb);
@@ -226,7 +243,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             for (int i = 0; i < n_it; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
@@ -235,11 +252,13 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 const uint64_t da = ptx::umma_smem_desc_sw128(ptx::smem_u32(sA + s * A_STAGE_BYTES));
                 const uint64_t db = ptx::umma_smem_desc_sw128(ptx::smem_u32(sB + s * B_STAGE_BYTES));
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)      // +32 B per K=16 step inside the 128 B swizzle atom
-                    ptx::umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (i > 0 || k > 0) ? 1u : 0u);
-                ptx::umma_commit(&empty[s]);           // frees the smem stage when these MMAs retire
+                for (int k = 0; k < BK / 16; ++k) {    // +32 B per K=16 step inside the 128 B swizzle atom
+                    if (TWO) ptx::umma2_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                    else ptx::umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                if (TWO) ptx::umma2_commit(&empty[s]); else ptx::umma_commit(&empty[s]);   // frees the smem stage when these MMAs retire
             }
-            ptx::umma_commit(tmem_full);               // accumulator complete
+            if (TWO) ptx::umma2_commit(tmem_full); else ptx::umma_commit(tmem_full);       // accumulator complete
         }
     } else {
         // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
@@ -322,10 +341,10 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (TWO) ptx::cluster_sync_all(); else __syncthreads();      // the peer's smem / TMEM stay valid until both are done
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (TWO) ptx::tmem_dealloc2(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -443,20 +462,29 @@ int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims,
 struct TcGemm {
     TcParams prm;
     int block_n, stages, smem_bytes;
-    bool co_resident;
+    bool co_resident, two_cta;
     dim3 grid;
     int64_t ws_bytes;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TWO = false>
 int launch_cfg(const TcGemm* g, cudaStream_t s) {
-    constexpr int smem = STAGES * (A_STAGE_BYTES + BN * BK * 2) + 1024 + 256 + ADD_ROWS * BN * 4;
+    constexpr int smem = STAGES * (A_STAGE_BYTES + (TWO ? BN / 2 : BN) * BK * 2) + 1024 + 256 + ADD_ROWS * BN * 4;
     static bool configured = false;
     if (!configured) {
-        SDK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SDK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    SDK_CUDA(sdk_launch(conv_gemm_tc_kernel<BN, STAGES>, dim3(g->grid), dim3(TC_THREADS), (size_t)(smem), s, g->prm));
+    if (TWO) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = g->grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        SDK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, TWO>, g->prm));
+    } else
+    SDK_CUDA(sdk_launch(conv_gemm_tc_kernel<BN, STAGES, TWO>, dim3(g->grid), dim3(TC_THREADS), (size_t)(smem), s, g->prm));
     SDK_LAUNCH_CHECK();
     if (g->prm.splits > 1) {
         const long long items = g->prm.M * ((g->prm.N + 3) / 4);
@@ -523,43 +551,52 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     // partial round trip through the second (reduce) kernel.
     const int sms = sdk_num_sms();
     int bn = d->block_n, splits = d->splits;
+    bool two = false;
     {
         const int cands[5] = {256, 160, 128, 64, 32};
         double best = 1e30;
         int best_bn = 0, best_sp = 1;
-        for (int i = 0; i < 5; ++i) {
-            const int c = cands[i];
-            if (d->block_n && c != d->block_n) continue;
-            if (!d->block_n) {
-                if (c >= 64 && d->N % c != 0 && d->N > c) continue;       // exact tilings only (all UNet widths are multiples of 160)
-                if (c > 32 && d->N <= c / 2) continue;                      // do not waste most of a tile on padding
-            }
-            const int n_t = (d->N + c - 1) / c;
-            const int tiles = m_tiles * n_t;
-            const int max_sp = d->splits ? d->splits : (p.total_kb / 4 > 0 ? (p.total_kb / 4 < 32 ? p.total_kb / 4 : 32) : 1);
-            for (int sp = (d->splits ? d->splits : 1); sp <= max_sp; ++sp) {
-                const int kb_cta = (p.total_kb + sp - 1) / sp;
-                const int real_sp = (p.total_kb + kb_cta - 1) / kb_cta;
-                if (real_sp != sp && !d->splits) continue;
-                const long long ctas = (long long)tiles * real_sp;
-                const long long waves = (ctas + sms - 1) / sms;
-                const double active = (double)(ctas < sms ? ctas : sms);
-                double feed = 6300.0 / active; if (feed > 46.0) feed = 46.0;        // B/clk per SM
-                const double stage_bytes = 16384.0 + c * 128.0;
-                double t_kb = stage_bytes / feed;
-                if (t_kb < 2.0 * c) t_kb = 2.0 * c;
-                const double t_epi = c * (d->geglu ? 24.0 : 8.0) * (real_sp > 1 ? 0.5 : 1.0);
-                double t = waves * (kb_cta * t_kb + 2500.0 + t_epi);
-                const double w_bytes = (double)p.total_kb * 64.0 * d->N * 2.0;
-                const double t_hbm = w_bytes / 3400.0 * 1.0;                         // ~6.5 TB/s at ~1.9 GHz = 3400 B/clk
-                if (t < t_hbm) t = t_hbm;
-                if (real_sp > 1) t += 9000.0 + (double)real_sp * p.M * d->N * 8.0 / 2500.0;
-                if (t < best) { best = t; best_bn = c; best_sp = real_sp; }
-                if (d->splits) break;
+        bool best_two = false;
+        for (int pair = 0; pair < 2; ++pair) {
+            // pair == 1: cta_group::2 (256-row CTA pairs): needs an even number of m-tiles
+            if (pair == 1 && (d->two_cta == 1 || (m_tiles & 1) || m_tiles < 2)) continue;
+            if (pair == 0 && d->two_cta == 2 && !(m_tiles & 1) && m_tiles >= 2) continue;
+            for (int i = 0; i < 5; ++i) {
+                const int c = cands[i];
+                if (pair == 1 && c < 128) continue;
+                if (d->block_n && c != d->block_n) continue;
+                if (!d->block_n) {
+                    if (c >= 64 && d->N % c != 0 && d->N > c) continue;       // exact tilings only (all UNet widths are multiples of 160)
+                    if (c > 32 && d->N <= c / 2) continue;                      // do not waste most of a tile on padding
+                }
+                const int n_t = (d->N + c - 1) / c;
+                const int tiles = m_tiles * n_t;
+                const int max_sp = d->splits ? d->splits : (p.total_kb / 4 > 0 ? (p.total_kb / 4 < 32 ? p.total_kb / 4 : 32) : 1);
+                for (int sp = (d->splits ? d->splits : 1); sp <= max_sp; ++sp) {
+                    const int kb_cta = (p.total_kb + sp - 1) / sp;
+                    const int real_sp = (p.total_kb + kb_cta - 1) / kb_cta;
+                    if (real_sp != sp && !d->splits) continue;
+                    if (pair == 1 && kb_cta < 8 && d->two_cta != 2) continue;  // pairing costs two cluster barriers: not for short K
+                    const long long ctas = (long long)tiles * real_sp;
+                    const long long waves = (ctas + sms - 1) / sms;
+                    const double active = (double)(ctas < sms ? ctas : sms);
+                    double feed = 6300.0 / active; if (feed > 46.0) feed = 46.0;        // B/clk per SM
+                    const double stage_bytes = 16384.0 + c * (pair ? 64.0 : 128.0);
+                    double t_kb = stage_bytes / feed;
+                    if (t_kb < 2.0 * c) t_kb = 2.0 * c;
+                    const double t_epi = c * (d->geglu ? 24.0 : 8.0) * (real_sp > 1 ? 0.5 : 1.0);
+                    double t = waves * (kb_cta * t_kb + 2500.0 + (pair ? 1500.0 : 0.0) + t_epi);
+                    const double w_bytes = (double)p.total_kb * 64.0 * d->N * 2.0;
+                    const double t_hbm = w_bytes / 3400.0 * 1.0;                         // ~6.5 TB/s at ~1.9 GHz = 3400 B/clk
+                    if (t < t_hbm) t = t_hbm;
+                    if (real_sp > 1) t += 9000.0 + (double)real_sp * p.M * d->N * 8.0 / 2500.0;
+                    if (t < best) { best = t; best_bn = c; best_sp = real_sp; best_two = pair == 1; }
+                    if (d->splits) break;
+                }
             }
         }
         if (best_bn == 0) { delete g; return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_create: no tile for N=%d block_n=%d", d->N, d->block_n); }
-        bn = best_bn; splits = best_sp;
+        bn = best_bn; splits = best_sp; two = best_two;
     }
     const int n_tiles = (d->N + bn - 1) / bn;
     if (splits < 1) splits = 1;
@@ -576,11 +613,11 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         if (rc != SDK_OK) break;
         if (d->w_kmajor) {
             const uint64_t bdims[3] = {(uint64_t)BK, (uint64_t)d->N, (uint64_t)p.seg_taps[s] * p.seg_kb[s]};
-            const uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)bn, 1u};
+            const uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)(two ? bn / 2 : bn), 1u};
             rc = encode_bf16(&p.tmB[s], d->w[s], 3, bdims, bbox, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         } else {
             const uint64_t bdims[2] = {(uint64_t)p.seg_taps[s] * d->C[s], (uint64_t)d->N};
-            const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)bn};
+            const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)(two ? bn / 2 : bn)};
             rc = encode_bf16(&p.tmB[s], d->w[s], 2, bdims, bbox, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         }
     }
@@ -591,7 +628,8 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     g->grid = dim3(m_tiles, n_tiles, splits);
     // short K per CTA: the fixed prologue/epilogue cost dominates -> shallow pipeline so that 2 CTAs share an SM and
     // one CTA's epilogue overlaps the other's main loop
-    g->co_resident = p.kb_per_split <= 12;
+    g->two_cta = two;
+    g->co_resident = !two && p.kb_per_split <= 12;
     g->ws_bytes = splits > 1 ? (int64_t)splits * p.M * d->N * 4 + 256 : 0;
     *handle = g;
     return SDK_OK;
@@ -616,6 +654,7 @@ extern "C" int sdk_tc_gemm_info(void* handle, int* out, int n) {
     TcGemm* g = (TcGemm*)handle;
     out[0] = g->block_n; out[1] = g->prm.splits; out[2] = g->grid.x; out[3] = g->grid.y;
     out[4] = g->prm.TW; out[5] = g->prm.TH; out[6] = g->prm.TB; out[7] = g->prm.total_kb;
+    if (n >= 9) out[8] = g->two_cta ? 2 : 1;
     return SDK_OK;
 }
 
@@ -624,6 +663,14 @@ extern "C" int sdk_tc_gemm_launch(void* handle, void* stream) {
     TcGemm* g = (TcGemm*)handle;
     SDK_CHECK_ARG(g->prm.splits == 1 || g->prm.partial, "sdk_tc_gemm_launch: workspace not set for split-K");
     cudaStream_t s = (cudaStream_t)stream;
+    if (g->two_cta) {
+        switch (g->block_n) {
+            case 128: return launch_cfg<128, 8, true>(g, s);
+            case 160: return launch_cfg<160, 8, true>(g, s);
+            case 256: return launch_cfg<256, 6, true>(g, s);
+        }
+        return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_launch: 2-CTA block_n %d", g->block_n);
+    }
     if (g->co_resident) {
         switch (g->block_n) {
             case 32: return launch_cfg<32, 4>(g, s);

@@ -229,7 +229,7 @@ class StepProgram:
         d.B, d.H, d.W, d.N = p.B, p.Hin, p.Win, p.N
         d.bias, d.tbias, d.tb_stride, d.residual, d.out = p.bias, p.tbias, p.tb_stride, p.residual, p.out
         d.out_dtype, d.geglu, d.out_nchw = p.out_dtype, p.geglu, p.out_nchw
-        d.block_n, d.splits, d.w_kmajor = self.net.tc_block_n, self.net.tc_splits, 1
+        d.block_n, d.splits, d.w_kmajor, d.two_cta = self.net.tc_block_n, self.net.tc_splits, 1, self.net.tc_two_cta
         h = C.c_void_p()
         _lib.check(self.lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
         self.tc_handles.append(h)
@@ -538,6 +538,7 @@ class UNet(nn.Module):
         self.precision = os.environ.get("SDB200_PRECISION", "bf16")
         self.tc_block_n = int(os.environ.get("SDB200_TC_BLOCK_N", "0"))      # 0 = auto; tuning / test overrides
         self.tc_splits = int(os.environ.get("SDB200_TC_SPLITS", "0"))
+        self.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
         self.gn_mode = os.environ.get("SDB200_GN_MODE", "split")           # split (stats+apply kernels, fastest measured) | cluster | coop | auto
         self.gn_cluster_max_bytes = int(os.environ.get("SDB200_GN_CLUSTER_MAX_BYTES", str(3 << 20)))
         self.use_cuda_graph = os.environ.get("SDB200_CUDA_GRAPH", "1") != "0"

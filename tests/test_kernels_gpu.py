@@ -168,6 +168,58 @@ def test_tc_gemm(dev, case, wk):
     assert e < (4e-3 if odt == BF16_T else 2e-5)
 
 
+TWO_CTA_CASES = [
+    # name, B, H, W, C, N, k, block_n, splits, tbias, residual, geglu, out_dtype
+    ("conv_L0_cg2", 2, 64, 64, 320, 320, 3, 160, 1, "one", True, False, F32_T),
+    ("conv_L1_cg2_splitk", 2, 32, 32, 640, 640, 3, 128, 2, None, False, False, F32_T),
+    ("lin_geglu_cg2", 1, 1, 2048, 640, 5120, 1, 256, 1, None, False, True, BF16_T),
+    ("lin_ragged_cg2", 1, 1, 200, 1280, 256, 1, 256, 1, None, True, False, F32_T),
+]
+
+
+@pytest.mark.parametrize("case", TWO_CTA_CASES, ids=[c[0] for c in TWO_CTA_CASES])
+def test_tc_gemm_cta_pair(dev, case):
+    """tcgen05 cta_group::2: CTA pairs run one 256-row MMA; same results as the 1-CTA path."""
+    name, B, H, W, Cc, N, k, bn, splits, tbm, res, geglu, odt = case
+    lib = _lib.lib()
+    a = gen((B, H, W, Cc), 81, dev).bfloat16()
+    w = gen((N, k * k * Cc), 82, dev, 1.0 / math.sqrt(k * k * Cc)).bfloat16()
+    bias = gen((N,), 83, dev, 0.1)
+    tb = None if tbm is None else gen((1, N), 84, dev)
+    Nout = N // 2 if geglu else N
+    resid = gen((B, H, W, Nout), 85, dev) if res else None
+    outs = []
+    for two in (2, 1):
+        out = torch.full((B, H, W, Nout), float("nan"), device=dev, dtype=torch.float32 if odt == F32_T else torch.bfloat16)
+        d = TcGemmDesc()
+        wp = kmajor(w)
+        d.w_kmajor, d.two_cta = 1, two
+        d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = a.data_ptr(), wp.data_ptr(), Cc, k, 1
+        d.B, d.H, d.W, d.N = B, H, W, N
+        d.bias = bias.data_ptr()
+        d.tbias, d.tb_stride = (tb.data_ptr() if tb is not None else 0), 0
+        d.residual, d.out = (resid.data_ptr() if res else 0), out.data_ptr()
+        d.out_dtype, d.geglu, d.block_n, d.splits = odt, int(geglu), bn, splits
+        h = C.c_void_p()
+        _lib.check(lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
+        info = (C.c_int * 9)()
+        _lib.check(lib.sdk_tc_gemm_info(h, info, 9))
+        assert info[8] == two
+        ws = torch.zeros(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=dev)
+        _lib.check(lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr()))
+        _lib.check(lib.sdk_tc_gemm_launch(h, stream()))
+        torch.cuda.synchronize()
+        lib.sdk_tc_gemm_destroy(h)
+        outs.append(out)
+    tbe = None if tb is None else tb.expand(B, N)
+    want = ref_conv([a], w, bias, k, 1, False, tbe, resid, geglu)
+    e = rel_l2(outs[0].float(), want)
+    print(f"{name}: cta_group::2 rel-L2 {e:.2e}")
+    assert not torch.isnan(outs[0].float()).any()
+    assert e < (4e-3 if odt == BF16_T else 2e-5)
+    assert torch.equal(outs[0], outs[1]), "2-CTA and 1-CTA paths accumulate in the same order"
+
+
 def test_tc_gemm_two_segments(dev):
     """conv_2 (3x3 over a2) + fused 1x1 shortcut over the raw concat input (unet.py:188-193)."""
     lib = _lib.lib()

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--splits", type=int, default=0)
     ap.add_argument("--only", default="")
     ap.add_argument("--rowmajor", action="store_true")
+    ap.add_argument("--two-cta", type=int, default=0)
     ap.add_argument("--warm", action="store_true", help="no L2 flush between launches; time 20 back-to-back launches")
     ap.add_argument("--shape", default="", help="custom: name,B,H,W,C,N,k")
     args = ap.parse_args()
@@ -60,14 +61,15 @@ def main():
         if not args.rowmajor:
             w = w.view(N, k * k * Cc // 64, 64).permute(1, 0, 2).contiguous()
         d.w_kmajor = 0 if args.rowmajor else 1
+        d.two_cta = args.two_cta
         d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = a.data_ptr(), w.data_ptr(), Cc, k, 1
         d.B, d.H, d.W, d.N = B, H, W, N
         d.bias, d.out = bias.data_ptr(), out.data_ptr()
         d.out_dtype, d.geglu, d.block_n, d.splits = (BF16_T if geglu else F32_T), int(geglu), args.block_n, args.splits
         h = C.c_void_p()
         _lib.check(lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
-        info = (C.c_int * 8)()
-        lib.sdk_tc_gemm_info(h, info, 8)
+        info = (C.c_int * 9)()
+        lib.sdk_tc_gemm_info(h, info, 9)
         ws = torch.zeros(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=dev)
         lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr())
         _lib.check(lib.sdk_tc_gemm_launch(h, stream))
@@ -92,7 +94,7 @@ def main():
         gf = 2.0 * B * H * W * N * k * k * Cc / 1e9
         wmb = N * k * k * Cc * 2 / 1e6
         us = min(ts)
-        print(f"{name:16s} bn={info[0]:3d} splits={info[1]:2d} grid=({info[2]},{info[3]}) tile=({info[4]},{info[5]},{info[6]}) "
+        print(f"{name:16s} cg={info[8]} bn={info[0]:3d} splits={info[1]:2d} grid=({info[2]},{info[3]}) tile=({info[4]},{info[5]},{info[6]}) "
               f"{gf:7.2f} GF  w={wmb:6.1f} MB  {us:8.1f} us  {gf / us * 1e3:7.1f} TF/s  w-stream {wmb / us * 1e3:7.1f} GB/s")
         lib.sdk_tc_gemm_destroy(h)
 
