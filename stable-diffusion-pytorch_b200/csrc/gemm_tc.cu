@@ -559,7 +559,9 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         bool best_two = false;
         for (int pair = 0; pair < 2; ++pair) {
             // pair == 1: cta_group::2 (256-row CTA pairs): needs an even number of m-tiles
-            if (pair == 1 && (d->two_cta == 1 || (m_tiles & 1) || m_tiles < 2)) continue;
+            // Measured on B200 (profiles/r01_gemm_pairs.txt): the pair form is 1-5 % SLOWER than two independent CTAs on every
+            // UNet shape (the 1-CTA kernel is not bound by the B-tile fill), so auto (0) never picks it; 2 forces it.
+            if (pair == 1 && (d->two_cta != 2 || (m_tiles & 1) || m_tiles < 2)) continue;
             if (pair == 0 && d->two_cta == 2 && !(m_tiles & 1) && m_tiles >= 2) continue;
             for (int i = 0; i < 5; ++i) {
                 const int c = cands[i];
