@@ -126,6 +126,14 @@ int sdk_attention_bf16(const void* q, int64_t q_row, int64_t q_batch, const void
                        const void* v, int64_t v_row, int64_t v_batch, void* out, int64_t o_row, int64_t o_batch,
                        int B, int heads, int Sq, int Sk, int D, float scale, void* stream);
 
+/* tcgen05 flash attention for head_dim 40 | 64 (S in TMEM, thread-per-row softmax, P V on the tensor core, operands by TMA
+ * from per-head 4-D tensor maps).  Plan object = the TMA descriptors; same stride contract as sdk_attention_bf16. */
+int sdk_attention_tc_create(const void* q, int64_t q_row, int64_t q_batch, const void* k, int64_t k_row, int64_t k_batch,
+                            const void* v, int64_t v_row, int64_t v_batch, void* out, int64_t o_row, int64_t o_batch,
+                            int B, int heads, int Sq, int Sk, int D, float scale, void** handle);
+int sdk_attention_tc_launch(void* handle, void* stream);
+int sdk_attention_tc_destroy(void* handle);
+
 /* ---- tcgen05 / TMEM / TMA implicit GEMM (bf16 operands, fp32 accumulate) -----------------------------
  * Same math as sdk_conv_gemm_f32 for stride-1 "same" convolutions (ksize 1|3) and linears, with up to two
  * (activation, weight) segments accumulated into one output (segment 1 = a fused 1x1 shortcut conv,

@@ -48,6 +48,10 @@ SIGNATURES = {
     "sdk_attention_f32": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, P],
     # --- attention_mma.cu
     "sdk_attention_bf16": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, P],
+    # --- attention_tc.cu
+    "sdk_attention_tc_create": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, P],
+    "sdk_attention_tc_launch": [P, P],
+    "sdk_attention_tc_destroy": [P],
     # --- gemm_tc.cu
     "sdk_tc_gemm_create": [P, P],
     "sdk_tc_gemm_workspace_bytes": [P],

@@ -1,0 +1,312 @@
+// tcgen05 flash attention for head dims <= 64 (SD-1.5 level 0: D = 40, S = 4096; SD-2.1: D = 64, S up to 9216):
+// out = softmax(q k^T * scale) v per (batch, head)   (models/unet/attention.py:29-50).
+//
+// CTA = 128 queries x one head; K/V stream in 128-key tiles.  Both contractions run on the 5th-gen tensor cores with
+// TMEM accumulators, operands fetched by TMA straight out of the fused [B][S][3C] qkv buffer:
+//   * per-head tiles come from 4-D tensor maps (d, head, token, batch) with a 64-wide box: for D = 40 the 24 columns
+//     past the head are OUT OF BOUNDS in the innermost dimension and arrive as zeros, so a 128-byte-swizzled
+//     [128][64] tile is exactly the zero-padded operand the MMA needs (no padding pass, no neighbour-head leakage).
+//   * S = Q K^T : A = Q (K-major), B = K tile (K-major), 128 x 128 fp32 in TMEM columns [0,128)
+//   * softmax  : thread = query row = TMEM lane; row max / exp2 / row sum need NO cross-thread traffic.
+//                P (bf16) is written to shared memory in the K-major SW128 layout = A operand of the second MMA.
+//   * PV       : A = P (smem), B = V tile used AS STORED ([key][d], d contiguous) through an MN-major descriptor,
+//                128 x 64 fp32 in TMEM columns [128,192); rows accumulate O in registers (O = O*corr + PV).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 softmax (128 threads).  Single-buffered
+// K, V, P, S: K(t+1) loads as soon as QK^T(t) retires, V(t+1) as soon as PV(t) retires; two CTAs per SM (80 KiB of
+// smem, 256 TMEM columns each) overlap one CTA's softmax with the other's MMAs.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <new>
+#include <string.h>
+
+namespace {
+
+constexpr int BQ = 128, BKV = 128, DP = 64, AT_THREADS = 192;
+constexpr int TILE_BYTES = 128 * DP * 2;             // 16 KiB: one [128][64] bf16 tile
+
+struct alignas(64) AttnParams {
+    CUtensorMap tmQ, tmK, tmV;
+    __nv_bfloat16* out; long long o_row, o_batch;
+    int heads, Sq, Sk, kv_bcast;
+    float scale_log2;
+};
+
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// MN-major SW128 operand: tile stored [K rows][64 MN elements] (128 B per K row), 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(TILE_BYTES >> 4) << 16;          // LBO: next 64-wide MN atom (unused: N = 64 is one atom)
+    d |= (uint64_t)(1024 >> 4) << 32;                // SBO: next group of 8 K rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ AttnParams p) {
+    constexpr int KS = (D + 15) / 16;                                  // K=16 steps of Q K^T (zero padded past D)
+    constexpr uint32_t IDESC_S = ptx::umma_idesc_bf16(128, BKV);       // 128 x 128, both operands K-major
+    constexpr uint32_t IDESC_O = ptx::umma_idesc_bf16(128, DP) | (1u << 16);   // 128 x 64, B (= V) MN-major
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TILE_BYTES;
+    uint8_t* sV = sK + TILE_BYTES;
+    uint8_t* sP = sV + TILE_BYTES;                                     // 2 x 16 KiB: keys [0,64) and [64,128)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
+    uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
+             *s_full = bars + 5, *p_full = bars + 6, *pv_full = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.y, b = bh / p.heads, h = bh - b * p.heads;
+    const int q0 = blockIdx.x * BQ;
+    const int kvb = p.kv_bcast ? 0 : b;
+    const int ntiles = (p.Sk + BKV - 1) / BKV;
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(q_full, 1); ptx::mbar_init(k_full, 1); ptx::mbar_init(k_empty, 1); ptx::mbar_init(v_full, 1);
+        ptx::mbar_init(v_empty, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, 128); ptx::mbar_init(pv_full, 1);
+        ptx::fence_barrier_init();
+        ptx::prefetch_tmap(&p.tmQ); ptx::prefetch_tmap(&p.tmK); ptx::prefetch_tmap(&p.tmV);
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_expect_tx(q_full, TILE_BYTES);
+            ptx::tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
+            for (int t = 0; t < ntiles; ++t) {
+                const uint32_t ph = (uint32_t)t & 1u;
+                ptx::mbar_wait(k_empty, ph ^ 1u);
+                ptx::mbar_expect_tx(k_full, TILE_BYTES);
+                ptx::tma_load_4d(sK, &p.tmK, k_full, 0, h, t * BKV, kvb);
+                ptx::mbar_wait(v_empty, ph ^ 1u);
+                ptx::mbar_expect_tx(v_full, TILE_BYTES);
+                ptx::tma_load_4d(sV, &p.tmV, v_full, 0, h, t * BKV, kvb);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint64_t dq = ptx::umma_smem_desc_sw128(ptx::smem_u32(sQ));
+            const uint64_t dk = ptx::umma_smem_desc_sw128(ptx::smem_u32(sK));
+            const uint64_t dp0 = ptx::umma_smem_desc_sw128(ptx::smem_u32(sP));
+            const uint64_t dp1 = ptx::umma_smem_desc_sw128(ptx::smem_u32(sP + TILE_BYTES));
+            const uint64_t dv = umma_desc_mn_sw128(ptx::smem_u32(sV));
+            ptx::mbar_wait(q_full, 0);
+            for (int t = 0; t < ntiles; ++t) {
+                const uint32_t ph = (uint32_t)t & 1u;
+                // ---- S = Q K^T   (S of the previous tile has been consumed: p_full(t-1) was waited before PV(t-1))
+                ptx::mbar_wait(k_full, ph);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < KS; ++k)
+                    ptx::umma_bf16(tmem_base, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), IDESC_S, k > 0 ? 1u : 0u);
+                ptx::umma_commit(k_empty);
+                ptx::umma_commit(s_full);
+                // ---- PV = P V
+                ptx::mbar_wait(p_full, ph);
+                ptx::mbar_wait(v_full, ph);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    const uint64_t da = (k < 4 ? dp0 : dp1) + (uint64_t)((k & 3) * 2);     // +32 B per 16 keys inside a 64-key atom
+                    const uint64_t db = dv + (uint64_t)(k * 16 * 128 >> 4);                // +16 key rows of 128 B
+                    ptx::umma_bf16(tmem_base + 128, da, db, IDESC_O, k > 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(v_empty);
+                ptx::umma_commit(pv_full);
+            }
+        }
+    } else {
+        // ================= softmax / output: thread = query row = TMEM lane =================
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
+        uint8_t* prow = sP + r * 128;
+        const int swz = r & 7;
+        float o[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) o[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int t = 0; t < ntiles; ++t) {
+            const uint32_t ph = (uint32_t)t & 1u;
+            ptx::mbar_wait(s_full, ph);
+            ptx::tc_fence_after();
+            const int kbase = t * BKV;
+            const bool ragged = kbase + BKV > p.Sk;
+            // pass 1: row max
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t u[32];
+                ptx::tmem_ld32(taddr + c * 32, u);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float s = __uint_as_float(u[j]);
+                    if (ragged && kbase + c * 32 + j >= p.Sk) s = -INFINITY;
+                    mx = fmaxf(mx, s);
+                }
+            }
+            const float m_new = fmaxf(m_run, mx);                    // finite: every tile holds >= 1 valid key
+            const float corr = ex2((m_run - m_new) * p.scale_log2);
+            const float msc = m_new * p.scale_log2;
+            m_run = m_new;
+            // pass 2: p = exp2(s*scale - m*scale), row sum, P -> smem (bf16, K-major SW128)
+            float ps = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t u[32];
+                ptx::tmem_ld32(taddr + c * 32, u);
+                ptx::tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float s0 = __uint_as_float(u[j]), s1 = __uint_as_float(u[j + 1]);
+                    if (ragged) {
+                        if (kbase + c * 32 + j >= p.Sk) s0 = -INFINITY;
+                        if (kbase + c * 32 + j + 1 >= p.Sk) s1 = -INFINITY;
+                    }
+                    const float p0 = ex2(fmaf(s0, p.scale_log2, -msc)), p1 = ex2(fmaf(s1, p.scale_log2, -msc));
+                    __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                    // the row sum uses the ROUNDED probabilities, i.e. exactly what the second MMA multiplies with V
+                    const float2 pf = __bfloat1622float2(pb);
+                    ps += pf.x + pf.y;
+                    pk[j >> 1] = *reinterpret_cast<uint32_t*>(&pb);
+                }
+                // 32 keys = 4 chunks of 16 B; chunk index within the 64-key atom: (c & 1) * 4 + i, XOR-swizzled by the row
+                uint8_t* atom = prow + (c >> 1) * TILE_BYTES;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int chunk = ((c & 1) * 4 + i) ^ swz;
+                    *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                }
+            }
+            l_run = l_run * corr + ps;
+            ptx::fence_proxy_async();                                // generic-proxy smem writes -> visible to the MMA (async proxy)
+            ptx::tc_fence_before();                                  // our TMEM reads of S are ordered before the arrive
+            ptx::mbar_arrive(p_full);
+            // O = O*corr + P V
+            ptx::mbar_wait(pv_full, ph);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < (D + 31) / 32; ++c) {
+                uint32_t u[32];
+                ptx::tmem_ld32(taddr + 128 + c * 32, u);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c * 32 + j < D) o[c * 32 + j] = fmaf(o[c * 32 + j], corr, __uint_as_float(u[j]));
+            }
+            ptx::tc_fence_before();
+        }
+        if (q0 + r < p.Sq) {
+            const float inv = 1.f / l_run;
+            __nv_bfloat16* op = p.out + (size_t)b * p.o_batch + (size_t)(q0 + r) * p.o_row + (size_t)h * D;
+#pragma unroll
+            for (int i = 0; i < D; i += 8) {
+                __nv_bfloat162 a = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv), b2 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
+                __nv_bfloat162 c2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv), d2 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
+                uint4 w;
+                w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b2);
+                w.z = *reinterpret_cast<uint32_t*>(&c2); w.w = *reinterpret_cast<uint32_t*>(&d2);
+                *reinterpret_cast<uint4*>(op + i) = w;
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 256); }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// (d, head, token, batch) view of a [B][S][row] bf16 buffer whose row holds `heads` heads of D elements
+int encode_heads(CUtensorMap* m, const void* base, int D, int heads, int S, int B, int64_t row, int64_t batch) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return sdk_fail(SDK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t gdim[4] = {(cuuint64_t)D, (cuuint64_t)heads, (cuuint64_t)S, (cuuint64_t)B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)D * 2, (cuuint64_t)row * 2, (cuuint64_t)(batch > 0 ? batch : (int64_t)S * row) * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)DP, 1u, 128u, 1u};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sdk_fail(SDK_ERR_CUDA, "cuTensorMapEncodeTiled(attention, D=%d heads=%d S=%d) failed with %d", D, heads, S, (int)r);
+    return SDK_OK;
+}
+
+struct AttnPlan { AttnParams prm; dim3 grid; int D; };
+
+template <int D>
+int launch(const AttnPlan* a, cudaStream_t s) {
+    constexpr int smem = 5 * TILE_BYTES + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        SDK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    SDK_CUDA(sdk_launch(attention_tc_kernel<D>, a->grid, dim3(AT_THREADS), (size_t)smem, s, a->prm));
+    return SDK_OK;
+}
+
+}  // namespace
+
+// Plan-style API (TMA descriptors are built once): strides in ELEMENTS as for sdk_attention_bf16; kv_batch == 0 broadcasts K/V.
+extern "C" int sdk_attention_tc_create(const void* q, int64_t q_row, int64_t q_batch, const void* k, int64_t k_row, int64_t k_batch,
+                                       const void* v, int64_t v_row, int64_t v_batch, void* out, int64_t o_row, int64_t o_batch,
+                                       int B, int heads, int Sq, int Sk, int D, float scale, void** handle) {
+    SDK_CHECK_ARG(q && k && v && out && handle, "sdk_attention_tc_create: null pointer");
+    SDK_CHECK_ARG(D == 40 || D == 64, "sdk_attention_tc_create: head_dim %d not in {40, 64}", D);
+    SDK_CHECK_ARG(B > 0 && heads > 0 && Sq > 0 && Sk > 0 && B * heads < 65536, "sdk_attention_tc_create: bad sizes");
+    SDK_CHECK_ARG((q_row % 8) == 0 && (k_row % 8) == 0 && (v_row % 8) == 0 && (q_batch % 8) == 0 && (k_batch % 8) == 0 && (v_batch % 8) == 0 &&
+                  (o_row % 8) == 0 && (o_batch % 8) == 0, "sdk_attention_tc_create: strides must keep rows 16-byte aligned");
+    SDK_CHECK_ARG((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0, "sdk_attention_tc_create: unaligned pointer");
+    SDK_CHECK_ARG((k_batch == 0) == (v_batch == 0), "sdk_attention_tc_create: k and v must broadcast together");
+    AttnPlan* a = new (std::nothrow) AttnPlan();
+    if (!a) return sdk_fail(SDK_ERR_CUDA, "out of host memory");
+    memset(&a->prm, 0, sizeof(a->prm));
+    int rc = encode_heads(&a->prm.tmQ, q, D, heads, Sq, B, q_row, q_batch);
+    const int kvB = k_batch == 0 ? 1 : B;
+    if (rc == SDK_OK) rc = encode_heads(&a->prm.tmK, k, D, heads, Sk, kvB, k_row, k_batch);
+    if (rc == SDK_OK) rc = encode_heads(&a->prm.tmV, v, D, heads, Sk, kvB, v_row, v_batch);
+    if (rc != SDK_OK) { delete a; return rc; }
+    a->prm.out = (__nv_bfloat16*)out; a->prm.o_row = o_row; a->prm.o_batch = o_batch;
+    a->prm.heads = heads; a->prm.Sq = Sq; a->prm.Sk = Sk; a->prm.kv_bcast = k_batch == 0;
+    a->prm.scale_log2 = scale * 1.4426950408889634f;
+    a->grid = dim3((Sq + BQ - 1) / BQ, B * heads);
+    a->D = D;
+    *handle = a;
+    return SDK_OK;
+}
+
+extern "C" int sdk_attention_tc_launch(void* handle, void* stream) {
+    SDK_CHECK_ARG(handle, "sdk_attention_tc_launch: null handle");
+    AttnPlan* a = (AttnPlan*)handle;
+    return a->D == 40 ? launch<40>(a, (cudaStream_t)stream) : launch<64>(a, (cudaStream_t)stream);
+}
+
+extern "C" int sdk_attention_tc_destroy(void* handle) {
+    delete (AttnPlan*)handle;
+    return SDK_OK;
+}

@@ -170,6 +170,7 @@ class StepProgram:
         self.pool = _Pool(dev)
         self.n_launch = 0
         self.tc_handles = []
+        self.attn_handles = []
 
         f32 = torch.float32
         # static I/O staging (graph-stable addresses)
@@ -272,7 +273,14 @@ class StepProgram:
 
     def _attention(self, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch, B, heads, Sq, Sk, D, Cc):
         out = self.pool.get(B * Sq, Cc, self.act)
-        es = 4 if self.act == F32_T else 2
+        if self.act != F32_T and D in (40, 64) and self.net.attn_tc:
+            # tcgen05 flash attention (S and P.V on the tensor core, thread-per-row softmax)
+            h = C.c_void_p()
+            _lib.check(self.lib.sdk_attention_tc_create(q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch,
+                                                        out.data_ptr(), Cc, Sq * Cc, B, heads, Sq, Sk, D, float(D ** -0.5), C.byref(h)))
+            self.attn_handles.append(h)
+            self._emit(self.lib.sdk_attention_tc_launch, h)
+            return out
         fn = self.lib.sdk_attention_f32 if self.act == F32_T else self.lib.sdk_attention_bf16
         self._emit(fn, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch,
                    out.data_ptr(), Cc, Sq * Cc, B, heads, Sq, Sk, D, float(D ** -0.5))
@@ -495,6 +503,8 @@ class StepProgram:
         try:
             for h in getattr(self, "tc_handles", []):
                 self.lib.sdk_tc_gemm_destroy(h)
+            for h in getattr(self, "attn_handles", []):
+                self.lib.sdk_attention_tc_destroy(h)
         except Exception:
             pass
 
@@ -538,6 +548,7 @@ class UNet(nn.Module):
         self.precision = os.environ.get("SDB200_PRECISION", "bf16")
         self.tc_block_n = int(os.environ.get("SDB200_TC_BLOCK_N", "0"))      # 0 = auto; tuning / test overrides
         self.tc_splits = int(os.environ.get("SDB200_TC_SPLITS", "0"))
+        self.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention for head_dim 40 / 64
         self.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
         self.gn_mode = os.environ.get("SDB200_GN_MODE", "split")           # split (stats+apply kernels, fastest measured) | cluster | coop | auto
         self.gn_cluster_max_bytes = int(os.environ.get("SDB200_GN_CLUSTER_MAX_BYTES", str(3 << 20)))

@@ -285,6 +285,47 @@ def test_attention(dev, case, mode):
     assert e < (2e-5 if mode == "f32" else 6e-3)
 
 
+ATT_TC_CASES = [(2, 8, 4096, 4096, 40), (1, 8, 1024, 77, 40), (2, 5, 2304, 2304, 64), (2, 8, 200, 333, 40), (1, 10, 576, 77, 64),
+                (3, 8, 128, 128, 40)]
+
+
+@pytest.mark.parametrize("case", ATT_TC_CASES)
+def test_attention_tc(dev, case):
+    """tcgen05 flash attention (head_dim 40 / 64) vs fp32 softmax(QK^T/sqrt(D))V on the bf16-rounded inputs."""
+    B, Hh, Sq, Sk, D = case
+    lib = _lib.lib()
+    Cc = Hh * D
+    dt = torch.bfloat16
+    if Sq == Sk:
+        qkv = gen((B, Sq, 3 * Cc), 91, dev).to(dt)
+        q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+        strides = (3 * Cc, Sq * 3 * Cc, 3 * Cc, Sk * 3 * Cc, 3 * Cc, Sk * 3 * Cc)
+    else:
+        q = gen((B, Sq, Cc), 92, dev).to(dt)
+        kv = gen((1, Sk, 2 * Cc), 93, dev).to(dt)                       # batch-broadcast context
+        k, v = kv[..., :Cc], kv[..., Cc:]
+        strides = (Cc, Sq * Cc, 2 * Cc, 0, 2 * Cc, 0)
+    out = torch.full((B, Sq, Cc), float("nan"), device=dev, dtype=dt)
+    h = C.c_void_p()
+    _lib.check(lib.sdk_attention_tc_create(q.data_ptr(), strides[0], strides[1], k.data_ptr(), strides[2], strides[3],
+                                           v.data_ptr(), strides[4], strides[5], out.data_ptr(), Cc, Sq * Cc, B, Hh, Sq, Sk, D,
+                                           float(D ** -0.5), C.byref(h)))
+    for _ in range(2):
+        _lib.check(lib.sdk_attention_tc_launch(h, stream()))
+    torch.cuda.synchronize()
+    lib.sdk_attention_tc_destroy(h)
+
+    def heads(t):
+        return t.float().expand(B, -1, -1).reshape(B, t.shape[1], Hh, D).permute(0, 2, 1, 3)
+
+    w = torch.softmax((heads(q) @ heads(k).transpose(-1, -2)) * D ** -0.5, dim=-1)
+    want = (w @ heads(v)).permute(0, 2, 1, 3).reshape(B, Sq, Cc)
+    e = rel_l2(out.float(), want)
+    print(f"attention tcgen05 {case}: rel-L2 {e:.2e}")
+    assert not torch.isnan(out.float()).any()
+    assert e < 6e-3
+
+
 @pytest.mark.parametrize("shape", [(2, 256, 320, 0), (2, 64, 1280, 640), (1, 4096, 640, 320), (3, 16, 2560, 0), (2, 1024, 960, 0)])
 @pytest.mark.parametrize("odt", [F32_T, BF16_T])
 def test_groupnorm(dev, shape, odt):

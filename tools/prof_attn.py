@@ -26,18 +26,26 @@ def main():
         out = torch.empty((B, Sq, Cc), device=dev, dtype=torch.bfloat16)
         args = (q.data_ptr(), Cc, Sq * Cc, kv.data_ptr(), 2 * Cc, Sk * 2 * Cc, kv.data_ptr() + Cc * 2, 2 * Cc, Sk * 2 * Cc,
                 out.data_ptr(), Cc, Sq * Cc, B, Hh, Sq, Sk, D, float(D ** -0.5), stream)
-        _lib.check(lib.sdk_attention_bf16(*args))
+        use_tc = os.environ.get("ATTN_TC", "0") == "1" and D in (40, 64)
+        if use_tc:
+            h = C.c_void_p()
+            _lib.check(lib.sdk_attention_tc_create(*args[:-1], C.byref(h)))
+            run = lambda: _lib.check(lib.sdk_attention_tc_launch(h, stream))
+        else:
+            run = lambda: _lib.check(lib.sdk_attention_bf16(*args))
+        run()
         torch.cuda.synchronize()
         ts = []
         for _ in range(5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _lib.check(lib.sdk_attention_bf16(*args))
+            run()
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
+        name = name + ("[tc]" if use_tc else "")
         gf = 4.0 * B * Hh * Sq * Sk * D / 1e9
-        print(f"{name:10s} B={B} H={Hh} Sq={Sq} Sk={Sk} D={D}: {min(ts):8.1f} us  {gf / min(ts) * 1e3:7.1f} TF/s  exps/us={B * Hh * Sq * Sk / min(ts) / 1e6:6.2f} G/s")
+        print(f"{name:14s} B={B} H={Hh} Sq={Sq} Sk={Sk} D={D}: {min(ts):8.1f} us  {gf / min(ts) * 1e3:7.1f} TF/s  exps/us={B * Hh * Sq * Sk / min(ts) / 1e6:6.2f} G/s")
 
 
 if __name__ == "__main__":
