@@ -7,11 +7,12 @@
 //     past the head are OUT OF BOUNDS in the innermost dimension and arrive as zeros, so a 128-byte-swizzled
 //     [128][64] tile is exactly the zero-padded operand the MMA needs (no padding pass, no neighbour-head leakage).
 //   * S = Q K^T : A = Q (K-major), B = K tile (K-major), 128 x 128 fp32 in TMEM columns [0,128)
-//   * softmax  : thread = query row = TMEM lane; row max / exp2 / row sum need NO cross-thread traffic.
+//   * softmax  : a query row = one TMEM lane, handled by two threads (64 keys each); the only cross-thread traffic is one
+//                float per tile (partial row max) through shared memory.
 //                P (bf16) is written to shared memory in the K-major SW128 layout = A operand of the second MMA.
 //   * PV       : A = P (smem), B = V tile used AS STORED ([key][d], d contiguous) through an MN-major descriptor,
 //                128 x 64 fp32 in TMEM columns [128,192); rows accumulate O in registers (O = O*corr + PV).
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 softmax (128 threads).  Single-buffered
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 softmax (two threads per row).  Single-buffered
 // K, V, P, S: K(t+1) loads as soon as QK^T(t) retires, V(t+1) as soon as PV(t) retires; two CTAs per SM (80 KiB of
 // smem, 256 TMEM columns each) overlap one CTA's softmax with the other's MMAs.
 #include "common.cuh"
@@ -21,7 +22,7 @@
 
 namespace {
 
-constexpr int BQ = 128, BKV = 128, DP = 64, AT_THREADS = 192;
+constexpr int BQ = 128, BKV = 128, DP = 64, AT_THREADS = 64 + 256;    // TMA warp, MMA warp, 8 softmax warps
 constexpr int TILE_BYTES = 128 * DP * 2;             // 16 KiB: one [128][64] bf16 tile
 
 struct alignas(64) AttnParams {
@@ -32,6 +33,7 @@ struct alignas(64) AttnParams {
 };
 
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float max3(float a, float b, float c) { float y; asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c)); return y; }
 
 // MN-major SW128 operand: tile stored [K rows][64 MN elements] (128 B per K row), 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
@@ -60,6 +62,7 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
     uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
              *s_full = bars + 5, *p_full = bars + 6, *pv_full = bars + 7;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* s_max = reinterpret_cast<float*>(bars + 10);               // [2 tile parities][2 halves][128 rows]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y, b = bh / p.heads, h = bh - b * p.heads;
@@ -69,7 +72,7 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
 
     if (threadIdx.x == 0) {
         ptx::mbar_init(q_full, 1); ptx::mbar_init(k_full, 1); ptx::mbar_init(k_empty, 1); ptx::mbar_init(v_full, 1);
-        ptx::mbar_init(v_empty, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, 128); ptx::mbar_init(pv_full, 1);
+        ptx::mbar_init(v_empty, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, 256); ptx::mbar_init(pv_full, 1);
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmQ); ptx::prefetch_tmap(&p.tmK); ptx::prefetch_tmap(&p.tmV);
     }
@@ -127,99 +130,107 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
             }
         }
     } else {
-        // ================= softmax / output: thread = query row = TMEM lane =================
+        // ================= softmax / output: TWO threads per query row (8 warps) =================
+        // warps 2..5 ("half 0") own keys [0,64) of every tile and output columns [0,32); warps 6..9 ("half 1") own keys
+        // [64,128) and output columns [32,D).  A warp may only touch TMEM lanes 32*(warp%4)..+31, so the two threads of
+        // row r sit in warps with equal warp%4.  Per tile the halves exchange one float (their partial row max) through
+        // shared memory; row sums are kept per half and combined once at the end.
         const int qd = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int r = qd * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
-        uint8_t* prow = sP + r * 128;
+        uint8_t* prow = sP + half * TILE_BYTES + r * 128;                 // this half's 64-key atom of P
         const int swz = r & 7;
-        float o[D];
+        constexpr int OD = 32;                                           // output columns held per thread (half 1 uses D - 32 of them)
+        const int my_d0 = half * 32;
+        const int my_nd = half == 0 ? (D < 32 ? D : 32) : D - 32;
+        float o[OD];
 #pragma unroll
-        for (int i = 0; i < D; ++i) o[i] = 0.f;
+        for (int i = 0; i < OD; ++i) o[i] = 0.f;
         float m_run = -INFINITY, l_run = 0.f;
         for (int t = 0; t < ntiles; ++t) {
             const uint32_t ph = (uint32_t)t & 1u;
             ptx::mbar_wait(s_full, ph);
             ptx::tc_fence_after();
-            const int kbase = t * BKV;
-            const bool ragged = kbase + BKV > p.Sk;
-            // pass 1: row max
+            const int kbase = t * BKV + half * 64;
+            const bool ragged = t * BKV + BKV > p.Sk;
+            uint32_t u[32];
+            // pass 1: partial row max over this half's 64 keys
             float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t u[32];
-                ptx::tmem_ld32(taddr + c * 32, u);
-                ptx::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float s = __uint_as_float(u[j]);
-                    if (ragged && kbase + c * 32 + j >= p.Sk) s = -INFINITY;
-                    mx = fmaxf(mx, s);
+            for (int c = 0; c < 2; ++c) {
+                ptx::tmem_ld32(taddr + half * 64 + c * 32, u);
+                ptx::tmem_ld_wait();
+                if (ragged) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (kbase + c * 32 + j >= p.Sk) ? -INFINITY : __uint_as_float(u[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) mx = max3(mx, __uint_as_float(u[j]), __uint_as_float(u[j + 1]));
                 }
             }
+            s_max[(ph * 2 + half) * 128 + r] = mx;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            mx = fmaxf(mx, s_max[(ph * 2 + (half ^ 1)) * 128 + r]);
             const float m_new = fmaxf(m_run, mx);                    // finite: every tile holds >= 1 valid key
             const float corr = ex2((m_run - m_new) * p.scale_log2);
             const float msc = m_new * p.scale_log2;
             m_run = m_new;
-            // pass 2: p = exp2(s*scale - m*scale), row sum, P -> smem (bf16, K-major SW128)
+            // pass 2: p = exp2(s*scale - m*scale), partial row sum, P -> smem (bf16, K-major SW128)
             float ps = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t u[32];
-                ptx::tmem_ld32(taddr + c * 32, u);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                ptx::tmem_ld32(taddr + half * 64 + c * 32, u);
                 ptx::tmem_ld_wait();
-                uint32_t pk[16];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float s0 = __uint_as_float(u[j]), s1 = __uint_as_float(u[j + 1]);
-                    if (ragged) {
-                        if (kbase + c * 32 + j >= p.Sk) s0 = -INFINITY;
-                        if (kbase + c * 32 + j + 1 >= p.Sk) s1 = -INFINITY;
+                for (int i = 0; i < 4; ++i) {                         // 4 chunks of 8 keys = 16 B each
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = i * 8 + jj * 2;
+                        float s0 = __uint_as_float(u[j]), s1 = __uint_as_float(u[j + 1]);
+                        if (ragged) {
+                            if (kbase + c * 32 + j >= p.Sk) s0 = -INFINITY;
+                            if (kbase + c * 32 + j + 1 >= p.Sk) s1 = -INFINITY;
+                        }
+                        const float p0 = ex2(fmaf(s0, p.scale_log2, -msc)), p1 = ex2(fmaf(s1, p.scale_log2, -msc));
+                        ps += p0 + p1;                               // fp32 row sum (rounding of P is zero-mean)
+                        __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                        pk[jj] = *reinterpret_cast<uint32_t*>(&pb);
                     }
-                    const float p0 = ex2(fmaf(s0, p.scale_log2, -msc)), p1 = ex2(fmaf(s1, p.scale_log2, -msc));
-                    __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                    // the row sum uses the ROUNDED probabilities, i.e. exactly what the second MMA multiplies with V
-                    const float2 pf = __bfloat1622float2(pb);
-                    ps += pf.x + pf.y;
-                    pk[j >> 1] = *reinterpret_cast<uint32_t*>(&pb);
-                }
-                // 32 keys = 4 chunks of 16 B; chunk index within the 64-key atom: (c & 1) * 4 + i, XOR-swizzled by the row
-                uint8_t* atom = prow + (c >> 1) * TILE_BYTES;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int chunk = ((c & 1) * 4 + i) ^ swz;
-                    *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                    const int chunk = (c * 4 + i) ^ swz;              // XOR-swizzled 16-byte slot inside the 128-byte row
+                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
             l_run = l_run * corr + ps;
             ptx::fence_proxy_async();                                // generic-proxy smem writes -> visible to the MMA (async proxy)
             ptx::tc_fence_before();                                  // our TMEM reads of S are ordered before the arrive
             ptx::mbar_arrive(p_full);
-            // O = O*corr + P V
+            // O = O*corr + P V   (this half's 32 output columns)
             ptx::mbar_wait(pv_full, ph);
             ptx::tc_fence_after();
+            ptx::tmem_ld32(taddr + 128 + my_d0, u);
+            ptx::tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < (D + 31) / 32; ++c) {
-                uint32_t u[32];
-                ptx::tmem_ld32(taddr + 128 + c * 32, u);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c * 32 + j < D) o[c * 32 + j] = fmaf(o[c * 32 + j], corr, __uint_as_float(u[j]));
-            }
+            for (int j = 0; j < OD; ++j) o[j] = fmaf(o[j], corr, __uint_as_float(u[j]));
             ptx::tc_fence_before();
         }
+        // combine the two halves' row sums, normalise, store
+        s_max[half * 128 + r] = l_run;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float inv = 1.f / (l_run + s_max[(half ^ 1) * 128 + r]);
         if (q0 + r < p.Sq) {
-            const float inv = 1.f / l_run;
-            __nv_bfloat16* op = p.out + (size_t)b * p.o_batch + (size_t)(q0 + r) * p.o_row + (size_t)h * D;
+            __nv_bfloat16* op = p.out + (size_t)b * p.o_batch + (size_t)(q0 + r) * p.o_row + (size_t)h * D + my_d0;
 #pragma unroll
-            for (int i = 0; i < D; i += 8) {
-                __nv_bfloat162 a = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv), b2 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
-                __nv_bfloat162 c2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv), d2 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
-                uint4 w;
-                w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b2);
-                w.z = *reinterpret_cast<uint32_t*>(&c2); w.w = *reinterpret_cast<uint32_t*>(&d2);
-                *reinterpret_cast<uint4*>(op + i) = w;
+            for (int i = 0; i < OD; i += 8) {
+                if (i < my_nd) {
+                    __nv_bfloat162 a = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv), b2 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
+                    __nv_bfloat162 c2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv), d2 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
+                    uint4 w;
+                    w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b2);
+                    w.z = *reinterpret_cast<uint32_t*>(&c2); w.w = *reinterpret_cast<uint32_t*>(&d2);
+                    *reinterpret_cast<uint4*>(op + i) = w;
+                }
             }
         }
     }
@@ -260,7 +271,7 @@ struct AttnPlan { AttnParams prm; dim3 grid; int D; };
 
 template <int D>
 int launch(const AttnPlan* a, cudaStream_t s) {
-    constexpr int smem = 5 * TILE_BYTES + 1024 + 256;
+    constexpr int smem = 5 * TILE_BYTES + 1024 + 256 + 4 * 128 * 4;
     static bool configured = false;
     if (!configured) {
         SDK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
