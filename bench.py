@@ -340,7 +340,16 @@ def main():
         gemm_gflop = GEMM_GFLOP_B2_SD15_64 * (ub / 2.0) if (cfg["arch"], cfg["hw"]) == ("sd15", 64) else None
         if gemm_gflop:
             ach = gemm_gflop / gemm_ms            # GFLOP / ms == TFLOP/s
-            roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+                    tj = json.load(f)
+                if ub == 2:                       # captured for UNet batch 2 only
+                    traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            except Exception:
+                pass
+            roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": traffic,
+                    "traffic_note": "DRAM bytes of all launches of the kernel in one step (ncu, cold L2 per launch): profiles/r01_gemm_traffic.json",
                     "kernel": "conv_gemm_tc_kernel (tcgen05 implicit GEMM), all launches of one step",
                     "launches_per_step": gemm_launches, "ms_per_step_in_kernel": gemm_ms, "share_of_step": gemm_ms / ms_step,
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"}
