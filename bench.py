@@ -184,6 +184,46 @@ def time_gemm_family(loop, iters=5, fns=None):
     return e0.elapsed_time(e1) / iters, len(ops)
 
 
+def torch_eager_on_gpu(cfg, sd, arch, dev, steps=8):
+    """The reference's op sequence (oracle port, SDPA attention as in attention.py:37-43) executed by STOCK PyTorch eager
+    kernels (cuDNN / cuBLAS / SDPA) on the same GPU: the 'library kernels on the same box' comparator of SURVEY 8(d)."""
+    from oracle import unet_oracle as UO
+    UO.USE_SDPA = True
+    out = {}
+    sd_d = {k: v.to(dev) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(1234)
+    lat = torch.randn((1, 4, cfg["hw"], cfg["hw"]), generator=g).to(dev)
+    ctx = torch.randn((2, 77, cfg["dctx"]), generator=g).to(dev)
+    t = torch.tensor([981], device=dev)
+    for name, ac in (("fp32_tf32", None), ("autocast_bf16", torch.bfloat16)):
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+        def step():
+            with torch.no_grad():
+                if ac is None:
+                    o = UO.unet_forward(sd_d, lat.repeat(2, 1, 1, 1), t, ctx, **arch)
+                else:
+                    with torch.autocast("cuda", dtype=ac):
+                        o = UO.unet_forward(sd_d, lat.repeat(2, 1, 1, 1), t, ctx, **arch)
+                u, c = o.float().chunk(2)
+                return u + 7.5 * (c - u)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"ms_per_step": ms, "images_per_s": 1.0 / (cfg["steps"] * ms * 1e-3)}
+    UO.USE_SDPA = False
+    del sd_d
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -196,6 +236,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also time each kernel class of one step as its own graph")
+    ap.add_argument("--no-torch-eager", action="store_true", help="skip timing the reference op sequence in stock PyTorch eager on this GPU")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch_per_gpu:
@@ -370,6 +411,11 @@ def main():
     }
     if breakdown:
         line["breakdown_ms_per_step"] = breakdown
+    if not args.no_torch_eager and cfg["cfg"] and world == 1:
+        try:
+            line["torch_eager_same_gpu"] = torch_eager_on_gpu(cfg, sd, arch, dev)
+        except Exception as ex:
+            line["torch_eager_same_gpu"] = {"error": repr(ex)}
     if not args.no_cpu_baseline and world >= 1:
         try:
             sec, used = cpu_loop_body_seconds(cfg, sd, arch, cfg["hw"], 2, budget_s=45)

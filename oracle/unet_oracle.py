@@ -128,7 +128,7 @@ def make_state_dict(seed: int = 0, **cfg) -> Dict[str, torch.Tensor]:
 def time_embedding(sd, timestep, t_embed_dim=320):
     """unet.py:209-220: [cos(t f), sin(t f)], f_i = exp(-ln(1e4) i/half); Linear-SiLU-Linear."""
     half = t_embed_dim // 2
-    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=timestep.device) / half)
     x = timestep[:, None].float() * freqs[None, :]
     e = torch.cat([torch.cos(x), torch.sin(x)], dim=-1)
     h = Fn.linear(e, sd["time_embedding.ffn.0.weight"], sd["time_embedding.ffn.0.bias"])
@@ -148,6 +148,9 @@ def resblock(sd, p, x, t_embed, eps=1e-5):
     return h + x
 
 
+USE_SDPA = False     # bench.py's "stock PyTorch eager on the same GPU" comparator sets this (the reference calls SDPA, attention.py:37-43)
+
+
 def attention(sd, p, x, cond, heads):
     """unet/attention.py:29-50,70-87: no q/k/v bias, softmax(q k^T / sqrt(D)) v per head, out bias."""
     ctx = x if cond is None else cond
@@ -161,8 +164,11 @@ def attention(sd, p, x, cond, heads):
         return t.view(t.shape[0], t.shape[1], heads, d).permute(0, 2, 1, 3)
 
     q, k, v = split(q), split(k), split(v)
-    w = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5), dim=-1)
-    o = (w @ v).transpose(1, 2).reshape(b, s, c)
+    if USE_SDPA:
+        o = Fn.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, s, c)
+    else:
+        w = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5), dim=-1)
+        o = (w @ v).transpose(1, 2).reshape(b, s, c)
     return Fn.linear(o, sd[f"{p}.out_proj.weight"], sd[f"{p}.out_proj.bias"])
 
 
