@@ -35,6 +35,8 @@ int sdk_version(void);
 int sdk_device_info(int* out, int n);
 /* programmatic dependent launch for all kernels (1 = on; default off): kernel N+1's prologue overlaps kernel N's tail */
 int sdk_set_pdl(int enabled);
+/* 1: all kernels request the max-shared-memory L1 carve-out (0 = driver heuristic, default; measured no difference) */
+int sdk_set_uniform_carveout(int enabled);
 
 /* ---- sampler: fused CFG blend + scheduler update (models/diffusion.py:233-236) ------------------
  * coef_table: [T][8] fp32 per-timestep scalars built by the host sampler; the timestep is read from
@@ -162,6 +164,8 @@ int sdk_tc_gemm_set_workspace(void* handle, void* workspace);   /* zeroed once b
 int sdk_tc_gemm_info(void* handle, int* out, int n);            /* block_n, splits, grid.x, grid.y, TW, TH, TB, k-blocks [, cta group size if n >= 9] */
 int sdk_tc_gemm_launch(void* handle, void* stream);
 int sdk_tc_gemm_destroy(void* handle);
+/* developer aid: record 7 %globaltimer stamps of CTA (0,0,0) into device memory stamps[8] (NULL = off) */
+int sdk_tc_gemm_set_debug(void* handle, void* stamps);
 /* stride-2 3x3 conv (unet.py:236): gather fp32 NHWC -> bf16 [B*Ho*Wo][9*C] rows, then a 1-tap sdk_tc_gemm */
 int sdk_im2col_s2(const float* src, void* dst, int B, int H, int W, int C, void* stream);
 

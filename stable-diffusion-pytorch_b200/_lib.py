@@ -59,10 +59,12 @@ SIGNATURES = {
     "sdk_tc_gemm_info": [P, P, I32],
     "sdk_tc_gemm_launch": [P, P],
     "sdk_tc_gemm_destroy": [P],
+    "sdk_tc_gemm_set_debug": [P, P],
     "sdk_im2col_s2": [P, P, I32, I32, I32, I32, P],
     # --- misc
     "sdk_device_info": [P, I32],
     "sdk_set_pdl": [I32],
+    "sdk_set_uniform_carveout": [I32],
 }
 
 
@@ -110,6 +112,7 @@ def lib():
                 fn.argtypes = argtypes
                 fn.restype = RESTYPES.get(name, C.c_int)
             h.sdk_set_pdl(1 if os.environ.get("SDB200_PDL", "0") == "1" else 0)
+            h.sdk_set_uniform_carveout(1 if os.environ.get("SDB200_UNIFORM_CARVEOUT", "0") == "1" else 0)
             _lib = h
     return _lib
 

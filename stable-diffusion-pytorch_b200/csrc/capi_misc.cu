@@ -13,6 +13,19 @@ int sdk_fail(int code, const char* fmt, ...) {
     return code;
 }
 
+#include <mutex>
+#include <unordered_set>
+static int g_carveout = 0;   // measured: no effect on the step time (5.51 vs 5.49 ms) -> off by default
+void sdk_prefer_max_smem_once(const void* fn) {
+    static std::mutex mu;
+    static std::unordered_set<const void*> seen;
+    if (!g_carveout) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (seen.insert(fn).second) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+// 1: every kernel prefers the max-shared carve-out; 0 (default): leave the driver's per-kernel heuristic
+extern "C" int sdk_set_uniform_carveout(int enabled) { g_carveout = enabled ? 1 : 0; return SDK_OK; }
+
 static int g_pdl = 0;   // measured on B200 inside CUDA graphs: -3.5 % with early triggers -> off by default
 bool sdk_pdl_enabled() { return g_pdl != 0; }
 // enable (1) / disable (0, default) programmatic dependent launch for all subsequent launches

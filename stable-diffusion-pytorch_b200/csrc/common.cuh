@@ -68,6 +68,9 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool sdk_pdl_enabled();
+// one-time per kernel: ask for the max-shared-memory L1 carve-out so that the SM configuration does not flip between the
+// big-smem tensor-core kernels and the small elementwise kernels that run in between (a carve-out change drains the SM)
+void sdk_prefer_max_smem_once(const void* fn);
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t sdk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
@@ -77,6 +80,7 @@ static inline cudaError_t sdk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 b
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = sdk_pdl_enabled() ? 1 : 0;
+    sdk_prefer_max_smem_once(reinterpret_cast<const void*>(kernel));
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -43,7 +43,16 @@ struct alignas(64) TcParams {
     const float* bias; const float* tbias; long long tb_stride; const float* residual;
     void* out; int out_dtype, geglu, out_nchw;
     float* partial; long long M;
+    unsigned long long* dbg;     // optional [8] %globaltimer stamps of CTA (0,0,0) (tools/prof_gemm.py --stamps)
 };
+
+__device__ __forceinline__ void stamp(const TcParams& p, int slot) {
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg[slot] = t;
+    }
+}
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* v) {
     __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
@@ -179,9 +188,11 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    float* s_add = reinterpret_cast<float*>(tmem_slot + 4);        // [ADD_ROWS][BN]: bias + time-bias of the tile's samples
+    // [ADD_ROWS][BN]: bias + time-bias of the tile's samples (16-byte aligned: read as float4)
+    float* s_add = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) stamp(p, 0);
 
     // ---- tile coordinates
     int t = blockIdx.x;
@@ -211,6 +222,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();          // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+    if (threadIdx.x == 0) stamp(p, 1);
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -249,6 +261,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
+                if (i == 0) stamp(p, 2);
                 const uint64_t da = ptx::umma_smem_desc_sw128(ptx::smem_u32(sA + s * A_STAGE_BYTES));
                 const uint64_t db = ptx::umma_smem_desc_sw128(ptx::smem_u32(sB + s * B_STAGE_BYTES));
 #pragma unroll
@@ -259,6 +272,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 if (TWO) ptx::umma2_commit(&empty[s]); else ptx::umma_commit(&empty[s]);   // frees the smem stage when these MMAs retire
             }
             if (TWO) ptx::umma2_commit(tmem_full); else ptx::umma_commit(tmem_full);       // accumulator complete
+            stamp(p, 3);
         }
     } else {
         // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
@@ -286,40 +300,90 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        const float* my_add = staged ? s_add + tb_i * BN : nullptr;
-        // residual prefetch (plain NHWC epilogue, full chunks): chunk c+1 is in flight while chunk c is finished
-        const bool rpf = p.splits == 1 && p.residual && valid && !p.geglu && !p.out_nchw && (n0 + BN <= p.N);
-        float4 rcur[8], rnext[8];
-        if (rpf) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rcur[j] = __ldg(reinterpret_cast<const float4*>(p.residual + grow * p.N + n0) + j);
-        }
+        // Coalesced epilogue.  TMEM hands every thread ONE ROW (32 consecutive columns per load); storing that directly
+        // makes each warp store instruction hit 32 different 128-byte lines with 16 bytes each (5120 LSU transactions
+        // per 128x160 tile = 4.5 us measured).  Instead each warp transposes its 32x32 sub-tile through a private
+        // shared-memory patch (the pipeline stages are free once the accumulator is complete) and then writes 4 full
+        // rows x 128 B per instruction; residual reads and split-K partial writes use the same mapping.
+        constexpr int PITCH = 36;                                        // floats per staged row (32 + 4: 16-byte aligned, conflict-light)
+        float* stg = reinterpret_cast<float*>(sA) + (warp - 2) * 32 * PITCH;
+        const int sub_r = lane >> 3, c4 = (lane & 7) << 2;               // store mapping: 4 rows x 8 float4 per instruction
+        const bool fast = !p.out_nchw && (n0 + BN <= p.N);               // full tile of an NHWC output: the common case
 
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
-        if (p.splits == 1) {
+        if (threadIdx.x == 64) stamp(p, 4);
+        if (fast) {
+            const int Nout = p.Nout;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t u[32];
                 ptx::tmem_ld32(taddr + c * 32, u);
-                if (rpf && c + 1 < BN / 32) {
+                ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) rnext[j] = __ldg(reinterpret_cast<const float4*>(p.residual + grow * p.N + n0 + (c + 1) * 32) + j);
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * PITCH + j) =
+                        make_float4(__uint_as_float(u[j]), __uint_as_float(u[j + 1]), __uint_as_float(u[j + 2]), __uint_as_float(u[j + 3]));
+                __syncwarp();
+                const int ncol = n0 + c * 32 + c4;                        // absolute GEMM column of this lane's float4
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = q * 32 + it * 4 + sub_r;              // tile row handled by this lane in this iteration
+                    const int tw2 = rr % p.TW, th2 = (rr / p.TW) % p.TH, tb2 = rr / (p.TW * p.TH);
+                    const int ox2 = w0 + tw2, oy2 = h0 + th2, b2 = b0 + tb2;
+                    if (!(rr < p.rows && ox2 < p.W && oy2 < p.H && b2 < p.B)) continue;
+                    const long long grow2 = ((long long)b2 * p.H + oy2) * p.W + ox2;
+                    float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + sub_r) * PITCH + c4);
+                    if (p.splits > 1) {                                   // raw partial sums [split][M][N]
+                        __stcg(reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.z * p.M + (size_t)grow2) * p.N + ncol), x);
+                        continue;
+                    }
+                    if (staged) {
+                        const float4 ad = *reinterpret_cast<const float4*>(s_add + tb2 * BN + c * 32 + c4);
+                        x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w;
+                    } else {
+                        if (p.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + ncol)); x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w; }
+                        if (p.tbias) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(p.tbias + (long long)b2 * p.tb_stride + ncol));
+                            x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+                        }
+                    }
+                    if (p.geglu) {                                        // (value, gate) pairs -> 2 outputs per float4
+                        const long long off = grow2 * Nout + (ncol >> 1);
+                        float o0 = x.x * gelu_erf_f(x.y), o1 = x.z * gelu_erf_f(x.w);
+                        if (p.residual) { const float2 r2 = __ldg(reinterpret_cast<const float2*>(p.residual + off)); o0 += r2.x; o1 += r2.y; }
+                        if (p.out_dtype == SDK_BF16) *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)p.out + off) = __floats2bfloat162_rn(o0, o1);
+                        else *reinterpret_cast<float2*>((float*)p.out + off) = make_float2(o0, o1);
+                    } else {
+                        const long long off = grow2 * p.N + ncol;
+                        if (p.residual) { const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + off)); x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w; }
+                        if (p.out_dtype == SDK_BF16) {
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                            uint2 w2; w2.x = *reinterpret_cast<unsigned*>(&lo); w2.y = *reinterpret_cast<unsigned*>(&hi);
+                            *reinterpret_cast<uint2*>((__nv_bfloat16*)p.out + off) = w2;
+                        } else {
+                            *reinterpret_cast<float4*>((float*)p.out + off) = x;
+                        }
+                    }
                 }
+                __syncwarp();                                             // patch is rewritten by the next chunk
+            }
+        } else if (p.splits == 1) {
+            const float* my_add = staged ? s_add + tb_i * BN : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t u[32];
+                ptx::tmem_ld32(taddr + c * 32, u);
                 ptx::tmem_ld_wait();
                 if (valid) {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
-                    epilogue_chunk(p, v, n0 + c * 32, grow, b, oy, ox, my_add ? my_add + c * 32 : nullptr, rpf ? rcur : nullptr);
-                }
-                if (rpf) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
+                    epilogue_chunk(p, v, n0 + c * 32, grow, b, oy, ox, my_add ? my_add + c * 32 : nullptr, nullptr);
                 }
             }
         } else {
-            // split-K: raw fp32 partial sums, row-major [split][M][N]; reduced by splitk_reduce_kernel
+            // split-K with a ragged N tile or NCHW output: per-thread rows
             float* mine = p.partial + ((size_t)blockIdx.z * p.M + (size_t)(valid ? grow : 0)) * p.N + n0;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
@@ -340,8 +404,10 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
             }
         }
     }
+    if (threadIdx.x == 64) stamp(p, 5);
     ptx::tc_fence_before();
     if (TWO) ptx::cluster_sync_all(); else __syncthreads();      // the peer's smem / TMEM stay valid until both are done
+    if (threadIdx.x == 0) stamp(p, 6);
     if (warp == 1) {
         ptx::tc_fence_after();
         if (TWO) ptx::tmem_dealloc2(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -690,6 +756,14 @@ extern "C" int sdk_tc_gemm_launch(void* handle, void* stream) {
         case 256: return launch_cfg<256, 4>(g, s);
     }
     return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_launch: block_n %d", g->block_n);
+}
+
+// developer aid: stamps[0..6] = %globaltimer (ns) of CTA (0,0,0) at entry / prologue done / first operands landed /
+// last MMA issued / accumulator ready / epilogue done / after the final barrier
+extern "C" int sdk_tc_gemm_set_debug(void* handle, void* stamps) {
+    SDK_CHECK_ARG(handle, "sdk_tc_gemm_set_debug: null handle");
+    ((TcGemm*)handle)->prm.dbg = (unsigned long long*)stamps;
+    return SDK_OK;
 }
 
 extern "C" int sdk_tc_gemm_destroy(void* handle) {

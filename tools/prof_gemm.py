@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--rowmajor", action="store_true")
     ap.add_argument("--two-cta", type=int, default=0)
+    ap.add_argument("--stamps", action="store_true", help="print in-kernel %%globaltimer stamps of CTA (0,0,0)")
     ap.add_argument("--warm", action="store_true", help="no L2 flush between launches; time 20 back-to-back launches")
     ap.add_argument("--shape", default="", help="custom: name,B,H,W,C,N,k")
     args = ap.parse_args()
@@ -74,6 +75,17 @@ def main():
         lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr())
         _lib.check(lib.sdk_tc_gemm_launch(h, stream))
         torch.cuda.synchronize()
+        if args.stamps:
+            st = torch.zeros(8, dtype=torch.int64, device=dev)
+            lib.sdk_tc_gemm_set_debug(h, st.data_ptr())
+            for _ in range(3):
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); _lib.check(lib.sdk_tc_gemm_launch(h, stream)); e1.record()
+                torch.cuda.synchronize()
+                v = st.tolist()
+                print("   stamps (ns since entry): prologue %d | operands landed %d | last MMA issued %d | accumulator ready %d | epilogue done %d | exit %d ; event time %.1f us"
+                      % tuple([v[i] - v[0] for i in range(1, 7)] + [e0.elapsed_time(e1) * 1e3]))
+            lib.sdk_tc_gemm_set_debug(h, 0)
         ts = []
         if args.warm:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
