@@ -11,8 +11,13 @@
 //   directly through shared-memory descriptors; the fp32 accumulator lives in TMEM (BN columns).
 // * A second (A, W) segment accumulates into the same TMEM tile (ResBlock 1x1 shortcut fused into conv_2).
 // * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM owner, warps 2..5 =
-//   epilogue (tcgen05.ld 32 lanes x 32 columns -> bias / time-bias / residual / GEGLU -> global).
+//   epilogue (tcgen05.ld 32 lanes x 32 columns -> bias / time-bias / residual / GEGLU).
 //   smem stages are recycled through full/empty mbarriers (tcgen05.commit releases a stage).
+// * Epilogue output leaves through TMA: the finished 128 x 32-column chunk is written to shared memory in the
+//   swizzled layout of a 5-D output tensor map {N, W, H, B, split} and ONE thread issues the tensor store; the
+//   residual tile arrives the same way (TMA load, prefetched while the main loop runs).  Measured on B200
+//   (tools/ubench/store_bw.cu): an SM drains a 128x160 fp32 tile in 1.5 us through TMA, 2.5 us with coalesced
+//   STG.128 from 4 warps, 3.8 us with the thread-per-row stores tcgen05.ld's layout suggests.
 // * Weights are stored k-block-major [K/64][N][64] so that a CTA's B stage is ONE contiguous BN*128-byte
 //   run of HBM (sequential DRAM pages) instead of BN 128-byte pieces 2*K bytes apart.
 // * Small-M layers (deep UNet levels at small batch) are weight-streaming bound: split-K over
@@ -43,6 +48,11 @@ struct alignas(64) TcParams {
     const float* bias; const float* tbias; long long tb_stride; const float* residual;
     void* out; int out_dtype, geglu, out_nchw;
     float* partial; long long M;
+    // TMA epilogue (epi_tma): 5-D output map {Nout, W, H, B, split} (direct output, or the split-K partial planes) and the
+    // fp32 residual map of the same geometry; smem rows are epi_rowbytes wide, 16-byte units XOR-swizzled with epi_swz.
+    CUtensorMap tmOut, tmRes;
+    int epi_tma, epi_res, epi_rowbytes, epi_swz, epi_buf_stride, epi_cols;
+    int stages;
     unsigned long long* dbg;     // optional [8] %globaltimer stamps of CTA (0,0,0) (tools/prof_gemm.py --stamps)
 };
 
@@ -170,24 +180,33 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
 // instead of 16 KiB + BN*128 B; accumulator rows of each half live in that CTA's own TMEM.  Only the leader (rank 0)
 // issues MMAs; TMA completions of both CTAs are counted on the leader's "full" barrier, stage release and
 // accumulator-ready are multicast to both CTAs by tcgen05.commit.
-template <int BN, int STAGES, bool TWO>
-__global__ void __launch_bounds__(TC_THREADS, (!TWO && (STAGES <= 3 || (BN <= 64 && STAGES <= 4))) ? 2 : 1)
+constexpr int MAX_STAGES = 8;
+constexpr int EPI_BUFS = 3;                          // output staging ring (one named barrier per chunk needs three buffers)
+constexpr int RES_BUF_BYTES = BM * 128;              // one residual chunk: <= 128 rows x 32 fp32
+
+template <int BN, bool TWO>
+__global__ void __launch_bounds__(TC_THREADS, TWO ? 1 : 2)
 conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int B_ROWS = TWO ? BN / 2 : BN;
     constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
+    constexpr int NCH = BN / 32;
     constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(TWO ? 2 * BM : BM, BN);
     const uint32_t rank = TWO ? ptx::cluster_ctarank() : 0u;
     if (TWO) ptx::cluster_sync_all();                  // both CTAs resident before the paired TMEM allocation
+    const int STAGES = p.stages;
 
+    // shared memory: [A stages][B stages][2 residual chunks (only with a TMA residual)][barriers][s_add]
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint8_t* sRes = sB + STAGES * B_STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (p.epi_res ? 2 * RES_BUF_BYTES : 0));
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* tmem_full = empty + MAX_STAGES;
+    uint64_t* res_full = tmem_full + 1;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
     // [ADD_ROWS][BN]: bias + time-bias of the tile's samples (16-byte aligned: read as float4)
     float* s_add = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
 
@@ -208,10 +227,13 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], TWO ? 2 : 1); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(tmem_full, 1);
+        ptx::mbar_init(&res_full[0], 1); ptx::mbar_init(&res_full[1], 1);
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmA[0]);
         ptx::prefetch_tmap(&p.tmB[0]);
         if (p.nseg > 1) { ptx::prefetch_tmap(&p.tmA[1]); ptx::prefetch_tmap(&p.tmB[1]); }
+        if (p.epi_tma) ptx::prefetch_tmap(&p.tmOut);
+        if (p.epi_res) ptx::prefetch_tmap(&p.tmRes);
     }
     if (warp == 1) {
         if (TWO) { ptx::tmem_alloc2(tmem_slot, TMEM_COLS); ptx::tmem_relinquish2(); }
@@ -229,9 +251,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         if (lane == 0) {
             const uint32_t stage_bytes = (uint32_t)p.rows * (BK * 2) + (uint32_t)B_STAGE_BYTES;
             const int seg0_its = p.seg_taps[0] * p.seg_kb[0];
+            int s = 0; uint32_t ph = 0;
             for (int i = 0; i < n_it; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 int it = kb_begin + i, seg = 0;
                 if (it >= seg0_its) { it -= seg0_its; seg = 1; }
                 const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
@@ -245,20 +266,20 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                     else ptx::tma2_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, nb);
                     if (rank == 0) ptx::mbar_expect_tx(&full[s], 2u * stage_bytes);   // bytes of BOTH CTAs land on the leader's barrier
                     else ptx::mbar_arrive_remote(&full[s], 0);
-                    continue;
+                } else {
+                    ptx::mbar_expect_tx(&full[s], stage_bytes);
+                    ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 + dx, h0 + dy, b0);
+                    if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, tap * p.seg_kb[seg] + kb);
+                    else ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, n0);
                 }
-                ptx::mbar_expect_tx(&full[s], stage_bytes);
-                ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 + dx, h0 + dy, b0);
-                if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, tap * p.seg_kb[seg] + kb);
-                else ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, n0);
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0 && rank == 0) {
+            int s = 0; uint32_t ph = 0;
             for (int i = 0; i < n_it; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
                 if (i == 0) stamp(p, 2);
@@ -270,6 +291,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                     else ptx::umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 if (TWO) ptx::umma2_commit(&empty[s]); else ptx::umma_commit(&empty[s]);   // frees the smem stage when these MMAs retire
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
             if (TWO) ptx::umma2_commit(tmem_full); else ptx::umma_commit(tmem_full);       // accumulator complete
             stamp(p, 3);
@@ -278,17 +300,26 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
         const int q = warp & 3;
         const int r = q * 32 + lane;                    // tile row == TMEM lane
+        const int et = threadIdx.x - 64;                // 0..127 within the epilogue warps
         const int tw_i = r % p.TW, th_i = (r / p.TW) % p.TH, tb_i = r / (p.TW * p.TH);
         const int ox = w0 + tw_i, oy = h0 + th_i, b = b0 + tb_i;
         const bool valid = r < p.rows && ox < p.W && oy < p.H && b < p.B;
         const long long grow = ((long long)b * p.H + oy) * p.W + ox;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool epi_direct = p.epi_tma && p.splits == 1;    // TMA epilogue with the full bias/residual/activation
 
+        // residual chunks 0 and 1 start travelling now (dedicated buffers: the pipeline stages are still in use)
+        if (p.epi_res && et == 0) {
+#pragma unroll
+            for (int c = 0; c < (NCH < 2 ? NCH : 2); ++c) {
+                ptx::mbar_expect_tx(&res_full[c], (uint32_t)p.rows * 128u);
+                ptx::tma_load_4d(sRes + c * RES_BUF_BYTES, &p.tmRes, &res_full[c], n0 + c * 32, w0, h0, b0);
+            }
+        }
         // While the main loop runs, stage the additive epilogue terms of this tile in shared memory:
         // s_add[tb][j] = bias[n0+j] + tbias[b0+tb][n0+j]  (one row per sample the tile touches, <= ADD_ROWS)
-        const bool staged = p.splits == 1 && p.TB <= ADD_ROWS && (p.bias || p.tbias);
+        const bool staged = epi_direct || (p.splits == 1 && p.TB <= ADD_ROWS && (p.bias || p.tbias));
         if (staged) {
-            const int et = threadIdx.x - 64;                  // 0..127 within the epilogue warps
             for (int i = et; i < p.TB * BN; i += 128) {
                 const int tbi = i / BN, j = i - tbi * BN;
                 float x = 0.f;
@@ -300,23 +331,84 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        // Coalesced epilogue.  TMEM hands every thread ONE ROW (32 consecutive columns per load); storing that directly
-        // makes each warp store instruction hit 32 different 128-byte lines with 16 bytes each (5120 LSU transactions
-        // per 128x160 tile = 4.5 us measured).  Instead each warp transposes its 32x32 sub-tile through a private
-        // shared-memory patch (the pipeline stages are free once the accumulator is complete) and then writes 4 full
-        // rows x 128 B per instruction; residual reads and split-K partial writes use the same mapping.
-        constexpr int PITCH = 36;                                        // floats per staged row (32 + 4: 16-byte aligned, conflict-light)
-        float* stg = reinterpret_cast<float*>(sA) + (warp - 2) * 32 * PITCH;
-        const int sub_r = lane >> 3, c4 = (lane & 7) << 2;               // store mapping: 4 rows x 8 float4 per instruction
         const bool fast = !p.out_nchw && (n0 + BN <= p.N);               // full tile of an NHWC output: the common case
 
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
         if (threadIdx.x == 64) stamp(p, 4);
-        if (fast) {
+        if (p.epi_tma) {
+            // ---- TMA epilogue: registers -> swizzled smem chunk -> one tensor store per 32 accumulator columns.
+            // The chunk buffers alias the pipeline stages (idle once the accumulator is complete).
+            const int rowbytes = p.epi_rowbytes;
+            const uint32_t swz = ((uint32_t)(r * rowbytes) >> 7) & (uint32_t)p.epi_swz;
+            const bool in_box = r < p.rows;
+            const float* my_add = s_add + (in_box ? tb_i : 0) * BN;
+            const bool glu = p.geglu && epi_direct;                 // split-K partials stay raw fp32: GEGLU runs in the reduce kernel
+            const int ocol0 = glu ? (n0 >> 1) : n0;
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                uint32_t u[32];
+                ptx::tmem_ld32(taddr + c * 32, u);
+                uint8_t* ob = smem + (c % EPI_BUFS) * p.epi_buf_stride + r * rowbytes;
+                ptx::tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                if (epi_direct) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 a = *reinterpret_cast<const float4*>(my_add + c * 32 + j);     // warp-wide broadcast
+                        v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+                    }
+                    if (p.epi_res) {
+                        ptx::mbar_wait(&res_full[c & 1], (uint32_t)(c >> 1) & 1u);
+                        const uint8_t* rb = sRes + (c & 1) * RES_BUF_BYTES + r * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 a = *reinterpret_cast<const float4*>(rb + ((j ^ (r & 7)) << 4));
+                            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                        }
+                    }
+                }
+                if (in_box) {
+                    if (glu) {                         // (value, gate) column pairs -> 16 bf16 outputs (models/activation_fn.py:17-20)
+                        float o[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf_f(v[2 * j + 1]);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob + ((j ^ swz) << 4)), o + 8 * j);
+                    } else if (rowbytes == 64) {       // bf16 output
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob + ((j ^ swz) << 4)), v + 8 * j);
+                    } else {                           // fp32 output / split-K partial
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(ob + ((j ^ swz) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+                ptx::fence_proxy_async();              // this thread's smem writes -> visible to the TMA engine
+                // the buffer the NEXT chunk writes was read by the store issued two chunks ago
+                if (et == 0) ptx::bulk_wait_read<1>();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    ptx::tma_store_5d(&p.tmOut, smem + (c % EPI_BUFS) * p.epi_buf_stride, ocol0 + c * p.epi_cols, w0, h0, b0, (int)blockIdx.z);
+                    ptx::bulk_commit();
+                    if (p.epi_res && c + 2 < NCH) {    // every thread has consumed residual chunk c: refill its buffer
+                        ptx::mbar_expect_tx(&res_full[c & 1], (uint32_t)p.rows * 128u);
+                        ptx::tma_load_4d(sRes + (c & 1) * RES_BUF_BYTES, &p.tmRes, &res_full[c & 1], n0 + (c + 2) * 32, w0, h0, b0);
+                    }
+                }
+            }
+            if (et == 0) ptx::bulk_wait_read<0>();     // shared memory must outlive the last store's read
+        } else if (fast) {
+            // ---- fallback 1: coalesced stores through a per-warp 32x32 transpose (4 rows x 128 B per instruction)
+            constexpr int PITCH = 36;                                        // floats per staged row (32 + 4: 16-byte aligned, conflict-light)
+            float* stg = reinterpret_cast<float*>(sA) + (warp - 2) * 32 * PITCH;
+            const int sub_r = lane >> 3, c4 = (lane & 7) << 2;
+            const int packed = valid ? (int)grow | (tb_i << 24) : -1;        // create() guarantees M < 2^24; tb_i < 128
             const int Nout = p.Nout;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 uint32_t u[32];
                 ptx::tmem_ld32(taddr + c * 32, u);
                 ptx::tmem_ld_wait();
@@ -326,52 +418,58 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                         make_float4(__uint_as_float(u[j]), __uint_as_float(u[j + 1]), __uint_as_float(u[j + 2]), __uint_as_float(u[j + 3]));
                 __syncwarp();
                 const int ncol = n0 + c * 32 + c4;                        // absolute GEMM column of this lane's float4
+                float4 x[8];
+                int pk[8];
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
-                    const int rr = q * 32 + it * 4 + sub_r;              // tile row handled by this lane in this iteration
-                    const int tw2 = rr % p.TW, th2 = (rr / p.TW) % p.TH, tb2 = rr / (p.TW * p.TH);
-                    const int ox2 = w0 + tw2, oy2 = h0 + th2, b2 = b0 + tb2;
-                    if (!(rr < p.rows && ox2 < p.W && oy2 < p.H && b2 < p.B)) continue;
-                    const long long grow2 = ((long long)b2 * p.H + oy2) * p.W + ox2;
-                    float4 x = *reinterpret_cast<const float4*>(stg + (it * 4 + sub_r) * PITCH + c4);
-                    if (p.splits > 1) {                                   // raw partial sums [split][M][N]
-                        __stcg(reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.z * p.M + (size_t)grow2) * p.N + ncol), x);
-                        continue;
-                    }
-                    if (staged) {
-                        const float4 ad = *reinterpret_cast<const float4*>(s_add + tb2 * BN + c * 32 + c4);
-                        x.x += ad.x; x.y += ad.y; x.z += ad.z; x.w += ad.w;
-                    } else {
-                        if (p.bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + ncol)); x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w; }
-                        if (p.tbias) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(p.tbias + (long long)b2 * p.tb_stride + ncol));
-                            x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+                    pk[it] = __shfl_sync(0xffffffffu, packed, it * 4 + sub_r);   // (sample-in-tile << 24 | output row) or -1
+                    x[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + sub_r) * PITCH + c4);
+                }
+                if (p.splits > 1) {                                       // raw partial sums [split][M][N]
+#pragma unroll
+                    for (int it = 0; it < 8; ++it)
+                        if (pk[it] >= 0)
+                            __stcg(reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.z * p.M + (size_t)(pk[it] & 0x00ffffff)) * p.N + ncol), x[it]);
+                } else {
+                    float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!staged && p.bias) ad = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        if (pk[it] < 0) continue;
+                        const long long row = pk[it] & 0x00ffffff;
+                        float4 a = ad;
+                        if (staged) a = *reinterpret_cast<const float4*>(s_add + (pk[it] >> 24) * BN + c * 32 + c4);
+                        else if (p.tbias) {
+                            const float4 tv = __ldg(reinterpret_cast<const float4*>(p.tbias + (long long)(b0 + (pk[it] >> 24)) * p.tb_stride + ncol));
+                            a.x += tv.x; a.y += tv.y; a.z += tv.z; a.w += tv.w;
                         }
-                    }
-                    if (p.geglu) {                                        // (value, gate) pairs -> 2 outputs per float4
-                        const long long off = grow2 * Nout + (ncol >> 1);
-                        float o0 = x.x * gelu_erf_f(x.y), o1 = x.z * gelu_erf_f(x.w);
-                        if (p.residual) { const float2 r2 = __ldg(reinterpret_cast<const float2*>(p.residual + off)); o0 += r2.x; o1 += r2.y; }
-                        if (p.out_dtype == SDK_BF16) *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)p.out + off) = __floats2bfloat162_rn(o0, o1);
-                        else *reinterpret_cast<float2*>((float*)p.out + off) = make_float2(o0, o1);
-                    } else {
-                        const long long off = grow2 * p.N + ncol;
-                        if (p.residual) { const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + off)); x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w; }
-                        if (p.out_dtype == SDK_BF16) {
-                            __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
-                            uint2 w2; w2.x = *reinterpret_cast<unsigned*>(&lo); w2.y = *reinterpret_cast<unsigned*>(&hi);
-                            *reinterpret_cast<uint2*>((__nv_bfloat16*)p.out + off) = w2;
+                        float4 o = make_float4(x[it].x + a.x, x[it].y + a.y, x[it].z + a.z, x[it].w + a.w);
+                        if (p.geglu) {                                    // (value, gate) pairs -> 2 outputs per float4
+                            const long long off = row * Nout + (ncol >> 1);
+                            float o0 = o.x * gelu_erf_f(o.y), o1 = o.z * gelu_erf_f(o.w);
+                            if (p.residual) { const float2 r2 = __ldg(reinterpret_cast<const float2*>(p.residual + off)); o0 += r2.x; o1 += r2.y; }
+                            if (p.out_dtype == SDK_BF16) *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)p.out + off) = __floats2bfloat162_rn(o0, o1);
+                            else *reinterpret_cast<float2*>((float*)p.out + off) = make_float2(o0, o1);
                         } else {
-                            *reinterpret_cast<float4*>((float*)p.out + off) = x;
+                            const long long off = row * p.N + ncol;
+                            if (p.residual) { const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + off)); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+                            if (p.out_dtype == SDK_BF16) {
+                                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                                uint2 w2; w2.x = *reinterpret_cast<unsigned*>(&lo); w2.y = *reinterpret_cast<unsigned*>(&hi);
+                                *reinterpret_cast<uint2*>((__nv_bfloat16*)p.out + off) = w2;
+                            } else {
+                                *reinterpret_cast<float4*>((float*)p.out + off) = o;
+                            }
                         }
                     }
                 }
                 __syncwarp();                                             // patch is rewritten by the next chunk
             }
         } else if (p.splits == 1) {
+            // ---- fallback 2: thread-per-row stores (NCHW head conv, ragged N tiles)
             const float* my_add = staged ? s_add + tb_i * BN : nullptr;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 uint32_t u[32];
                 ptx::tmem_ld32(taddr + c * 32, u);
                 ptx::tmem_ld_wait();
@@ -386,7 +484,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
             // split-K with a ragged N tile or NCHW output: per-thread rows
             float* mine = p.partial + ((size_t)blockIdx.z * p.M + (size_t)(valid ? grow : 0)) * p.N + n0;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 uint32_t u[32];
                 ptx::tmem_ld32(taddr + c * 32, u);
                 ptx::tmem_ld_wait();
@@ -507,50 +605,58 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, CUtensorMapL2promotion promo) {
-    // densely packed tensor, innermost dimension first
+// densely packed tensor of up to 5 dimensions, innermost first
+int encode_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int esize, int rank, const uint64_t* dims, const uint32_t* box,
+               CUtensorMapSwizzle swz, CUtensorMapL2promotion promo) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return sdk_fail(SDK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t gdim[4]; cuuint64_t gstride[3]; cuuint32_t bdim[4]; cuuint32_t estr[4];
-    uint64_t stride = 2;
+    cuuint64_t gdim[5]; cuuint64_t gstride[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
+    uint64_t stride = (uint64_t)esize;
     for (int i = 0; i < rank; ++i) {
         gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1;
         stride *= dims[i];
         if (i < rank - 1) gstride[i] = stride;
     }
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, bdim, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sdk_fail(SDK_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rank %d dims %llu %llu box %u %u)", (int)r, rank,
                                            (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
     return SDK_OK;
 }
 
+int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, CUtensorMapL2promotion promo) {
+    return encode_map(m, ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rank, dims, box, CU_TENSOR_MAP_SWIZZLE_128B, promo);
+}
+
 struct TcGemm {
     TcParams prm;
-    int block_n, stages, smem_bytes;
+    int block_n, smem_bytes;
     bool co_resident, two_cta;
     dim3 grid;
     int64_t ws_bytes;
 };
 
-template <int BN, int STAGES, bool TWO = false>
+// shared memory outside the pipeline stages: 1 KiB alignment slack, barriers + TMEM slot, staged bias rows, residual chunks
+int fixed_smem(int bn, bool res) { return 1024 + 256 + ADD_ROWS * bn * 4 + (res ? 2 * RES_BUF_BYTES : 0); }
+int stage_smem(int bn, bool two) { return A_STAGE_BYTES + (two ? bn / 2 : bn) * BK * 2; }
+
+template <int BN, bool TWO = false>
 int launch_cfg(const TcGemm* g, cudaStream_t s) {
-    constexpr int smem = STAGES * (A_STAGE_BYTES + (TWO ? BN / 2 : BN) * BK * 2) + 1024 + 256 + ADD_ROWS * BN * 4;
-    static bool configured = false;
-    if (!configured) {
-        SDK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+    static int configured = 0;                       // largest dynamic smem size this instantiation has been opted in for
+    if (g->smem_bytes > configured) {
+        SDK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->smem_bytes));
+        configured = g->smem_bytes;
     }
     if (TWO) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = g->grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cfg.gridDim = g->grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = g->smem_bytes; cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        SDK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, TWO>, g->prm));
+        SDK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, TWO>, g->prm));
     } else
-    SDK_CUDA(sdk_launch(conv_gemm_tc_kernel<BN, STAGES, TWO>, dim3(g->grid), dim3(TC_THREADS), (size_t)(smem), s, g->prm));
+    SDK_CUDA(sdk_launch(conv_gemm_tc_kernel<BN, TWO>, dim3(g->grid), dim3(TC_THREADS), (size_t)(g->smem_bytes), s, g->prm));
     SDK_LAUNCH_CHECK();
     if (g->prm.splits > 1) {
         const long long items = g->prm.M * ((g->prm.N + 3) / 4);
@@ -609,6 +715,7 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     }
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     p.M = (long long)d->B * d->H * d->W;
+    SDK_CHECK_ARG(p.M < (1ll << 24), "sdk_tc_gemm_create: B*H*W = %lld output rows exceeds 2^24", p.M);
     p.w_kmajor = d->w_kmajor;
     // ---- N tile and split-K: pick the (block_n, splits) pair with the lowest modelled time.
     // Model (SM clocks), constants measured on B200 (profiles/): a CTA's k-block is bound by the L2->smem feed of
@@ -694,11 +801,59 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     p.out = d->out; p.out_dtype = d->out_dtype; p.geglu = d->geglu; p.out_nchw = d->out_nchw;
     g->block_n = bn;
     g->grid = dim3(m_tiles, n_tiles, splits);
+    g->two_cta = two;
+    g->ws_bytes = splits > 1 ? (int64_t)splits * p.M * d->N * 4 + 256 : 0;
+    // ---- epilogue route.  TMA (tensor store of swizzled 32-column chunks) needs full N tiles, NHWC output and - for the
+    // direct form - the bias rows staged in smem; split-K partial planes qualify too (map encoded in set_workspace).
+    const bool full_tiles = d->N % bn == 0 && !d->out_nchw;
+    if (full_tiles && splits == 1 && p.TB <= ADD_ROWS && !(d->geglu && (d->out_dtype != SDK_BF16 || d->residual)) &&
+        ((uintptr_t)d->out & 15) == 0 && ((uintptr_t)d->residual & 15) == 0) {
+        const bool bf = d->out_dtype == SDK_BF16;
+        p.epi_tma = 1;
+        p.epi_cols = d->geglu ? 16 : 32;
+        p.epi_rowbytes = p.epi_cols * (bf ? 2 : 4);
+        p.epi_swz = p.epi_rowbytes == 128 ? 7 : p.epi_rowbytes == 64 ? 3 : 1;
+        const uint64_t odims[5] = {(uint64_t)p.Nout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B, 1};
+        const uint32_t obox[5] = {(uint32_t)p.epi_cols, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB, 1};
+        rc = encode_map(&p.tmOut, d->out, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, bf ? 2 : 4, 5, odims, obox,
+                        p.epi_swz == 7 ? CU_TENSOR_MAP_SWIZZLE_128B : p.epi_swz == 3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE);
+        if (rc == SDK_OK && d->residual) {
+            p.epi_res = 1;
+            const uint64_t rdims[4] = {(uint64_t)d->N, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+            const uint32_t rbox[4] = {32u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
+            rc = encode_map(&p.tmRes, d->residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 4, rdims, rbox, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+        }
+        if (rc != SDK_OK) { delete g; return rc; }
+    } else if (full_tiles && splits > 1) {
+        p.epi_tma = 1; p.epi_cols = 32; p.epi_rowbytes = 128; p.epi_swz = 7;      // tmOut: see sdk_tc_gemm_set_workspace
+    }
+    p.epi_buf_stride = ((p.rows * p.epi_rowbytes + 1023) / 1024) * 1024;
+    // ---- pipeline depth (run-time): as many stages as fit, at most MAX_STAGES and not many more than the k-blocks of a CTA.
     // short K per CTA: the fixed prologue/epilogue cost dominates -> shallow pipeline so that 2 CTAs share an SM and
     // one CTA's epilogue overlaps the other's main loop
-    g->two_cta = two;
+    const int fixed = fixed_smem(bn, p.epi_res != 0), per_stage = stage_smem(bn, two);
+    const int min_stages = p.epi_tma ? (EPI_BUFS * p.epi_buf_stride + per_stage - 1) / per_stage : 2;   // chunk buffers alias the stages
+    const int SMEM_1 = 232448, SMEM_2 = 115712;       // opt-in limit per CTA; per CTA when two share an SM (1 KiB reserved each)
     g->co_resident = !two && p.kb_per_split <= 12;
-    g->ws_bytes = splits > 1 ? (int64_t)splits * p.M * d->N * 4 + 256 : 0;
+    int stages = 0;
+    if (g->co_resident) {
+        stages = (SMEM_2 - fixed) / per_stage;
+        const int want = bn <= 64 ? 4 : bn <= 160 ? 3 : 2;
+        if (stages > want) stages = want;
+        if (stages < 2 || stages < min_stages) { g->co_resident = false; stages = 0; }
+    }
+    if (!g->co_resident) {
+        stages = (SMEM_1 - fixed) / per_stage;
+        if (stages > MAX_STAGES) stages = MAX_STAGES;
+        int useful = p.kb_per_split > min_stages ? p.kb_per_split : min_stages;
+        if (useful < 2) useful = 2;
+        if (stages > useful) stages = useful;
+    }
+    if (stages < 2 || stages < min_stages) { delete g; return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: no pipeline fits (block_n %d)", bn); }
+    p.stages = stages;
+    g->smem_bytes = fixed + stages * per_stage;
     *handle = g;
     return SDK_OK;
 }
@@ -711,7 +866,15 @@ extern "C" int sdk_tc_gemm_set_workspace(void* handle, void* ws) {
     TcGemm* g = (TcGemm*)handle;
     if (g->prm.splits > 1) {
         SDK_CHECK_ARG(ws && ((uintptr_t)ws & 15) == 0, "sdk_tc_gemm_set_workspace: split-K GEMM needs a 16-byte aligned workspace");
-        g->prm.partial = (float*)ws;
+        TcParams& p = g->prm;
+        p.partial = (float*)ws;
+        if (p.epi_tma) {
+            const uint64_t odims[5] = {(uint64_t)p.N, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B, (uint64_t)p.splits};
+            const uint32_t obox[5] = {32u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB, 1u};
+            const int rc = encode_map(&p.tmOut, ws, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 5, odims, obox, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_NONE);
+            if (rc != SDK_OK) return rc;
+        }
     }
     return SDK_OK;
 }
@@ -733,27 +896,18 @@ extern "C" int sdk_tc_gemm_launch(void* handle, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (g->two_cta) {
         switch (g->block_n) {
-            case 128: return launch_cfg<128, 8, true>(g, s);
-            case 160: return launch_cfg<160, 8, true>(g, s);
-            case 256: return launch_cfg<256, 6, true>(g, s);
+            case 128: return launch_cfg<128, true>(g, s);
+            case 160: return launch_cfg<160, true>(g, s);
+            case 256: return launch_cfg<256, true>(g, s);
         }
         return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_launch: 2-CTA block_n %d", g->block_n);
     }
-    if (g->co_resident) {
-        switch (g->block_n) {
-            case 32: return launch_cfg<32, 4>(g, s);
-            case 64: return launch_cfg<64, 4>(g, s);
-            case 128: return launch_cfg<128, 3>(g, s);
-            case 160: return launch_cfg<160, 3>(g, s);
-            case 256: return launch_cfg<256, 2>(g, s);
-        }
-    }
     switch (g->block_n) {
-        case 32: return launch_cfg<32, 8>(g, s);
-        case 64: return launch_cfg<64, 8>(g, s);
-        case 128: return launch_cfg<128, 6>(g, s);
-        case 160: return launch_cfg<160, 6>(g, s);
-        case 256: return launch_cfg<256, 4>(g, s);
+        case 32: return launch_cfg<32>(g, s);
+        case 64: return launch_cfg<64>(g, s);
+        case 128: return launch_cfg<128>(g, s);
+        case 160: return launch_cfg<160>(g, s);
+        case 256: return launch_cfg<256>(g, s);
     }
     return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_launch: block_n %d", g->block_n);
 }

@@ -118,6 +118,10 @@ TC_CASES = [
     ("odd_hw", 3, 24, 24, 320, 640, 3, None, True, False, F32_T, 0, 0, 0),
     ("tiny_hw", 2, 4, 4, 1280, 1280, 3, None, False, False, F32_T, 0, 0, 0),
     ("conv1x1_sp", 2, 16, 16, 2560, 1280, 1, None, False, False, F32_T, 0, 0, 0),
+    ("lin_bf16_res", 1, 1, 4096, 640, 640, 1, "one", True, False, BF16_T, 0, 0, 0),
+    ("conv_res_bn256", 2, 32, 32, 640, 1280, 3, "per", True, False, F32_T, 0, 256, 1),
+    ("conv_res_bn32", 4, 8, 8, 320, 320, 3, "per", True, False, F32_T, 0, 32, 1),
+    ("splitk_geglu", 1, 1, 256, 1280, 10240, 1, None, False, True, BF16_T, 0, 256, 4),
 ]
 
 

@@ -76,7 +76,7 @@ def main():
         _lib.check(lib.sdk_tc_gemm_launch(h, stream))
         torch.cuda.synchronize()
         if args.stamps:
-            st = torch.zeros(8, dtype=torch.int64, device=dev)
+            st = torch.zeros(16, dtype=torch.int64, device=dev)
             lib.sdk_tc_gemm_set_debug(h, st.data_ptr())
             for _ in range(3):
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -85,6 +85,9 @@ def main():
                 v = st.tolist()
                 print("   stamps (ns since entry): prologue %d | operands landed %d | last MMA issued %d | accumulator ready %d | epilogue done %d | exit %d ; event time %.1f us"
                       % tuple([v[i] - v[0] for i in range(1, 7)] + [e0.elapsed_time(e1) * 1e3]))
+                if v[8]:
+                    print("      epilogue detail (ns since accumulator ready): tmem ld %d | patch written %d | patch read %d | chunk0 stored %d | chunk1 stored %d"
+                          % tuple(v[i] - v[4] for i in (8, 9, 10, 11, 12)))
             lib.sdk_tc_gemm_set_debug(h, 0)
         ts = []
         if args.warm:
