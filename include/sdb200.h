@@ -32,6 +32,8 @@ extern "C" {
 const char* sdk_last_error(void);
 int sdk_version(void);
 /* out[0]=SM count, out[1..2]=compute capability, out[3]=max opt-in shared memory per block */
+/* stream-ordered memset to zero (graph-capturable) */
+int sdk_zero(void* ptr, int64_t bytes, void* stream);
 int sdk_device_info(int* out, int n);
 /* programmatic dependent launch for all kernels (1 = on; default off): kernel N+1's prologue overlaps kernel N's tail */
 int sdk_set_pdl(int enabled);
@@ -69,7 +71,16 @@ int sdk_groupnorm_stats(const float* src0, int C0, const float* src1, int C1, in
 int sdk_groupnorm_apply(const float* src0, int C0, const float* src1, int C1, int B, int HW,
                         const float* stats, const float* gamma, const float* beta, int silu,
                         void* out, void* raw_out, int out_dtype, void* stream);
-/* statistics + apply in ONE cooperative launch (what the step program uses); same workspace */
+/* GroupNorm apply fed by per-channel (sum, sum of squares) tables cs0 [B][C0][2], cs1 [B][C1][2] (double) of the sources --
+ * accumulated by the producing GEMM's epilogue (sdk_tc_gemm_set_stats) or written by sdk_channel_stats -- instead of a statistics
+ * pass over the tensor (what the bf16 step program uses; the group fold of nn.GroupNorm, unet.py:156,160,65,398, happens in
+ * the kernel's prologue). */
+int sdk_groupnorm_apply_cs(const float* src0, int C0, const double* cs0, const float* src1, int C1, const double* cs1,
+                           int B, int HW, float eps, const float* gamma, const float* beta, int silu,
+                           void* out, void* raw_out, int out_dtype, void* stream);
+/* per-channel (sum, sum of squares) of an fp32 [B][HW][C] tensor -> out [B][C][2] (double, overwritten) */
+int sdk_channel_stats(const float* src, int B, int HW, int C, double* out, void* stream);
+/* statistics + apply in ONE cooperative launch; same workspace as sdk_groupnorm_stats */
 int sdk_groupnorm_fused(const float* src0, int C0, const float* src1, int C1, int B, int HW, float eps,
                         const float* gamma, const float* beta, int silu, void* out, void* raw_out, int out_dtype,
                         void* workspace, void* stream);
@@ -164,6 +175,10 @@ int sdk_tc_gemm_set_workspace(void* handle, void* workspace);   /* zeroed once b
 int sdk_tc_gemm_info(void* handle, int* out, int n);            /* block_n, splits, grid.x, grid.y, TW, TH, TB, k-blocks [, cta group size if n >= 9] */
 int sdk_tc_gemm_launch(void* handle, void* stream);
 int sdk_tc_gemm_destroy(void* handle);
+/* Also ACCUMULATE the per-channel (sum, sum of squares) table chan_stats [B][N][2] (double; input of sdk_groupnorm_apply_cs) of
+ * the fp32 NHWC output: the caller zeroes the table before every launch (sdk_zero; the step program zeroes all its tables with one
+ * call).  SDK_ERR_UNSUPPORTED when this plan cannot (bf16/GEGLU/NCHW output, tiles that straddle samples): use sdk_channel_stats. */
+int sdk_tc_gemm_set_stats(void* handle, double* chan_stats);
 /* developer aid: record 7 %globaltimer stamps of CTA (0,0,0) into device memory stamps[8] (NULL = off) */
 int sdk_tc_gemm_set_debug(void* handle, void* stamps);
 /* stride-2 3x3 conv (unet.py:236): gather fp32 NHWC -> bf16 [B*Ho*Wo][9*C] rows, then a 1-tap sdk_tc_gemm */

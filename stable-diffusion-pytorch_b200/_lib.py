@@ -34,6 +34,8 @@ SIGNATURES = {
     "sdk_groupnorm_workspace_bytes": [I32, I32],
     "sdk_groupnorm_stats": [P, I32, P, I32, I32, I32, F32, P, P, P],
     "sdk_groupnorm_apply": [P, I32, P, I32, I32, I32, P, P, P, I32, P, P, I32, P],
+    "sdk_groupnorm_apply_cs": [P, I32, P, P, I32, P, I32, I32, F32, P, P, I32, P, P, I32, P],
+    "sdk_channel_stats": [P, I32, I32, I32, P, P],
     "sdk_groupnorm_fused": [P, I32, P, I32, I32, I32, F32, P, P, I32, P, P, I32, P, P],
     "sdk_groupnorm_cluster": [P, I32, P, I32, I32, I32, F32, P, P, I32, P, P, I32, P],
     "sdk_layernorm": [P, P, P, F32, P, I32, I64, I32, P],
@@ -60,6 +62,8 @@ SIGNATURES = {
     "sdk_tc_gemm_launch": [P, P],
     "sdk_tc_gemm_destroy": [P],
     "sdk_tc_gemm_set_debug": [P, P],
+    "sdk_tc_gemm_set_stats": [P, P],
+    "sdk_zero": [P, I64, P],
     "sdk_im2col_s2": [P, P, I32, I32, I32, I32, P],
     # --- misc
     "sdk_device_info": [P, I32],

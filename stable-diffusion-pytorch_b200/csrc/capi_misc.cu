@@ -35,6 +35,12 @@ extern "C" const char* sdk_last_error() { return g_err; }
 extern "C" int sdk_version() { return 100; }
 
 // out[0]=sm count, out[1]=cc major, out[2]=cc minor, out[3]=max opt-in smem per block
+extern "C" int sdk_zero(void* ptr, int64_t bytes, void* stream) {
+    SDK_CHECK_ARG(ptr && bytes >= 0, "sdk_zero: bad args");
+    if (bytes) SDK_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
+    return SDK_OK;
+}
+
 extern "C" int sdk_device_info(int* out, int n) {
     SDK_CHECK_ARG(out && n >= 4, "sdk_device_info: need 4 ints");
     int dev = 0;

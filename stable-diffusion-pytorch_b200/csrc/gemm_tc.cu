@@ -53,6 +53,10 @@ struct alignas(64) TcParams {
     CUtensorMap tmOut, tmRes;
     int epi_tma, epi_res, epi_rowbytes, epi_swz, epi_buf_stride, epi_cols;
     int stages;
+    // per-channel statistics of the fp32 output for the GroupNorm that consumes it: cstat_out [B][N] (sum, sum of squares) in
+    // double, ACCUMULATED with atomics by every tile (the caller zeroes the table before the launch).  Adding <= 24-bit
+    // partials into 53-bit accumulators is exact for all practical magnitudes, so the result does not depend on tile order.
+    double2* cstat_out;
     unsigned long long* dbg;     // optional [8] %globaltimer stamps of CTA (0,0,0) (tools/prof_gemm.py --stamps)
 };
 
@@ -209,6 +213,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
     // [ADD_ROWS][BN]: bias + time-bias of the tile's samples (16-byte aligned: read as float4)
     float* s_add = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
+    float2* s_stat = reinterpret_cast<float2*>(s_add + ADD_ROWS * BN);        // [2][4][32] column partials of the row quarters
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) stamp(p, 0);
@@ -343,6 +348,24 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
             const uint32_t swz = ((uint32_t)(r * rowbytes) >> 7) & (uint32_t)p.epi_swz;
             const bool in_box = r < p.rows;
             const float* my_add = s_add + (in_box ? tb_i : 0) * BN;
+            // statistics bookkeeping (cstat_out): rows of this tile that exist, and the fold of the four row-quarter partials
+            const bool do_stats = p.cstat_out && epi_direct;       // split-K: the reduce pass owns the statistics
+            const int stat_rows = p.TB > 1 ? p.rows : p.TW * min(p.TH, p.H - h0);
+            auto cstat_flush = [&](int cc) {
+                const int rps = p.TW * p.TH;                          // tile rows per sample
+                const int smp = et >> 5;                              // sample within the tile handled by this warp
+                if (smp < p.TB && b0 + smp < p.B) {
+                    const int p_lo = p.TB > 1 ? smp * (rps >> 5) : 0, p_n = p.TB > 1 ? (rps >> 5) : 4;
+                    double sum = 0.0, sq = 0.0;
+                    for (int i = 0; i < p_n; ++i) {
+                        const float2 v2 = s_stat[((cc & 1) * 4 + p_lo + i) * 32 + lane];
+                        sum += (double)v2.x; sq += (double)v2.y;
+                    }
+                    double* dst = reinterpret_cast<double*>(p.cstat_out + (size_t)(b0 + smp) * p.N + n0 + cc * 32 + lane);
+                    atomicAdd(dst, sum);
+                    atomicAdd(dst + 1, sq);
+                }
+            };
             const bool glu = p.geglu && epi_direct;                 // split-K partials stay raw fp32: GEGLU runs in the reduce kernel
             const int ocol0 = glu ? (n0 >> 1) : n0;
 #pragma unroll 1
@@ -398,8 +421,39 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                         ptx::tma_load_4d(sRes + (c & 1) * RES_BUF_BYTES, &p.tmRes, &res_full[c & 1], n0 + (c + 2) * 32, w0, h0, b0);
                     }
                 }
+                if (do_stats) {
+                    // GroupNorm statistics of the consumer, for free: column sums of the finished fp32 chunk (still in smem)
+                    if (c > 0) cstat_flush(c - 1);
+                    const uint8_t* cb = smem + (c % EPI_BUFS) * p.epi_buf_stride + ((lane & 3) << 2);
+                    const int r_lo = (et >> 5) * 32, r_n = min(32, stat_rows - r_lo), jq = lane >> 2;
+                    float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (r_n == 32) {                   // full quarter: all loads of a batch in flight, no branches
+#pragma unroll
+                        for (int i0 = 0; i0 < 32; i0 += 8) {
+                            float x[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int rr = r_lo + i0 + k;           // r_lo is a multiple of 32: rr & 7 == k
+                                x[k] = *reinterpret_cast<const float*>(cb + rr * 128 + ((jq ^ k) << 4));
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) { sa[k & 3] += x[k]; qa[k & 3] = fmaf(x[k], x[k], qa[k & 3]); }
+                        }
+                    } else {
+                        for (int i = 0; i < r_n; ++i) {
+                            const int rr = r_lo + i;
+                            const float x = *reinterpret_cast<const float*>(cb + rr * 128 + ((jq ^ (rr & 7)) << 4));
+                            sa[0] += x; qa[0] = fmaf(x, x, qa[0]);
+                        }
+                    }
+                    s_stat[((c & 1) * 4 + (et >> 5)) * 32 + lane] = make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
+                }
             }
             if (et == 0) ptx::bulk_wait_read<0>();     // shared memory must outlive the last store's read
+            if (do_stats) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cstat_flush(NCH - 1);
+            }
         } else if (fast) {
             // ---- fallback 1: coalesced stores through a per-warp 32x32 transpose (4 rows x 128 B per instruction)
             constexpr int PITCH = 36;                                        // floats per staged row (32 + 4: 16-byte aligned, conflict-light)
@@ -587,6 +641,62 @@ splitk_reduce_kernel(const __grid_constant__ TcParams p) {
     }
 }
 
+// Split-K second pass that also produces the per-channel statistics: CTA = 32 rows x 32 columns of one sample; thread =
+// (row, float4 column).  Column sums: one shared-memory fold over the 32 rows, then 64 double atomics per CTA.
+// Sums the splits in the same order as splitk_reduce_kernel (identical values).  fp32 NHWC output, no GEGLU; H*W % 32 == 0.
+__global__ void __launch_bounds__(256)
+splitk_reduce_stats_kernel(const __grid_constant__ TcParams p) {
+    pdl_wait();
+    __shared__ float s_red[32][8][8];
+    const int N = p.N, HW = p.H * p.W;
+    const int rl = threadIdx.x >> 3, n = blockIdx.x * 32 + ((threadIdx.x & 7) << 2);
+    const long long grow = (long long)blockIdx.y * 32 + rl;
+    const int b = (int)((long long)blockIdx.y * 32 / HW);
+    const size_t plane = (size_t)p.M * N;
+    float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) add = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    if (p.tbias) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.tbias + (long long)b * p.tb_stride + n));
+        add.x += t4.x; add.y += t4.y; add.z += t4.z; add.w += t4.w;
+    }
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+        const size_t off = (size_t)grow * N + n;
+        const float* src = p.partial + off;
+        int sp = 0;
+        for (; sp + 4 <= p.splits; sp += 4) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sp * plane));
+            const float4 b4 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 1) * plane));
+            const float4 c = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 2) * plane));
+            const float4 d = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 3) * plane));
+            v[0] = (((v[0] + a.x) + b4.x) + c.x) + d.x; v[1] = (((v[1] + a.y) + b4.y) + c.y) + d.y;
+            v[2] = (((v[2] + a.z) + b4.z) + c.z) + d.z; v[3] = (((v[3] + a.w) + b4.w) + c.w) + d.w;
+        }
+        for (; sp < p.splits; ++sp) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sp * plane));
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+        }
+        v[0] += add.x; v[1] += add.y; v[2] += add.z; v[3] += add.w;
+        if (p.residual) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+            v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+        }
+        *reinterpret_cast<float4*>((float*)p.out + off) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    float* dst = &s_red[rl][threadIdx.x & 7][0];
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[0] * v[0], v[1] * v[1], v[2] * v[2], v[3] * v[3]);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int col = threadIdx.x & 31, which = threadIdx.x >> 5;        // which: 0 = sum, 1 = sum of squares
+        const int q = col >> 2, j = (col & 3) + 4 * which;
+        double acc = 0.0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) acc += (double)s_red[l][q][j];
+        atomicAdd(reinterpret_cast<double*>(p.cstat_out + (size_t)b * N + blockIdx.x * 32 + col) + which, acc);
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
@@ -637,7 +747,7 @@ struct TcGemm {
 };
 
 // shared memory outside the pipeline stages: 1 KiB alignment slack, barriers + TMEM slot, staged bias rows, residual chunks
-int fixed_smem(int bn, bool res) { return 1024 + 256 + ADD_ROWS * bn * 4 + (res ? 2 * RES_BUF_BYTES : 0); }
+int fixed_smem(int bn, bool res) { return 1024 + 256 + ADD_ROWS * bn * 4 + 2 * 4 * 32 * 8 + 32 + (res ? 2 * RES_BUF_BYTES : 0); }
 int stage_smem(int bn, bool two) { return A_STAGE_BYTES + (two ? bn / 2 : bn) * BK * 2; }
 
 template <int BN, bool TWO = false>
@@ -662,7 +772,8 @@ int launch_cfg(const TcGemm* g, cudaStream_t s) {
         const long long items = g->prm.M * ((g->prm.N + 3) / 4);
         long long blocks = (items + 255) / 256, cap = (long long)sdk_num_sms() * 8;
         if (blocks > cap) blocks = cap;
-        SDK_CUDA(sdk_launch(splitk_reduce_kernel, dim3((int)blocks), dim3(256), (size_t)(0), s, g->prm));
+        if (g->prm.cstat_out) SDK_CUDA(sdk_launch(splitk_reduce_stats_kernel, dim3(g->prm.N / 32, (unsigned)(g->prm.M / 32)), dim3(256), (size_t)(0), s, g->prm));
+        else SDK_CUDA(sdk_launch(splitk_reduce_kernel, dim3((int)blocks), dim3(256), (size_t)(0), s, g->prm));
         SDK_LAUNCH_CHECK();
     }
     return SDK_OK;
@@ -876,6 +987,27 @@ extern "C" int sdk_tc_gemm_set_workspace(void* handle, void* ws) {
             if (rc != SDK_OK) return rc;
         }
     }
+    return SDK_OK;
+}
+
+// Per-channel statistics of the output for the GroupNorm that consumes it: chan_stats = double [B][N][2] (sum, sum of squares per
+// sample and column), ACCUMULATED by the launch -- the caller zeroes the table before every launch (sdk_zero).  Supported for
+// fp32 NHWC outputs produced by the TMA epilogue or by split-K; anything else returns SDK_ERR_UNSUPPORTED (use sdk_channel_stats).
+extern "C" int sdk_tc_gemm_set_stats(void* handle, double* chan_stats) {
+    SDK_CHECK_ARG(handle, "sdk_tc_gemm_set_stats: null handle");
+    TcGemm* g = (TcGemm*)handle;
+    TcParams& p = g->prm;
+    if (!chan_stats) { p.cstat_out = nullptr; return SDK_OK; }
+    SDK_CHECK_ARG(((uintptr_t)chan_stats & 15) == 0, "sdk_tc_gemm_set_stats: table must be 16-byte aligned");
+    const bool ok_out = p.out_dtype == SDK_F32 && !p.geglu && !p.out_nchw && p.N % 32 == 0;
+    if (!ok_out) return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_set_stats: needs an fp32 NHWC output with N %% 32 == 0");
+    const int rps = p.TW * p.TH;
+    if (p.splits > 1) {                                  // statistics come from the reduce pass (32-row patches)
+        if ((p.H * p.W) % 32 != 0) return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_set_stats: split-K needs H*W %% 32 == 0");
+    } else if (!p.epi_tma || (p.TB == 1 && p.W % p.TW != 0) || (p.TB > 1 && rps % 32 != 0)) {
+        return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_set_stats: tile %dx%dx%d of a %dx%d map cannot attribute rows to samples", p.TW, p.TH, p.TB, p.W, p.H);
+    }
+    p.cstat_out = (double2*)chan_stats;
     return SDK_OK;
 }
 

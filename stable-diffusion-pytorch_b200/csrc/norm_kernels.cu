@@ -141,6 +141,9 @@ struct GNApplyArgs {
     const float* stats; const float* gamma; const float* beta;
     void* out; void* raw_out;
     int silu;
+    // alternative to `stats`: per-channel (sum, sum of squares) of each source in double, [B][C0] and [B][C1], written by the kernels
+    // that produced the sources (sdk_tc_gemm_set_stats / sdk_channel_stats); the group fold happens in this kernel's prologue
+    const double2* cs0; const double2* cs1; float eps;
 };
 
 template <typename TOut>
@@ -167,6 +170,26 @@ gn_apply_kernel(GNApplyArgs a, int pix_per_chunk, int px_lanes, int q_iters) {
     const int p1 = min(a.HW, p0 + pix_per_chunk);
     const int qlanes = GN_THREADS / px_lanes;
     const int pl = threadIdx.x / qlanes, ql = threadIdx.x - pl * qlanes;
+    __shared__ float2 s_gstat[GROUPS];
+    if (a.cs0) {
+        // 8 threads per group: channel sums -> (mean, rstd), fixed order (double accumulation, as gn_stats_kernel's fold)
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+        double sum = 0.0, sq = 0.0;
+        for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
+            const double2 v = c < a.C0 ? __ldg(a.cs0 + (size_t)b * a.C0 + c) : __ldg(a.cs1 + (size_t)b * a.C1 + (c - a.C0));
+            sum += v.x; sq += v.y;
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+        if (sub == 0) {
+            const double n = (double)cpg * (double)a.HW;
+            const double mean = sum / n;
+            double var = sq / n - mean * mean;      // biased variance (nn.GroupNorm)
+            if (var < 0.0) var = 0.0;
+            s_gstat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+        }
+        __syncthreads();
+    }
     if (pl >= px_lanes) return;
     TOut* out = reinterpret_cast<TOut*>(a.out) + (size_t)b * a.HW * C;
     TOut* raw = a.raw_out ? reinterpret_cast<TOut*>(a.raw_out) + (size_t)b * a.HW * C : nullptr;
@@ -184,7 +207,7 @@ gn_apply_kernel(GNApplyArgs a, int pix_per_chunk, int px_lanes, int q_iters) {
             const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float2 st = __ldg(reinterpret_cast<const float2*>(a.stats) + (size_t)b * GROUPS + (c + j) / cpg);
+                const float2 st = a.cs0 ? s_gstat[(c + j) / cpg] : __ldg(reinterpret_cast<const float2*>(a.stats) + (size_t)b * GROUPS + (c + j) / cpg);
                 sc[j] = st.y * gs[j];
                 sh[j] = bs[j] - st.x * sc[j];
             }
@@ -610,15 +633,9 @@ extern "C" int sdk_groupnorm_stats(const float* src0, int C0, const float* src1,
     return SDK_OK;
 }
 
-extern "C" int sdk_groupnorm_apply(const float* src0, int C0, const float* src1, int C1, int B, int HW,
-                                   const float* stats, const float* gamma, const float* beta, int silu,
-                                   void* out, void* raw_out, int out_dtype, void* stream) {
-    SDK_CHECK_ARG(src0 && stats && gamma && beta && out, "sdk_groupnorm_apply: null pointer");
-    const int C = C0 + C1;
-    SDK_CHECK_ARG(C % GROUPS == 0 && C0 % 4 == 0 && C1 % 4 == 0 && (C1 == 0 || src1), "sdk_groupnorm_apply: bad channels %d+%d", C0, C1);
-    GNApplyArgs a;
-    a.src0 = src0; a.src1 = src1; a.C0 = C0; a.C1 = C1; a.HW = HW; a.B = B;
-    a.stats = stats; a.gamma = gamma; a.beta = beta; a.out = out; a.raw_out = raw_out; a.silu = silu;
+namespace {
+int launch_gn_apply(GNApplyArgs& a, int out_dtype, cudaStream_t stream) {
+    const int C = a.C0 + a.C1, B = a.B, HW = a.HW;
     const int nq = C / 4;
     int px_lanes = GN_THREADS / (nq < GN_THREADS ? nq : GN_THREADS);
     if (px_lanes > HW) px_lanes = HW;
@@ -632,9 +649,75 @@ extern "C" int sdk_groupnorm_apply(const float* src0, int C0, const float* src1,
     if (chunks < want) { chunks = want < HW ? want : HW; ppc = (HW + chunks - 1) / chunks; }
     chunks = (HW + ppc - 1) / ppc;
     SDK_CHECK_ARG(B < 65536, "sdk_groupnorm_apply: batch too large");
-    if (out_dtype == SDK_F32) SDK_CUDA(sdk_launch(gn_apply_kernel<float>, dim3(chunks, B), dim3(GN_THREADS), (size_t)0, (cudaStream_t)stream, a, ppc, px_lanes, q_iters));
-    else if (out_dtype == SDK_BF16) SDK_CUDA(sdk_launch(gn_apply_kernel<__nv_bfloat16>, dim3(chunks, B), dim3(GN_THREADS), (size_t)0, (cudaStream_t)stream, a, ppc, px_lanes, q_iters));
+    if (out_dtype == SDK_F32) SDK_CUDA(sdk_launch(gn_apply_kernel<float>, dim3(chunks, B), dim3(GN_THREADS), (size_t)0, stream, a, ppc, px_lanes, q_iters));
+    else if (out_dtype == SDK_BF16) SDK_CUDA(sdk_launch(gn_apply_kernel<__nv_bfloat16>, dim3(chunks, B), dim3(GN_THREADS), (size_t)0, stream, a, ppc, px_lanes, q_iters));
     else return sdk_fail(SDK_ERR_ARG, "sdk_groupnorm_apply: out_dtype %d", out_dtype);
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+}  // namespace
+
+extern "C" int sdk_groupnorm_apply(const float* src0, int C0, const float* src1, int C1, int B, int HW,
+                                   const float* stats, const float* gamma, const float* beta, int silu,
+                                   void* out, void* raw_out, int out_dtype, void* stream) {
+    SDK_CHECK_ARG(src0 && stats && gamma && beta && out, "sdk_groupnorm_apply: null pointer");
+    const int C = C0 + C1;
+    SDK_CHECK_ARG(C % GROUPS == 0 && C0 % 4 == 0 && C1 % 4 == 0 && (C1 == 0 || src1), "sdk_groupnorm_apply: bad channels %d+%d", C0, C1);
+    GNApplyArgs a;
+    a.src0 = src0; a.src1 = src1; a.C0 = C0; a.C1 = C1; a.HW = HW; a.B = B;
+    a.stats = stats; a.gamma = gamma; a.beta = beta; a.out = out; a.raw_out = raw_out; a.silu = silu;
+    a.cs0 = nullptr; a.cs1 = nullptr; a.eps = 0.f;
+    return launch_gn_apply(a, out_dtype, (cudaStream_t)stream);
+}
+
+// GroupNorm apply whose statistics come from the per-channel sums of the sources (cs0 [B][C0][2], cs1 [B][C1][2], double) instead of a
+// separate statistics pass over the tensor: the producing GEMM's epilogue already reduced its columns (sdk_tc_gemm_set_stats).
+extern "C" int sdk_groupnorm_apply_cs(const float* src0, int C0, const double* cs0, const float* src1, int C1, const double* cs1,
+                                      int B, int HW, float eps, const float* gamma, const float* beta, int silu,
+                                      void* out, void* raw_out, int out_dtype, void* stream) {
+    SDK_CHECK_ARG(src0 && cs0 && gamma && beta && out, "sdk_groupnorm_apply_cs: null pointer");
+    const int C = C0 + C1;
+    SDK_CHECK_ARG(C % GROUPS == 0 && C0 % 4 == 0 && C1 % 4 == 0 && (C1 == 0 || (src1 && cs1)), "sdk_groupnorm_apply_cs: bad channels %d+%d", C0, C1);
+    GNApplyArgs a;
+    a.src0 = src0; a.src1 = src1; a.C0 = C0; a.C1 = C1; a.HW = HW; a.B = B;
+    a.stats = nullptr; a.gamma = gamma; a.beta = beta; a.out = out; a.raw_out = raw_out; a.silu = silu;
+    a.cs0 = reinterpret_cast<const double2*>(cs0); a.cs1 = reinterpret_cast<const double2*>(cs1); a.eps = eps;
+    return launch_gn_apply(a, out_dtype, (cudaStream_t)stream);
+}
+
+// Per-channel (sum, sum of squares) of an fp32 [B][HW][C] tensor -> out [B][C][2] (double, overwritten); for GroupNorm inputs whose producer cannot
+// deliver them (conv_in's FFMA kernel, unusual tilings).  CTA = (32 channels, sample); fixed-order fold (deterministic).
+namespace {
+__global__ void __launch_bounds__(256)
+channel_stats_kernel(const float* __restrict__ src, int HW, int C, double2* __restrict__ out) {
+    pdl_wait();
+    __shared__ float s_red[32][8][8];
+    const int b = blockIdx.y, rl = threadIdx.x >> 3, q = threadIdx.x & 7, c = blockIdx.x * 32 + (q << 2);
+    float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+        const float* p = src + (size_t)b * HW * C + c;
+        for (int r = rl; r < HW; r += 32) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)r * C));
+            sa[0] += v.x; sa[1] += v.y; sa[2] += v.z; sa[3] += v.w;
+            qa[0] = fmaf(v.x, v.x, qa[0]); qa[1] = fmaf(v.y, v.y, qa[1]); qa[2] = fmaf(v.z, v.z, qa[2]); qa[3] = fmaf(v.w, v.w, qa[3]);
+        }
+    }
+    *reinterpret_cast<float4*>(&s_red[rl][q][0]) = make_float4(sa[0], sa[1], sa[2], sa[3]);
+    *reinterpret_cast<float4*>(&s_red[rl][q][4]) = make_float4(qa[0], qa[1], qa[2], qa[3]);
+    __syncthreads();
+    if (threadIdx.x < 32 && blockIdx.x * 32 + threadIdx.x < C) {
+        const int qq = threadIdx.x >> 2, j = threadIdx.x & 3;
+        double sum = 0.0, sq = 0.0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) { sum += (double)s_red[l][qq][j]; sq += (double)s_red[l][qq][4 + j]; }
+        out[(size_t)b * C + blockIdx.x * 32 + threadIdx.x] = make_double2(sum, sq);
+    }
+}
+}  // namespace
+
+extern "C" int sdk_channel_stats(const float* src, int B, int HW, int C, double* out, void* stream) {
+    SDK_CHECK_ARG(src && out && B > 0 && B < 65536 && HW > 0 && C > 0 && C % 4 == 0, "sdk_channel_stats: bad args");
+    SDK_CUDA(sdk_launch(channel_stats_kernel, dim3((C + 31) / 32, B), dim3(256), (size_t)0, (cudaStream_t)stream, src, HW, C, reinterpret_cast<double2*>(out)));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }

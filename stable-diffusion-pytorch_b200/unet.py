@@ -171,6 +171,11 @@ class StepProgram:
         self.n_launch = 0
         self.tc_handles = []
         self.attn_handles = []
+        # GroupNorm statistics from per-channel sums accumulated by the producing GEMM (bf16 program) instead of a statistics
+        # kernel.  All tables live in one arena that the program zeroes with its first op.
+        self.gn_from_sums = pw.precision != "fp32" and net.gn_mode == "sums"
+        self.stat_arena = torch.zeros(8 << 20, dtype=torch.uint8, device=dev) if self.gn_from_sums else None
+        self.stat_used = 0
 
         f32 = torch.float32
         # static I/O staging (graph-stable addresses)
@@ -189,8 +194,9 @@ class StepProgram:
 
     def _conv(self, srcs, w, bias, B, Hin, Win, N, *, k=1, stride=1, up=False, tbias=0, tb_stride=0,
               residual=None, geglu=False, out_code=F32_T, out=None, out_nchw=False, in_code=None, ctx=False,
-              force_simt=False, seg2=None):
-        """srcs: [(tensor[rows, C], C)] (1 or 2).  Returns the output tensor [M, N or N/2]."""
+              force_simt=False, seg2=None, want_stats=False):
+        """srcs: [(tensor[rows, C], C)] (1 or 2).  Returns the output tensor [M, N or N/2].
+        want_stats: the output feeds a GroupNorm -> also produce its per-channel (sum, sum of squares) table (out._cstats)."""
         upf = 2 if up else 1
         pad = k // 2
         Hout = (Hin * upf + 2 * pad - k) // stride + 1
@@ -213,13 +219,29 @@ class StepProgram:
         p.in_dtype = self.act if in_code is None else in_code
         p.out_dtype, p.out_nchw, p.geglu = out_code, int(out_nchw), int(geglu)
         self.keep.append(p)
+        want_stats = want_stats and self.gn_from_sums and out_code == F32_T and not geglu and not out_nchw
+        cs = self._stat_table(B, N) if want_stats else None
+        fused = False
         if p.in_dtype == F32_T or force_simt:
             self._emit(self.lib.sdk_conv_gemm_f32, C.byref(p), ctx=ctx)
         else:
-            self._emit_tc_conv(p, srcs, w, ctx, seg2)
+            fused = self._emit_tc_conv(p, srcs, w, ctx, seg2, cs)
+        if want_stats:
+            if not fused:                                   # producer cannot reduce its own columns: one extra small launch
+                self._emit(self.lib.sdk_channel_stats, out.data_ptr(), B, Hout * Wout, N, cs.data_ptr(), ctx=ctx)
+            out._cstats = cs
         return out, Hout, Wout
 
-    def _emit_tc_conv(self, p, srcs, w, ctx, seg2=None):
+    def _stat_table(self, B, N):
+        """double [B][N][2] per-channel (sum, sum of squares) table carved from the arena."""
+        nbytes = (B * N * 16 + 255) // 256 * 256
+        if self.stat_used + nbytes > self.stat_arena.numel():
+            raise RuntimeError("statistics arena exhausted")
+        t = self.stat_arena[self.stat_used: self.stat_used + B * N * 16].view(torch.float64).view(B, N, 2)
+        self.stat_used += nbytes
+        return t
+
+    def _emit_tc_conv(self, p, srcs, w, ctx, seg2=None, cs=None):
         """tcgen05 implicit GEMM for a stride-1 conv / linear described by ConvParams ``p``."""
         if len(srcs) != 1 or p.stride != 1 or p.upsample:
             raise RuntimeError("tensor-core conv takes one pre-concatenated, pre-upsampled bf16 source at stride 1")
@@ -236,6 +258,14 @@ class StepProgram:
         self.tc_handles.append(h)
         self.keep.append(d)
         self._emit(self.lib.sdk_tc_gemm_launch, h, ctx=ctx)
+        if cs is None:
+            return False
+        # statistics of the output accumulated by the GEMM's own epilogue into the (zeroed once per step) table
+        rc = self.lib.sdk_tc_gemm_set_stats(h, cs.data_ptr())
+        if rc == -3:                                        # SDK_ERR_UNSUPPORTED: tiling cannot attribute rows to samples
+            return False
+        _lib.check(rc)
+        return True
 
     def _gn(self, srcs, B, HW, g, b, eps, silu, want_raw=False):
         """GroupNorm(32)(+SiLU) over the concat of srcs -> operand-typed tensor [B*HW, C]."""
@@ -247,6 +277,14 @@ class StepProgram:
         s1p = s1.data_ptr() if s1 is not None else 0
         rawp = raw.data_ptr() if raw is not None else 0
         mode = self.net.gn_mode
+        if self.gn_from_sums and all(getattr(sr, "_cstats", None) is not None for sr, _ in srcs):
+            cs0 = s0._cstats.data_ptr()
+            cs1 = s1._cstats.data_ptr() if s1 is not None else 0
+            self._emit(self.lib.sdk_groupnorm_apply_cs, s0.data_ptr(), c0, cs0, s1p, c1, cs1, B, HW, float(eps),
+                       g.data_ptr(), b.data_ptr(), int(silu), out.data_ptr(), rawp, self.act)
+            return out, raw
+        if mode == "sums":
+            mode = "split"
         if mode == "auto":
             # small tensors are latency-bound: one cluster launch (DSMEM reduce) beats two launches + ticketed tail;
             # large ones are bandwidth-bound and need the whole chip (measured on B200)
@@ -295,24 +333,25 @@ class StepProgram:
         a1, raw = self._gn(srcs, B, HW, t[f"{p}.groupnorm_1.g"], t[f"{p}.groupnorm_1.b"], r.eps, True, want_raw=need_raw)
         tb_ptr = self.tb.data_ptr() + 4 * r.tb_offset
         h1, _, _ = self._conv([(a1, r.cin_total)], t[f"{p}.conv_1.w"], t[f"{p}.conv_1.b"], B, H, W, r.cout, k=3,
-                              tbias=tb_ptr, tb_stride=(self.arch.tb_total if self.nt > 1 else 0))
+                              tbias=tb_ptr, tb_stride=(self.arch.tb_total if self.nt > 1 else 0), want_stats=True)
         self.pool.put(a1)
         a2, _ = self._gn([(h1, r.cout)], B, HW, t[f"{p}.groupnorm_2.g"], t[f"{p}.groupnorm_2.b"], r.eps, True)
         self.pool.put(h1)
         if r.has_proj:
             if self.act == F32_T:
                 sc, _, _ = self._conv(srcs, t[f"{p}.proj.w"], t[f"{p}.proj.b"], B, H, W, r.cout, k=1)
-                out, _, _ = self._conv([(a2, r.cout)], t[f"{p}.conv_2.w"], t[f"{p}.conv_2.b"], B, H, W, r.cout, k=3, residual=sc)
+                out, _, _ = self._conv([(a2, r.cout)], t[f"{p}.conv_2.w"], t[f"{p}.conv_2.b"], B, H, W, r.cout, k=3, residual=sc,
+                                       want_stats=True)
                 self.pool.put(sc)
             else:
                 # 1x1 shortcut conv (unet.py:192) as a second K segment of conv_2's GEMM: same TMEM accumulator,
                 # no fp32 round trip of the shortcut tensor; bias = conv_2.bias + proj_input.bias (packed)
                 out, _, _ = self._conv([(a2, r.cout)], t[f"{p}.conv_2.w"], t[f"{p}.conv2_proj.b"], B, H, W, r.cout, k=3,
-                                       seg2=(raw, r.cin_total, t[f"{p}.proj.w"]))
+                                       seg2=(raw, r.cin_total, t[f"{p}.proj.w"]), want_stats=True)
                 self.pool.put(raw)
         else:
             out, _, _ = self._conv([(a2, r.cout)], t[f"{p}.conv_2.w"], t[f"{p}.conv_2.b"], B, H, W, r.cout, k=3,
-                                   residual=srcs[0][0])
+                                   residual=srcs[0][0], want_stats=True)
         self.pool.put(a2)
         return out
 
@@ -360,7 +399,8 @@ class StepProgram:
         h4, _, _ = self._conv([(g, 4 * Cc)], t[f"{p}.ff1.w"], t[f"{p}.ff1.b"], 1, 1, M, Cc, residual=h3, out_code=self.act)
         self.pool.put(g)
         self.pool.put(h3)
-        out, _, _ = self._conv([(h4, Cc)], t[f"{p}.out.w"], t[f"{p}.out.b"], 1, 1, M, Cc, residual=x)
+        # conv_output + long residual feeds the next GroupNorm: (B, H, W) form so that tiles can be attributed to samples
+        out, _, _ = self._conv([(h4, Cc)], t[f"{p}.out.w"], t[f"{p}.out.b"], B, H, W, Cc, residual=x, want_stats=True)
         self.pool.put(h4)
         return out
 
@@ -402,7 +442,7 @@ class StepProgram:
         xin = self.pool.get(B * H * W, a.in_channels, F32_T)
         self._emit(lib.sdk_nchw_to_nhwc, self.x_in.data_ptr(), xin.data_ptr(), self.b_src, B, a.in_channels, H * W)
         x, _, _ = self._conv([(xin, a.in_channels)], t["conv_in.w"], t["conv_in.b"], B, H, W, BLOCK_OUT[0], k=3,
-                             in_code=F32_T, force_simt=True)
+                             in_code=F32_T, force_simt=True, want_stats=True)
         self.pool.put(xin)
         skips = [(x, BLOCK_OUT[0], H, W)]
         h, w = H, W
@@ -427,13 +467,13 @@ class StepProgram:
             if st.resample is not None:
                 wn, bn_ = t[f"{st.resample.prefix}.w"], t[f"{st.resample.prefix}.b"]
                 if self.act == F32_T:
-                    y, h, w = self._conv([(x, xc)], wn, bn_, B, h, w, xc, k=3, stride=2)
+                    y, h, w = self._conv([(x, xc)], wn, bn_, B, h, w, xc, k=3, stride=2, want_stats=True)
                 else:
                     # stride-2 3x3 (unet.py:236): gather the 9 taps into bf16 rows, then a 1-tap tensor-core GEMM
                     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
                     col = self.pool.get(B * ho * wo, 9 * xc, BF16_T)
                     self._emit(lib.sdk_im2col_s2, x.data_ptr(), col.data_ptr(), B, h, w, xc)
-                    y, _, _ = self._conv([(col, 9 * xc)], wn, bn_, 1, 1, B * ho * wo, xc, k=1)
+                    y, _, _ = self._conv([(col, 9 * xc)], wn, bn_, B, ho, wo, xc, k=1, want_stats=True)
                     self.pool.put(col)
                     h, w = ho, wo
                 x = y
@@ -469,9 +509,11 @@ class StepProgram:
                 up = not (skips and skips[-1][3] == prev_w)          # unet.py:346-349
                 op, tmp = self._operand(x, B, h, w, xc, up=2 if (up and self.act != F32_T) else 1)
                 if up and self.act != F32_T:
-                    y, h, w = self._conv([(op, xc)], t[f"{st.resample.prefix}.w"], t[f"{st.resample.prefix}.b"], B, 2 * h, 2 * w, xc, k=3)
+                    y, h, w = self._conv([(op, xc)], t[f"{st.resample.prefix}.w"], t[f"{st.resample.prefix}.b"], B, 2 * h, 2 * w, xc, k=3,
+                                         want_stats=True)
                 else:
-                    y, h, w = self._conv([(op, xc)], t[f"{st.resample.prefix}.w"], t[f"{st.resample.prefix}.b"], B, h, w, xc, k=3, up=up)
+                    y, h, w = self._conv([(op, xc)], t[f"{st.resample.prefix}.w"], t[f"{st.resample.prefix}.b"], B, h, w, xc, k=3, up=up,
+                                         want_stats=True)
                 if tmp:
                     self.pool.put(op)
                 self.pool.put(x)
@@ -490,6 +532,9 @@ class StepProgram:
         self.tc_ws = torch.zeros(max(need, 256), dtype=torch.uint8, device=self.device)
         for h in self.tc_handles:
             _lib.check(self.lib.sdk_tc_gemm_set_workspace(h, self.tc_ws.data_ptr()))
+        if self.gn_from_sums:                               # first op of the step: zero every statistics table at once
+            self.ops.insert(0, (self.lib.sdk_zero, (self.stat_arena.data_ptr(), self.stat_used)))
+            self.n_launch = len(self.ops)
 
     def tc_info(self):
         out = []
@@ -550,7 +595,9 @@ class UNet(nn.Module):
         self.tc_splits = int(os.environ.get("SDB200_TC_SPLITS", "0"))
         self.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention for head_dim 40 / 64
         self.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
-        self.gn_mode = os.environ.get("SDB200_GN_MODE", "split")           # split (stats+apply kernels, fastest measured) | cluster | coop | auto
+        # sums: statistics from per-channel sums reduced in the producing GEMM's epilogue (bf16 program; fastest measured) |
+        # split (stats + apply kernels) | cluster | coop | auto
+        self.gn_mode = os.environ.get("SDB200_GN_MODE", "sums")
         self.gn_cluster_max_bytes = int(os.environ.get("SDB200_GN_CLUSTER_MAX_BYTES", str(3 << 20)))
         self.use_cuda_graph = os.environ.get("SDB200_CUDA_GRAPH", "1") != "0"
         self._packed: Dict = {}

@@ -368,6 +368,89 @@ def test_groupnorm(dev, shape, odt):
     assert torch.equal(out3, out2) and rel_l2(raw3.float(), x) < (1e-7 if odt == F32_T else 4e-3)
 
 
+@pytest.mark.parametrize("shape", [(2, 256, 320, 0), (2, 64, 1280, 640), (1, 4096, 640, 320), (3, 16, 2560, 0), (2, 1024, 960, 0)])
+def test_groupnorm_from_channel_sums(dev, shape):
+    """sdk_channel_stats + sdk_groupnorm_apply_cs (statistics from per-channel sums, the bf16 step program's route) vs nn.GroupNorm."""
+    B, HW, C0, C1 = shape
+    lib = _lib.lib()
+    s0 = gen((B, HW, C0), 41, dev) * 2 + 0.5
+    s1 = gen((B, HW, C1), 42, dev) if C1 else None
+    Ct = C0 + C1
+    gamma, beta = gen((Ct,), 43, dev) * 0.1 + 1, gen((Ct,), 44, dev) * 0.1
+    cs0 = torch.full((B, C0, 2), float("nan"), device=dev, dtype=torch.float64)
+    cs1 = torch.full((B, max(C1, 1), 2), float("nan"), device=dev, dtype=torch.float64)
+    _lib.check(lib.sdk_channel_stats(s0.data_ptr(), B, HW, C0, cs0.data_ptr(), stream()))
+    if C1:
+        _lib.check(lib.sdk_channel_stats(s1.data_ptr(), B, HW, C1, cs1.data_ptr(), stream()))
+    assert rel_l2(cs0[..., 0], s0.double().sum(1)) < 1e-6 and rel_l2(cs0[..., 1], (s0.double() ** 2).sum(1)) < 1e-6
+    x = torch.cat([s0] + ([s1] if C1 else []), -1)
+    want = Fn.silu(Fn.group_norm(x.permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
+    for odt, dt, tol in ((F32_T, torch.float32, 2e-5), (BF16_T, torch.bfloat16, 4e-3)):
+        out = torch.full((B, HW, Ct), float("nan"), device=dev, dtype=dt)
+        raw = torch.full((B, HW, Ct), float("nan"), device=dev, dtype=dt)
+        _lib.check(lib.sdk_groupnorm_apply_cs(s0.data_ptr(), C0, cs0.data_ptr(), s1.data_ptr() if C1 else 0, C1, cs1.data_ptr() if C1 else 0,
+                                              B, HW, 1e-5, gamma.data_ptr(), beta.data_ptr(), 1, out.data_ptr(), raw.data_ptr(), odt, stream()))
+        assert rel_l2(out.float(), want) < tol
+        assert rel_l2(raw.float(), x) < (1e-7 if odt == F32_T else 4e-3)
+
+
+TC_STATS_CASES = [
+    # name, B, H, W, C, N, k, tbias, residual, block_n, splits
+    ("L0_conv", 2, 64, 64, 320, 320, 3, "per", False, 0, 0),
+    ("L1_conv_res", 2, 32, 32, 640, 640, 3, None, True, 0, 1),
+    ("L1_1x1_res", 3, 32, 32, 640, 640, 1, None, True, 0, 1),
+    ("L2_conv_bn256", 2, 16, 16, 1280, 1280, 3, "one", False, 256, 1),
+    ("L3_two_samples_per_tile", 3, 8, 8, 1280, 1280, 3, "per", True, 0, 1),
+    ("L3_splitk", 2, 8, 8, 1280, 1280, 3, "per", True, 0, 0),
+    ("odd_hw", 3, 24, 24, 320, 640, 3, None, True, 0, 1),
+    ("sd21_96", 1, 96, 96, 320, 320, 1, None, False, 0, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_STATS_CASES, ids=[c[0] for c in TC_STATS_CASES])
+def test_tc_gemm_channel_stats(dev, case):
+    """The GEMM epilogue's per-channel (sum, sum of squares) table == sums of the tensor it wrote."""
+    name, B, H, W, Cc, N, k, tbm, res, bn, splits = case
+    lib = _lib.lib()
+    a = gen((B, H, W, Cc), 11, dev).bfloat16()
+    w = gen((N, k * k * Cc), 12, dev, 1.0 / math.sqrt(k * k * Cc)).bfloat16()
+    bias = gen((N,), 13, dev, 0.1) + 0.3
+    tb = None if tbm is None else gen((B if tbm == "per" else 1, N), 14, dev)
+    resid = gen((B, H, W, N), 15, dev) if res else None
+    out = torch.full((B, H, W, N), float("nan"), device=dev)
+    d = TcGemmDesc()
+    wp = kmajor(w)
+    d.w_kmajor = 1
+    d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = a.data_ptr(), wp.data_ptr(), Cc, k, 1
+    d.B, d.H, d.W, d.N = B, H, W, N
+    d.bias = bias.data_ptr()
+    d.tbias, d.tb_stride = (tb.data_ptr() if tb is not None else 0), (N if tbm == "per" else 0)
+    d.residual, d.out = (resid.data_ptr() if res else 0), out.data_ptr()
+    d.out_dtype, d.geglu, d.out_nchw, d.block_n, d.splits = F32_T, 0, 0, bn, splits
+    h = C.c_void_p()
+    _lib.check(lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
+    info = (C.c_int * 8)()
+    _lib.check(lib.sdk_tc_gemm_info(h, info, 8))
+    ws = torch.zeros(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=dev)
+    _lib.check(lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr()))
+    cs = torch.full((2, B, N, 2), float("nan"), device=dev, dtype=torch.float64)
+    for i in range(2):                                     # the launch accumulates into a table the caller zeroed
+        _lib.check(lib.sdk_zero(cs[i].data_ptr(), cs[i].numel() * 8, stream()))
+        _lib.check(lib.sdk_tc_gemm_set_stats(h, cs[i].data_ptr()))
+        _lib.check(lib.sdk_tc_gemm_launch(h, stream()))
+    torch.cuda.synchronize()
+    lib.sdk_tc_gemm_destroy(h)
+    tbe = None if tb is None else tb.expand(B, N)
+    want = ref_conv([a], w, bias, k, 1, False, tbe, resid, False)
+    e = rel_l2(out, want)
+    flat = out.view(B, H * W, N).double()
+    e_sum, e_sq = rel_l2(cs[0, ..., 0].double(), flat.sum(1)), rel_l2(cs[0, ..., 1].double(), (flat * flat).sum(1))
+    print(f"{name}: block_n={info[0]} splits={info[1]} grid=({info[2]},{info[3]}) tile=({info[4]},{info[5]},{info[6]}) out {e:.2e} sum {e_sum:.2e} sumsq {e_sq:.2e}")
+    assert e < 2e-5
+    assert e_sum < 2e-6 and e_sq < 2e-6
+    assert rel_l2(cs[0], cs[1]) < 1e-13                    # atomics in double: order-independent to the last bits
+
+
 @pytest.mark.parametrize("C_", [320, 640, 1280, 768])
 def test_layernorm(dev, C_):
     lib = _lib.lib()

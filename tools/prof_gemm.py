@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--rowmajor", action="store_true")
     ap.add_argument("--two-cta", type=int, default=0)
+    ap.add_argument("--stats", action="store_true", help="also produce the per-channel statistics table (sdk_tc_gemm_set_stats)")
     ap.add_argument("--stamps", action="store_true", help="print in-kernel %%globaltimer stamps of CTA (0,0,0)")
     ap.add_argument("--warm", action="store_true", help="no L2 flush between launches; time 20 back-to-back launches")
     ap.add_argument("--shape", default="", help="custom: name,B,H,W,C,N,k")
@@ -73,6 +74,10 @@ def main():
         lib.sdk_tc_gemm_info(h, info, 9)
         ws = torch.zeros(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=dev)
         lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr())
+        if args.stats and not geglu:
+            cst = torch.zeros((B, N, 2), device=dev, dtype=torch.float64)
+            if lib.sdk_tc_gemm_set_stats(h, cst.data_ptr()) != 0:
+                print(f"{name}: statistics unsupported")
         _lib.check(lib.sdk_tc_gemm_launch(h, stream))
         torch.cuda.synchronize()
         if args.stamps:
@@ -86,7 +91,7 @@ def main():
                 print("   stamps (ns since entry): prologue %d | operands landed %d | last MMA issued %d | accumulator ready %d | epilogue done %d | exit %d ; event time %.1f us"
                       % tuple([v[i] - v[0] for i in range(1, 7)] + [e0.elapsed_time(e1) * 1e3]))
                 if v[8]:
-                    print("      epilogue detail (ns since accumulator ready): tmem ld %d | patch written %d | patch read %d | chunk0 stored %d | chunk1 stored %d"
+                    print("      epilogue detail (ns since accumulator ready): chunk0 done %d | chunk1 done %d | all chunks %d | partials fenced %d | ticket taken %d"
                           % tuple(v[i] - v[4] for i in (8, 9, 10, 11, 12)))
             lib.sdk_tc_gemm_set_debug(h, 0)
         ts = []
