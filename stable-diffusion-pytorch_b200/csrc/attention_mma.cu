@@ -55,6 +55,7 @@ attention_bf16_kernel(const __nv_bfloat16* __restrict__ q, long long q_row, long
                       const __nv_bfloat16* __restrict__ v, long long v_row, long long v_batch,
                       __nv_bfloat16* __restrict__ out, long long o_row, long long o_batch,
                       int heads, int Sq, int Sk, float scale_log2) {
+    pdl_trigger();
     pdl_wait();
     constexpr int DP = (D + 15) / 16 * 16;          // QK^T reduction length (zero padded)
     constexpr int LD = DP + 8;                      // smem row pitch in elements (+16 B: conflict-free ldmatrix)

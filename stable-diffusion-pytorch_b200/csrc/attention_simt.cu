@@ -17,6 +17,7 @@ attention_f32_kernel(const float* __restrict__ q, long long q_row, long long q_b
                      const float* __restrict__ v, long long v_row, long long v_batch,
                      float* __restrict__ out, long long o_row, long long o_batch,
                      int heads, int Sq, int Sk, float scale) {
+    pdl_trigger();
     pdl_wait();
     constexpr int DQ = D / 4;                    // output columns per thread
     extern __shared__ float smem[];

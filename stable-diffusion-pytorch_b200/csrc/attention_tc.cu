@@ -7,11 +7,16 @@
 //     past the head are OUT OF BOUNDS in the innermost dimension and arrive as zeros, so a 128-byte-swizzled
 //     [128][64] tile is exactly the zero-padded operand the MMA needs (no padding pass, no neighbour-head leakage).
 //   * S = Q K^T : A = Q (K-major), B = K tile (K-major), 128 x 128 fp32 in TMEM columns [0,128)
-//   * softmax  : a query row = one TMEM lane, handled by two threads (64 keys each); the only cross-thread traffic is one
-//                float per tile (partial row max) through shared memory.
+//   * softmax  : a query row = one TMEM lane, handled by TWO threads that run two INDEPENDENT flash streams: thread h of a
+//                row owns keys [64h, 64h+64) of every tile, with its own running max, row sum and its own P.V accumulator
+//                (split-KV inside the CTA).  No cross-thread traffic inside the loop; the two streams are merged once
+//                at the end (standard log-sum-exp merge).
 //                P (bf16) is written to shared memory in the K-major SW128 layout = A operand of the second MMA.
-//   * PV       : A = P (smem), B = V tile used AS STORED ([key][d], d contiguous) through an MN-major descriptor,
-//                128 x 64 fp32 in TMEM columns [128,192); rows accumulate O in registers (O = O*corr + PV).
+//   * PV       : per half h: A = P_h (smem, 128 x 64 keys), B = V rows [64h, 64h+64) used AS STORED ([key][d], d contiguous)
+//                through an MN-major descriptor, ACCUMULATED in TMEM columns [128+64h, 192+64h) across all tiles.
+//                The running max is only raised when the tile max exceeds it by more than 2^8 (P stays <= 256, exact in
+//                fp32 sums and harmless in bf16); a raise rescales the accumulator in TMEM (tcgen05.ld / st), which is
+//                rare after the first tiles.  Nothing waits for P.V inside the loop.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 softmax (two threads per row).  Single-buffered
 // K, V, P, S: K(t+1) loads as soon as QK^T(t) retires, V(t+1) as soon as PV(t) retires; two CTAs per SM (80 KiB of
 // smem, 256 TMEM columns each) overlap one CTA's softmax with the other's MMAs.
@@ -60,9 +65,9 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
     uint8_t* sP = sV + TILE_BYTES;                                     // 2 x 16 KiB: keys [0,64) and [64,128)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
     uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
-             *s_full = bars + 5, *p_full = bars + 6, *pv_full = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    float* s_max = reinterpret_cast<float*>(bars + 10);               // [2 tile parities][2 halves][128 rows]
+             *s_full = bars + 5, *p_full = bars + 6 /* [2] */, *pv_full = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float2* s_ml = reinterpret_cast<float2*>(bars + 10);              // [2 halves][128 rows] (scaled max, row sum) for the final merge
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y, b = bh / p.heads, h = bh - b * p.heads;
@@ -72,7 +77,8 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
 
     if (threadIdx.x == 0) {
         ptx::mbar_init(q_full, 1); ptx::mbar_init(k_full, 1); ptx::mbar_init(k_empty, 1); ptx::mbar_init(v_full, 1);
-        ptx::mbar_init(v_empty, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(p_full, 256); ptx::mbar_init(pv_full, 1);
+        ptx::mbar_init(v_empty, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(&p_full[0], 128); ptx::mbar_init(&p_full[1], 128);
+        ptx::mbar_init(pv_full, 1);
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmQ); ptx::prefetch_tmap(&p.tmK); ptx::prefetch_tmap(&p.tmV);
     }
@@ -81,6 +87,7 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
     pdl_wait();
 
     if (warp == 0) {
@@ -115,15 +122,18 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
                     ptx::umma_bf16(tmem_base, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), IDESC_S, k > 0 ? 1u : 0u);
                 ptx::umma_commit(k_empty);
                 ptx::umma_commit(s_full);
-                // ---- PV = P V
-                ptx::mbar_wait(p_full, ph);
+                // ---- O_h += P_h V_h for the two key halves (own accumulators, accumulated over all tiles)
                 ptx::mbar_wait(v_full, ph);
-                ptx::tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < BKV / 16; ++k) {
-                    const uint64_t da = (k < 4 ? dp0 : dp1) + (uint64_t)((k & 3) * 2);     // +32 B per 16 keys inside a 64-key atom
-                    const uint64_t db = dv + (uint64_t)(k * 16 * 128 >> 4);                // +16 key rows of 128 B
-                    ptx::umma_bf16(tmem_base + 128, da, db, IDESC_O, k > 0 ? 1u : 0u);
+                for (int hh = 0; hh < 2; ++hh) {
+                    ptx::mbar_wait(&p_full[hh], ph);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = (hh == 0 ? dp0 : dp1) + (uint64_t)(k * 2);               // +32 B per 16 keys inside the 64-key atom
+                        const uint64_t db = dv + (uint64_t)((hh * 4 + k) * 16 * 128 >> 4);           // +16 key rows of 128 B
+                        ptx::umma_bf16(tmem_base + 128 + hh * 64, da, db, IDESC_O, (t > 0 || k > 0) ? 1u : 0u);
+                    }
                 }
                 ptx::umma_commit(v_empty);
                 ptx::umma_commit(pv_full);
@@ -139,15 +149,12 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
         const int half = (warp - 2) >> 2;
         const int r = qd * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
+        const uint32_t oaddr = taddr + 128 + half * 64;                  // this stream's accumulator (64 columns, D <= 64 used)
         uint8_t* prow = sP + half * TILE_BYTES + r * 128;                 // this half's 64-key atom of P
         const int swz = r & 7;
-        constexpr int OD = 32;                                           // output columns held per thread (half 1 uses D - 32 of them)
-        const int my_d0 = half * 32;
-        const int my_nd = half == 0 ? (D < 32 ? D : 32) : D - 32;
-        float o[OD];
-#pragma unroll
-        for (int i = 0; i < OD; ++i) o[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;
+        constexpr float RAISE = 8.f;                                     // raise the running max only beyond 2^8 of head room
+        float m_sc = -INFINITY;                                          // running max * scale*log2(e) (the exponent offset in use)
+        float l_run = 0.f;
         for (int t = 0; t < ntiles; ++t) {
             const uint32_t ph = (uint32_t)t & 1u;
             ptx::mbar_wait(s_full, ph);
@@ -155,7 +162,7 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
             const int kbase = t * BKV + half * 64;
             const bool ragged = t * BKV + BKV > p.Sk;
             uint32_t u[32];
-            // pass 1: partial row max over this half's 64 keys
+            // pass 1: row max over this stream's 64 keys
             float mx = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -169,14 +176,27 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
                     for (int j = 0; j < 32; j += 2) mx = max3(mx, __uint_as_float(u[j]), __uint_as_float(u[j + 1]));
                 }
             }
-            s_max[(ph * 2 + half) * 128 + r] = mx;
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            mx = fmaxf(mx, s_max[(ph * 2 + (half ^ 1)) * 128 + r]);
-            const float m_new = fmaxf(m_run, mx);                    // finite: every tile holds >= 1 valid key
-            const float corr = ex2((m_run - m_new) * p.scale_log2);
-            const float msc = m_new * p.scale_log2;
-            m_run = m_new;
-            // pass 2: p = exp2(s*scale - m*scale), partial row sum, P -> smem (bf16, K-major SW128)
+            const float mx_sc = mx * p.scale_log2;                   // -inf when this half of a ragged tile holds no key
+            const bool raise = mx_sc > m_sc + RAISE || (m_sc == -INFINITY && mx_sc > -INFINITY);
+            if (t > 0 && __any_sync(0xffffffffu, raise)) {
+                // rescale this stream's accumulator (rows that do not raise use factor 1): needs P.V(t-1) retired
+                ptx::mbar_wait(pv_full, ph ^ 1u);
+                ptx::tc_fence_after();
+                const float corr = raise ? ex2(m_sc - mx_sc) : 1.f;   // m_sc == -inf (stream empty so far) -> 0
+                l_run *= corr;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    ptx::tmem_ld32(oaddr + c * 32, u);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) * corr);
+                    ptx::tmem_st32(oaddr + c * 32, u);
+                }
+                ptx::tmem_st_wait();
+            }
+            if (raise) m_sc = mx_sc;
+            const float msc = m_sc == -INFINITY ? 0.f : m_sc;        // empty stream: exp2(-inf - 0) = 0
+            // pass 2: p = exp2(s*scale - m*scale), row sum, P -> smem (bf16, K-major SW128)
             float ps = 0.f;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -202,30 +222,43 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
                     *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
-            l_run = l_run * corr + ps;
+            l_run += ps;
             ptx::fence_proxy_async();                                // generic-proxy smem writes -> visible to the MMA (async proxy)
-            ptx::tc_fence_before();                                  // our TMEM reads of S are ordered before the arrive
-            ptx::mbar_arrive(p_full);
-            // O = O*corr + P V   (this half's 32 output columns)
-            ptx::mbar_wait(pv_full, ph);
-            ptx::tc_fence_after();
-            ptx::tmem_ld32(taddr + 128 + my_d0, u);
+            ptx::tc_fence_before();                                  // our TMEM reads of S / writes of O are ordered before the arrive
+            ptx::mbar_arrive(&p_full[half]);
+        }
+        // merge the two streams of the row: O = (O_0 e_0 + O_1 e_1) / (l_0 e_0 + l_1 e_1), e_h = 2^(m_h - max(m_0, m_1))
+        s_ml[half * 128 + r] = make_float2(m_sc, l_run);
+        ptx::mbar_wait(pv_full, (uint32_t)(ntiles - 1) & 1u);
+        ptx::tc_fence_after();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float2 other = s_ml[(half ^ 1) * 128 + r];
+        const float m_all = fmaxf(m_sc, other.x);                    // finite: half 0 always holds a key
+        const float e_me = ex2(m_sc - m_all), e_ot = ex2(other.x - m_all);
+        const float inv = 1.f / (l_run * e_me + other.y * e_ot);
+        const float w_me = e_me * inv, w_ot = e_ot * inv;
+        constexpr int OD = 32;                                           // output columns per thread (half 1 stores D - 32 of them)
+        const int my_d0 = half * 32;
+        const int my_nd = half == 0 ? (D < 32 ? D : 32) : D - 32;
+        float o[OD];
+        {
+            uint32_t u[32];
+            ptx::tmem_ld32(oaddr + my_d0, u);                        // own accumulator, my 32 output columns
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < OD; ++j) o[j] = fmaf(o[j], corr, __uint_as_float(u[j]));
-            ptx::tc_fence_before();
+            for (int j = 0; j < OD; ++j) o[j] = __uint_as_float(u[j]) * w_me;
+            ptx::tmem_ld32(taddr + 128 + (half ^ 1) * 64 + my_d0, u); // the other stream's accumulator
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < OD; ++j) o[j] = fmaf(__uint_as_float(u[j]), w_ot, o[j]);
         }
-        // combine the two halves' row sums, normalise, store
-        s_max[half * 128 + r] = l_run;
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        const float inv = 1.f / (l_run + s_max[(half ^ 1) * 128 + r]);
         if (q0 + r < p.Sq) {
             __nv_bfloat16* op = p.out + (size_t)b * p.o_batch + (size_t)(q0 + r) * p.o_row + (size_t)h * D + my_d0;
 #pragma unroll
             for (int i = 0; i < OD; i += 8) {
                 if (i < my_nd) {
-                    __nv_bfloat162 a = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv), b2 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
-                    __nv_bfloat162 c2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv), d2 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
+                    __nv_bfloat162 a = __floats2bfloat162_rn(o[i], o[i + 1]), b2 = __floats2bfloat162_rn(o[i + 2], o[i + 3]);
+                    __nv_bfloat162 c2 = __floats2bfloat162_rn(o[i + 4], o[i + 5]), d2 = __floats2bfloat162_rn(o[i + 6], o[i + 7]);
                     uint4 w;
                     w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b2);
                     w.z = *reinterpret_cast<uint32_t*>(&c2); w.w = *reinterpret_cast<uint32_t*>(&d2);

@@ -63,6 +63,7 @@ __device__ __forceinline__ float4 load_b_quad(const float* __restrict__ w, int n
 
 __global__ void __launch_bounds__(THREADS)
 conv_gemm_f32_kernel(const SdkConvParams p) {
+    pdl_trigger();
     pdl_wait();
     __shared__ __align__(16) float As[2][BK][BM + PADM];
     __shared__ __align__(16) float Bs[2][BK][BN + PADM];

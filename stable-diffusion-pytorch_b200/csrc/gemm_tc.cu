@@ -248,6 +248,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     if (TWO) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
     pdl_wait();          // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
     if (threadIdx.x == 0) stamp(p, 1);
 
@@ -571,6 +572,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
 // order (deterministic) and run the epilogue.
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const __grid_constant__ TcParams p) {
+    pdl_trigger();
     pdl_wait();
     const int N = p.N, quads = (N + 3) >> 2;
     const long long total = p.M * quads;
@@ -646,6 +648,7 @@ splitk_reduce_kernel(const __grid_constant__ TcParams p) {
 // Sums the splits in the same order as splitk_reduce_kernel (identical values).  fp32 NHWC output, no GEGLU; H*W % 32 == 0.
 __global__ void __launch_bounds__(256)
 splitk_reduce_stats_kernel(const __grid_constant__ TcParams p) {
+    pdl_trigger();
     pdl_wait();
     __shared__ float s_red[32][8][8];
     const int N = p.N, HW = p.H * p.W;
@@ -1061,6 +1064,7 @@ extern "C" int sdk_tc_gemm_destroy(void* handle) {
 namespace {
 __global__ void __launch_bounds__(256)
 im2col_s2_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C, int Ho, int Wo) {
+    pdl_trigger();
     pdl_wait();
     const int nq = C >> 2;
     const long long total = (long long)B * Ho * Wo * 9 * nq;

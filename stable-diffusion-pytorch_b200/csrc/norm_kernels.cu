@@ -38,6 +38,7 @@ struct GNStatsArgs {
 
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(GNStatsArgs a) {
+    pdl_trigger();
     pdl_wait();
     extern __shared__ float s_part[];            // [nq][px_lanes][8] : 4 sums + 4 sums of squares per (quad, pixel lane)
     __shared__ bool s_last;
@@ -163,6 +164,7 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
 template <typename TOut>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(GNApplyArgs a, int pix_per_chunk, int px_lanes, int q_iters) {
+    pdl_trigger();
     pdl_wait();
     const int b = blockIdx.y;
     const int C = a.C0 + a.C1, cpg = C / GROUPS, nq = C >> 2;
@@ -250,6 +252,7 @@ struct GNFusedArgs {
 template <typename TOut>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_fused_kernel(GNFusedArgs a) {
+    pdl_trigger();
     pdl_wait();
     extern __shared__ float s_part[];            // phase 1: [nq][px_lanes][8]; phase 2: stats [GROUPS][2]
     const int C = a.C0 + a.C1, cpg = C / GROUPS, nq = C >> 2;
@@ -394,6 +397,7 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 template <typename TOut>
 __global__ void __launch_bounds__(GNC_THREADS, 1)
 gn_cluster_kernel(GNApplyArgs a, float eps, int CS, int px_lanes, int q_iters) {
+    pdl_trigger();
     pdl_wait();
     extern __shared__ float s_part[];                       // [nq][px_lanes][8]
     __shared__ double s_cl[GROUPS][2];                      // this CTA's per-group partial (read by the whole cluster)
@@ -512,6 +516,7 @@ template <typename TOut, int MAXQ>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, TOut* __restrict__ out, int C, long long rows) {
+    pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -555,6 +560,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 template <typename TOut>
 __global__ void __launch_bounds__(256)
 cast_upsample_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int B, int H, int W, int C, int up) {
+    pdl_trigger();
     pdl_wait();
     const int Ho = H * up, Wo = W * up, nquads = C >> 2;
     const long long total = (long long)B * Ho * Wo * nquads;
@@ -571,6 +577,7 @@ cast_upsample_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int 
 
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int B_src, int B_dst, int C, int HW) {
+    pdl_trigger();
     pdl_wait();
     // dst[b][p][c] = src[b % B_src][c][p]   (b % B_src implements latent.repeat(2,1,1,1), diffusion.py:228)
     const long long total = (long long)B_dst * HW * C;
@@ -690,6 +697,7 @@ extern "C" int sdk_groupnorm_apply_cs(const float* src0, int C0, const double* c
 namespace {
 __global__ void __launch_bounds__(256)
 channel_stats_kernel(const float* __restrict__ src, int HW, int C, double2* __restrict__ out) {
+    pdl_trigger();
     pdl_wait();
     __shared__ float s_red[32][8][8];
     const int b = blockIdx.y, rl = threadIdx.x >> 3, q = threadIdx.x & 7, c = blockIdx.x * 32 + (q << 2);

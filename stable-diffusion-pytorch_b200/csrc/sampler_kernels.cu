@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256)
 step_kernel(const float* x, const float* __restrict__ eu, const float* __restrict__ ec, float scale,
             const float* __restrict__ noise, float* out, long long n,      // x and out may alias (in-place latent state)
             const float* __restrict__ table, int T, const long long* __restrict__ t_dev, long long t_host, int vec_ok) {
+    pdl_trigger();
     pdl_wait();
     Coef k;
     const bool ok = load_coef(table, T, t_dev, t_host, k);
@@ -106,6 +107,7 @@ step_kernel(const float* x, const float* __restrict__ eu, const float* __restric
 __global__ void __launch_bounds__(256)
 forward_process_kernel(const float* __restrict__ x0, const float* __restrict__ noise, float* __restrict__ out,
                        long long per_sample, const float* __restrict__ table, int T, const long long* __restrict__ t) {
+    pdl_trigger();
     pdl_wait();
     const int b = blockIdx.y;
     long long tb = t[b];
@@ -122,6 +124,7 @@ forward_process_kernel(const float* __restrict__ x0, const float* __restrict__ n
 __global__ void __launch_bounds__(256)
 x0_from_eps_kernel(const float* __restrict__ x, const float* __restrict__ e, float sigma, float alpha,
                    float* __restrict__ out, long long n) {
+    pdl_trigger();
     pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(sigma, e[i])), alpha);
@@ -194,6 +197,7 @@ extern "C" int sdk_x0_from_eps(const float* x, const float* eps, float sigma, fl
 // work in between: the timestep sequence (host-built, bit-exact) is uploaded once and walked here.
 namespace {
 __global__ void next_timestep_kernel(const long long* __restrict__ table, int n, int* __restrict__ counter, long long* __restrict__ t_out) {
+    pdl_trigger();
     pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int i = counter[0];

@@ -9,6 +9,7 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 time_sinusoid_kernel(const long long* __restrict__ t, int n, int dim, float* __restrict__ out) {
+    pdl_trigger();
     pdl_wait();
     const int half = dim >> 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,6 +46,7 @@ template <typename TW, int NB>
 __global__ void __launch_bounds__(256)
 gemv_kernel(const TW* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x, float* __restrict__ y,
             int n, int R, int K, int act_in, int act_out) {
+    pdl_trigger();
     pdl_wait();
     constexpr int V = WVec<TW>::N;
     const int lane = threadIdx.x & 31;

@@ -290,7 +290,7 @@ def test_attention(dev, case, mode):
 
 
 ATT_TC_CASES = [(2, 8, 4096, 4096, 40), (1, 8, 1024, 77, 40), (2, 5, 2304, 2304, 64), (2, 8, 200, 333, 40), (1, 10, 576, 77, 64),
-                (3, 8, 128, 128, 40)]
+                (3, 8, 128, 128, 40), (2, 8, 256, 40, 40), (1, 5, 300, 9216, 64)]
 
 
 @pytest.mark.parametrize("case", ATT_TC_CASES)
