@@ -1,25 +1,27 @@
 // tcgen05 flash attention for head dims <= 64 (SD-1.5 level 0: D = 40, S = 4096; SD-2.1: D = 64, S up to 9216):
 // out = softmax(q k^T * scale) v per (batch, head)   (models/unet/attention.py:29-50).
 //
-// CTA = 128 queries x one head; K/V stream in 128-key tiles.  Both contractions run on the 5th-gen tensor cores with
+// CTA = 128 queries x one head; K/V stream in 64-key tiles.  Both contractions run on the 5th-gen tensor cores with
 // TMEM accumulators, operands fetched by TMA straight out of the fused [B][S][3C] qkv buffer:
 //   * per-head tiles come from 4-D tensor maps (d, head, token, batch) with a 64-wide box: for D = 40 the 24 columns
 //     past the head are OUT OF BOUNDS in the innermost dimension and arrive as zeros, so a 128-byte-swizzled
-//     [128][64] tile is exactly the zero-padded operand the MMA needs (no padding pass, no neighbour-head leakage).
-//   * S = Q K^T : A = Q (K-major), B = K tile (K-major), 128 x 128 fp32 in TMEM columns [0,128)
+//     [rows][64] tile is exactly the zero-padded operand the MMA needs (no padding pass, no neighbour-head leakage).
+//   * S = Q K^T : A = Q (K-major), B = K tile (K-major), 128 x 64 fp32, DOUBLE-BUFFERED in TMEM columns [0,64) / [64,128):
+//                 S(t+1) and S(t+2) are computed while the softmax of tile t runs, so the softmax warps never wait for
+//                 the tensor core in steady state.
 //   * softmax  : a query row = one TMEM lane, handled by TWO threads that run two INDEPENDENT flash streams: thread h of a
-//                row owns keys [64h, 64h+64) of every tile, with its own running max, row sum and its own P.V accumulator
-//                (split-KV inside the CTA).  No cross-thread traffic inside the loop; the two streams are merged once
-//                at the end (standard log-sum-exp merge).
-//                P (bf16) is written to shared memory in the K-major SW128 layout = A operand of the second MMA.
-//   * PV       : per half h: A = P_h (smem, 128 x 64 keys), B = V rows [64h, 64h+64) used AS STORED ([key][d], d contiguous)
-//                through an MN-major descriptor, ACCUMULATED in TMEM columns [128+64h, 192+64h) across all tiles.
-//                The running max is only raised when the tile max exceeds it by more than 2^8 (P stays <= 256, exact in
-//                fp32 sums and harmless in bf16); a raise rescales the accumulator in TMEM (tcgen05.ld / st), which is
-//                rare after the first tiles.  Nothing waits for P.V inside the loop.
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 softmax (two threads per row).  Single-buffered
-// K, V, P, S: K(t+1) loads as soon as QK^T(t) retires, V(t+1) as soon as PV(t) retires; two CTAs per SM (80 KiB of
-// smem, 256 TMEM columns each) overlap one CTA's softmax with the other's MMAs.
+//                row owns keys [32h, 32h+32) of every tile (one tcgen05.ld of 32 columns, kept in registers for both the
+//                max and the exp pass), with its own running max, row sum and its own P.V accumulator (split-KV inside
+//                the CTA).  No cross-thread traffic inside the loop; the streams are merged once at the end
+//                (log-sum-exp merge).  P (bf16) goes to shared memory in the K-major SW128 layout = A operand of the
+//                second MMA, double-buffered.
+//   * PV       : per stream h: A = P_h (smem, 128 x 32 keys), B = V rows [32h, 32h+32) used AS STORED ([key][d], d
+//                contiguous) through an MN-major descriptor, ACCUMULATED in TMEM columns [128+64h, 192+64h) over all tiles.
+//                The running max is only raised when the tile max exceeds it by more than 2^8 (P stays <= 256: exact in
+//                the fp32 row sums, harmless in bf16); a raise rescales the accumulator in TMEM (tcgen05.ld / st), which
+//                is rare after the first tiles.  Nothing waits for P.V inside the loop.
+// Warp roles: warp 0 TMA producer (3-stage K and V rings), warp 1 MMA issuer + TMEM owner, warps 2..9 softmax (two threads
+// per row).  ~98 KiB of smem and 256 TMEM columns per CTA: two CTAs per SM.
 #include "common.cuh"
 #include "ptx.cuh"
 #include <new>
@@ -27,8 +29,11 @@
 
 namespace {
 
-constexpr int BQ = 128, BKV = 128, DP = 64, AT_THREADS = 64 + 256;    // TMA warp, MMA warp, 8 softmax warps
-constexpr int TILE_BYTES = 128 * DP * 2;             // 16 KiB: one [128][64] bf16 tile
+constexpr int BQ = 128, BKV = 64, DP = 64, AT_THREADS = 64 + 256;     // TMA warp, MMA warp, 8 softmax warps
+constexpr int Q_BYTES = BQ * DP * 2;                 // 16 KiB: [128][64] bf16
+constexpr int KV_BYTES = BKV * DP * 2;               //  8 KiB: [64][64] bf16
+constexpr int P_BYTES = BQ * BKV * 2;                // 16 KiB: [128][64] bf16
+constexpr int KV_STAGES = 3;
 
 struct alignas(64) AttnParams {
     CUtensorMap tmQ, tmK, tmV;
@@ -44,7 +49,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) { float y; asm(
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(TILE_BYTES >> 4) << 16;          // LBO: next 64-wide MN atom (unused: N = 64 is one atom)
+    d |= (uint64_t)(KV_BYTES >> 4) << 16;            // LBO: next 64-wide MN atom (unused: N = 64 is one atom)
     d |= (uint64_t)(1024 >> 4) << 32;                // SBO: next group of 8 K rows
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
@@ -55,19 +60,19 @@ template <int D>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ AttnParams p) {
     constexpr int KS = (D + 15) / 16;                                  // K=16 steps of Q K^T (zero padded past D)
-    constexpr uint32_t IDESC_S = ptx::umma_idesc_bf16(128, BKV);       // 128 x 128, both operands K-major
+    constexpr uint32_t IDESC_S = ptx::umma_idesc_bf16(128, BKV);       // 128 x 64, both operands K-major
     constexpr uint32_t IDESC_O = ptx::umma_idesc_bf16(128, DP) | (1u << 16);   // 128 x 64, B (= V) MN-major
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;
-    uint8_t* sK = sQ + TILE_BYTES;
-    uint8_t* sV = sK + TILE_BYTES;
-    uint8_t* sP = sV + TILE_BYTES;                                     // 2 x 16 KiB: keys [0,64) and [64,128)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
-    uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
-             *s_full = bars + 5, *p_full = bars + 6 /* [2] */, *pv_full = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-    float2* s_ml = reinterpret_cast<float2*>(bars + 10);              // [2 halves][128 rows] (scaled max, row sum) for the final merge
+    uint8_t* sK = sQ + Q_BYTES;                                        // [KV_STAGES]
+    uint8_t* sV = sK + KV_STAGES * KV_BYTES;                           // [KV_STAGES]
+    uint8_t* sP = sV + KV_STAGES * KV_BYTES;                           // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+    uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 4, *v_full = bars + 7, *v_empty = bars + 10,
+             *s_full = bars + 13 /* [2] */, *p_full = bars + 15 /* [2] */, *pv_done = bars + 17 /* [2] */;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+    float2* s_ml = reinterpret_cast<float2*>(bars + 20);              // [2 streams][128 rows] (scaled max, row sum) for the final merge
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y, b = bh / p.heads, h = bh - b * p.heads;
@@ -76,9 +81,11 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
     const int ntiles = (p.Sk + BKV - 1) / BKV;
 
     if (threadIdx.x == 0) {
-        ptx::mbar_init(q_full, 1); ptx::mbar_init(k_full, 1); ptx::mbar_init(k_empty, 1); ptx::mbar_init(v_full, 1);
-        ptx::mbar_init(v_empty, 1); ptx::mbar_init(s_full, 1); ptx::mbar_init(&p_full[0], 128); ptx::mbar_init(&p_full[1], 128);
-        ptx::mbar_init(pv_full, 1);
+        ptx::mbar_init(q_full, 1);
+        for (int i = 0; i < KV_STAGES; ++i) {
+            ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&k_empty[i], 1); ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&v_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&p_full[i], 256); ptx::mbar_init(&pv_done[i], 1); }
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmQ); ptx::prefetch_tmap(&p.tmK); ptx::prefetch_tmap(&p.tmV);
     }
@@ -92,152 +99,147 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
 
     if (warp == 0) {
         if (lane == 0) {
-            ptx::mbar_expect_tx(q_full, TILE_BYTES);
+            ptx::mbar_expect_tx(q_full, Q_BYTES);
             ptx::tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
+            int st = 0; uint32_t ph = 0;
             for (int t = 0; t < ntiles; ++t) {
-                const uint32_t ph = (uint32_t)t & 1u;
-                ptx::mbar_wait(k_empty, ph ^ 1u);
-                ptx::mbar_expect_tx(k_full, TILE_BYTES);
-                ptx::tma_load_4d(sK, &p.tmK, k_full, 0, h, t * BKV, kvb);
-                ptx::mbar_wait(v_empty, ph ^ 1u);
-                ptx::mbar_expect_tx(v_full, TILE_BYTES);
-                ptx::tma_load_4d(sV, &p.tmV, v_full, 0, h, t * BKV, kvb);
+                ptx::mbar_wait(&k_empty[st], ph ^ 1u);
+                ptx::mbar_expect_tx(&k_full[st], KV_BYTES);
+                ptx::tma_load_4d(sK + st * KV_BYTES, &p.tmK, &k_full[st], 0, h, t * BKV, kvb);
+                ptx::mbar_wait(&v_empty[st], ph ^ 1u);
+                ptx::mbar_expect_tx(&v_full[st], KV_BYTES);
+                ptx::tma_load_4d(sV + st * KV_BYTES, &p.tmV, &v_full[st], 0, h, t * BKV, kvb);
+                if (++st == KV_STAGES) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint64_t dq = ptx::umma_smem_desc_sw128(ptx::smem_u32(sQ));
-            const uint64_t dk = ptx::umma_smem_desc_sw128(ptx::smem_u32(sK));
-            const uint64_t dp0 = ptx::umma_smem_desc_sw128(ptx::smem_u32(sP));
-            const uint64_t dp1 = ptx::umma_smem_desc_sw128(ptx::smem_u32(sP + TILE_BYTES));
-            const uint64_t dv = umma_desc_mn_sw128(ptx::smem_u32(sV));
-            ptx::mbar_wait(q_full, 0);
-            for (int t = 0; t < ntiles; ++t) {
-                const uint32_t ph = (uint32_t)t & 1u;
-                // ---- S = Q K^T   (S of the previous tile has been consumed: p_full(t-1) was waited before PV(t-1))
-                ptx::mbar_wait(k_full, ph);
+            int kst = 0; uint32_t kph = 0;                               // K ring position of the next Q K^T
+            auto issue_qk = [&](int t) {
+                ptx::mbar_wait(&k_full[kst], kph);
                 ptx::tc_fence_after();
+                const uint64_t dk = ptx::umma_smem_desc_sw128(ptx::smem_u32(sK + kst * KV_BYTES));
 #pragma unroll
                 for (int k = 0; k < KS; ++k)
-                    ptx::umma_bf16(tmem_base, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), IDESC_S, k > 0 ? 1u : 0u);
-                ptx::umma_commit(k_empty);
-                ptx::umma_commit(s_full);
-                // ---- O_h += P_h V_h for the two key halves (own accumulators, accumulated over all tiles)
-                ptx::mbar_wait(v_full, ph);
+                    ptx::umma_bf16(tmem_base + (uint32_t)(t & 1) * 64u, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), IDESC_S, k > 0 ? 1u : 0u);
+                ptx::umma_commit(&k_empty[kst]);
+                ptx::umma_commit(&s_full[t & 1]);
+                if (++kst == KV_STAGES) { kst = 0; kph ^= 1u; }
+            };
+            ptx::mbar_wait(q_full, 0);
+            issue_qk(0);
+            if (ntiles > 1) issue_qk(1);
+            int vst = 0; uint32_t vph = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                // ---- O_h += P_h V_h for the two key streams (own accumulators, accumulated over all tiles)
+                ptx::mbar_wait(&v_full[vst], vph);
+                ptx::mbar_wait(&p_full[t & 1], (uint32_t)(t >> 1) & 1u);
+                ptx::tc_fence_after();
+                const uint64_t dp = ptx::umma_smem_desc_sw128(ptx::smem_u32(sP + (t & 1) * P_BYTES));
+                const uint64_t dv = umma_desc_mn_sw128(ptx::smem_u32(sV + vst * KV_BYTES));
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    ptx::mbar_wait(&p_full[hh], ph);
-                    ptx::tc_fence_after();
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = (hh == 0 ? dp0 : dp1) + (uint64_t)(k * 2);               // +32 B per 16 keys inside the 64-key atom
-                        const uint64_t db = dv + (uint64_t)((hh * 4 + k) * 16 * 128 >> 4);           // +16 key rows of 128 B
+                    for (int k = 0; k < 2; ++k) {
+                        const uint64_t da = dp + (uint64_t)((hh * 2 + k) * 2);                       // +32 B per 16 keys inside the 64-key atom
+                        const uint64_t db = dv + (uint64_t)((hh * 2 + k) * 16 * 128 >> 4);           // +16 key rows of 128 B
                         ptx::umma_bf16(tmem_base + 128 + hh * 64, da, db, IDESC_O, (t > 0 || k > 0) ? 1u : 0u);
                     }
                 }
-                ptx::umma_commit(v_empty);
-                ptx::umma_commit(pv_full);
+                ptx::umma_commit(&v_empty[vst]);
+                ptx::umma_commit(&pv_done[t & 1]);
+                if (++vst == KV_STAGES) { vst = 0; vph ^= 1u; }
+                // S buffer (t & 1) has been consumed (p_full(t) implies the softmax threads are done reading it)
+                if (t + 2 < ntiles) issue_qk(t + 2);
             }
         }
     } else {
         // ================= softmax / output: TWO threads per query row (8 warps) =================
-        // warps 2..5 ("half 0") own keys [0,64) of every tile and output columns [0,32); warps 6..9 ("half 1") own keys
-        // [64,128) and output columns [32,D).  A warp may only touch TMEM lanes 32*(warp%4)..+31, so the two threads of
-        // row r sit in warps with equal warp%4.  Per tile the halves exchange one float (their partial row max) through
-        // shared memory; row sums are kept per half and combined once at the end.
+        // warps 2..5 ("stream 0") own keys [0,32) of every tile and output columns [0,32); warps 6..9 ("stream 1") own keys
+        // [32,64) and output columns [32,D).  A warp may only touch TMEM lanes 32*(warp%4)..+31, so the two threads of
+        // row r sit in warps with equal warp%4.
         const int qd = warp & 3;
         const int half = (warp - 2) >> 2;
         const int r = qd * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
         const uint32_t oaddr = taddr + 128 + half * 64;                  // this stream's accumulator (64 columns, D <= 64 used)
-        uint8_t* prow = sP + half * TILE_BYTES + r * 128;                 // this half's 64-key atom of P
         const int swz = r & 7;
         constexpr float RAISE = 8.f;                                     // raise the running max only beyond 2^8 of head room
         float m_sc = -INFINITY;                                          // running max * scale*log2(e) (the exponent offset in use)
         float l_run = 0.f;
         for (int t = 0; t < ntiles; ++t) {
-            const uint32_t ph = (uint32_t)t & 1u;
-            ptx::mbar_wait(s_full, ph);
+            const int buf = t & 1;
+            ptx::mbar_wait(&s_full[buf], (uint32_t)(t >> 1) & 1u);
             ptx::tc_fence_after();
-            const int kbase = t * BKV + half * 64;
+            const int kbase = t * BKV + half * 32;
             const bool ragged = t * BKV + BKV > p.Sk;
             uint32_t u[32];
-            // pass 1: row max over this stream's 64 keys
+            ptx::tmem_ld32(taddr + buf * 64 + half * 32, u);
+            ptx::tmem_ld_wait();
+            if (ragged) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (kbase + j >= p.Sk) u[j] = 0xff800000u;     // -inf
+            }
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                ptx::tmem_ld32(taddr + half * 64 + c * 32, u);
-                ptx::tmem_ld_wait();
-                if (ragged) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (kbase + c * 32 + j >= p.Sk) ? -INFINITY : __uint_as_float(u[j]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) mx = max3(mx, __uint_as_float(u[j]), __uint_as_float(u[j + 1]));
-                }
-            }
-            const float mx_sc = mx * p.scale_log2;                   // -inf when this half of a ragged tile holds no key
+            for (int j = 0; j < 32; j += 2) mx = max3(mx, __uint_as_float(u[j]), __uint_as_float(u[j + 1]));
+            const float mx_sc = mx * p.scale_log2;                   // -inf when this stream holds no key of a ragged tile
             const bool raise = mx_sc > m_sc + RAISE || (m_sc == -INFINITY && mx_sc > -INFINITY);
             if (t > 0 && __any_sync(0xffffffffu, raise)) {
                 // rescale this stream's accumulator (rows that do not raise use factor 1): needs P.V(t-1) retired
-                ptx::mbar_wait(pv_full, ph ^ 1u);
+                ptx::mbar_wait(&pv_done[(t - 1) & 1], (uint32_t)((t - 1) >> 1) & 1u);
                 ptx::tc_fence_after();
                 const float corr = raise ? ex2(m_sc - mx_sc) : 1.f;   // m_sc == -inf (stream empty so far) -> 0
                 l_run *= corr;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    ptx::tmem_ld32(oaddr + c * 32, u);
+                uint32_t w[8];
+#pragma unroll 1
+                for (int c = 0; c < DP / 8; ++c) {                   // 8 columns at a time: S stays in registers
+                    ptx::tmem_ld8(oaddr + c * 8, w);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(__uint_as_float(u[j]) * corr);
-                    ptx::tmem_st32(oaddr + c * 32, u);
+                    for (int j = 0; j < 8; ++j) w[j] = __float_as_uint(__uint_as_float(w[j]) * corr);
+                    ptx::tmem_st8(oaddr + c * 8, w);
                 }
                 ptx::tmem_st_wait();
             }
             if (raise) m_sc = mx_sc;
             const float msc = m_sc == -INFINITY ? 0.f : m_sc;        // empty stream: exp2(-inf - 0) = 0
-            // pass 2: p = exp2(s*scale - m*scale), row sum, P -> smem (bf16, K-major SW128)
+            // P buffer `buf` was last read by P.V(t-2)
+            if (t >= 2) ptx::mbar_wait(&pv_done[buf], (uint32_t)((t - 2) >> 1) & 1u);
+            uint8_t* prow = sP + buf * P_BYTES + r * 128;
             float ps = 0.f;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                ptx::tmem_ld32(taddr + half * 64 + c * 32, u);
-                ptx::tmem_ld_wait();
+            for (int i = 0; i < 4; ++i) {                             // 4 chunks of 8 keys = 16 B each
+                uint32_t pk[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {                         // 4 chunks of 8 keys = 16 B each
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = i * 8 + jj * 2;
-                        float s0 = __uint_as_float(u[j]), s1 = __uint_as_float(u[j + 1]);
-                        if (ragged) {
-                            if (kbase + c * 32 + j >= p.Sk) s0 = -INFINITY;
-                            if (kbase + c * 32 + j + 1 >= p.Sk) s1 = -INFINITY;
-                        }
-                        const float p0 = ex2(fmaf(s0, p.scale_log2, -msc)), p1 = ex2(fmaf(s1, p.scale_log2, -msc));
-                        ps += p0 + p1;                               // fp32 row sum (rounding of P is zero-mean)
-                        __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                        pk[jj] = *reinterpret_cast<uint32_t*>(&pb);
-                    }
-                    const int chunk = (c * 4 + i) ^ swz;              // XOR-swizzled 16-byte slot inside the 128-byte row
-                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = i * 8 + jj * 2;
+                    const float p0 = ex2(fmaf(__uint_as_float(u[j]), p.scale_log2, -msc));
+                    const float p1 = ex2(fmaf(__uint_as_float(u[j + 1]), p.scale_log2, -msc));
+                    ps += p0 + p1;                                   // fp32 row sum (rounding of P is zero-mean)
+                    __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                    pk[jj] = *reinterpret_cast<uint32_t*>(&pb);
                 }
+                const int chunk = (half * 4 + i) ^ swz;               // XOR-swizzled 16-byte slot inside the 128-byte row
+                *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
             l_run += ps;
             ptx::fence_proxy_async();                                // generic-proxy smem writes -> visible to the MMA (async proxy)
             ptx::tc_fence_before();                                  // our TMEM reads of S / writes of O are ordered before the arrive
-            ptx::mbar_arrive(&p_full[half]);
+            ptx::mbar_arrive(&p_full[buf]);
         }
         // merge the two streams of the row: O = (O_0 e_0 + O_1 e_1) / (l_0 e_0 + l_1 e_1), e_h = 2^(m_h - max(m_0, m_1))
         s_ml[half * 128 + r] = make_float2(m_sc, l_run);
-        ptx::mbar_wait(pv_full, (uint32_t)(ntiles - 1) & 1u);
+        ptx::mbar_wait(&pv_done[(ntiles - 1) & 1], (uint32_t)((ntiles - 1) >> 1) & 1u);
         ptx::tc_fence_after();
         asm volatile("bar.sync 2, 256;" ::: "memory");
         const float2 other = s_ml[(half ^ 1) * 128 + r];
-        const float m_all = fmaxf(m_sc, other.x);                    // finite: half 0 always holds a key
+        const float m_all = fmaxf(m_sc, other.x);                    // finite: stream 0 always holds a key
         const float e_me = ex2(m_sc - m_all), e_ot = ex2(other.x - m_all);
         const float inv = 1.f / (l_run * e_me + other.y * e_ot);
         const float w_me = e_me * inv, w_ot = e_ot * inv;
-        constexpr int OD = 32;                                           // output columns per thread (half 1 stores D - 32 of them)
+        constexpr int OD = 32;                                           // output columns per thread (stream 1 stores D - 32 of them)
         const int my_d0 = half * 32;
         const int my_nd = half == 0 ? (D < 32 ? D : 32) : D - 32;
         float o[OD];
@@ -287,12 +289,12 @@ EncodeTiledFn get_encode() {
 }
 
 // (d, head, token, batch) view of a [B][S][row] bf16 buffer whose row holds `heads` heads of D elements
-int encode_heads(CUtensorMap* m, const void* base, int D, int heads, int S, int B, int64_t row, int64_t batch) {
+int encode_heads(CUtensorMap* m, const void* base, int D, int heads, int S, int B, int64_t row, int64_t batch, int box_tokens) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return sdk_fail(SDK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     const cuuint64_t gdim[4] = {(cuuint64_t)D, (cuuint64_t)heads, (cuuint64_t)S, (cuuint64_t)B};
     const cuuint64_t gstr[3] = {(cuuint64_t)D * 2, (cuuint64_t)row * 2, (cuuint64_t)(batch > 0 ? batch : (int64_t)S * row) * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)DP, 1u, 128u, 1u};
+    const cuuint32_t box[4] = {(cuuint32_t)DP, 1u, (cuuint32_t)box_tokens, 1u};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -304,7 +306,7 @@ struct AttnPlan { AttnParams prm; dim3 grid; int D; };
 
 template <int D>
 int launch(const AttnPlan* a, cudaStream_t s) {
-    constexpr int smem = 5 * TILE_BYTES + 1024 + 256 + 4 * 128 * 4;
+    constexpr int smem = Q_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES + 1024 + 256 + 2 * 128 * 8;
     static bool configured = false;
     if (!configured) {
         SDK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -330,10 +332,10 @@ extern "C" int sdk_attention_tc_create(const void* q, int64_t q_row, int64_t q_b
     AttnPlan* a = new (std::nothrow) AttnPlan();
     if (!a) return sdk_fail(SDK_ERR_CUDA, "out of host memory");
     memset(&a->prm, 0, sizeof(a->prm));
-    int rc = encode_heads(&a->prm.tmQ, q, D, heads, Sq, B, q_row, q_batch);
+    int rc = encode_heads(&a->prm.tmQ, q, D, heads, Sq, B, q_row, q_batch, BQ);
     const int kvB = k_batch == 0 ? 1 : B;
-    if (rc == SDK_OK) rc = encode_heads(&a->prm.tmK, k, D, heads, Sk, kvB, k_row, k_batch);
-    if (rc == SDK_OK) rc = encode_heads(&a->prm.tmV, v, D, heads, Sk, kvB, v_row, v_batch);
+    if (rc == SDK_OK) rc = encode_heads(&a->prm.tmK, k, D, heads, Sk, kvB, k_row, k_batch, BKV);
+    if (rc == SDK_OK) rc = encode_heads(&a->prm.tmV, v, D, heads, Sk, kvB, v_row, v_batch, BKV);
     if (rc != SDK_OK) { delete a; return rc; }
     a->prm.out = (__nv_bfloat16*)out; a->prm.o_row = o_row; a->prm.o_batch = o_batch;
     a->prm.heads = heads; a->prm.Sq = Sq; a->prm.Sk = Sk; a->prm.kv_bcast = k_batch == 0;
