@@ -28,6 +28,7 @@
 #include "../../include/sdb200.h"
 #include <new>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -950,7 +951,11 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     const int fixed = fixed_smem(bn, p.epi_res != 0), per_stage = stage_smem(bn, two);
     const int min_stages = p.epi_tma ? (EPI_BUFS * p.epi_buf_stride + per_stage - 1) / per_stage : 2;   // chunk buffers alias the stages
     const int SMEM_1 = 232448, SMEM_2 = 115712;       // opt-in limit per CTA; per CTA when two share an SM (1 KiB reserved each)
-    g->co_resident = !two && p.kb_per_split <= 12;
+    // ... and multi-wave grids: with two CTAs per SM the prologue / epilogue of one tile overlaps the main loop of another
+    const long long total_ctas = (long long)m_tiles * n_tiles * splits;
+    // (measured at UNet batch 16: GEMM family 14.8 -> 14.1 ms/step; SDB200_TC_CORES2=0 turns it off, N = "more than N waves")
+    static const int multiwave_mode = getenv("SDB200_TC_CORES2") ? atoi(getenv("SDB200_TC_CORES2")) : 1;
+    g->co_resident = !two && (p.kb_per_split <= 12 || (multiwave_mode && total_ctas > (long long)sms * multiwave_mode));
     int stages = 0;
     if (g->co_resident) {
         stages = (SMEM_2 - fixed) / per_stage;

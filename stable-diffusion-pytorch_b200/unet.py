@@ -174,7 +174,7 @@ class StepProgram:
         # GroupNorm statistics from per-channel sums accumulated by the producing GEMM (bf16 program) instead of a statistics
         # kernel.  All tables live in one arena that the program zeroes with its first op.
         self.gn_from_sums = pw.precision != "fp32" and net.gn_mode == "sums"
-        self.stat_arena = torch.zeros(8 << 20, dtype=torch.uint8, device=dev) if self.gn_from_sums else None
+        self.stat_arena = torch.zeros(max(4, 2 * B) << 20, dtype=torch.uint8, device=dev) if self.gn_from_sums else None
         self.stat_used = 0
 
         f32 = torch.float32
