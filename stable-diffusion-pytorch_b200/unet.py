@@ -253,6 +253,8 @@ class StepProgram:
         d.bias, d.tbias, d.tb_stride, d.residual, d.out = p.bias, p.tbias, p.tb_stride, p.residual, p.out
         d.out_dtype, d.geglu, d.out_nchw = p.out_dtype, p.geglu, p.out_nchw
         d.block_n, d.splits, d.w_kmajor, d.two_cta = self.net.tc_block_n, self.net.tc_splits, 1, self.net.tc_two_cta
+        if self.net.tc_autotune and not d.block_n and not d.splits:
+            d.block_n, d.splits = self._autotune(d, srcs[0][0], cs)
         h = C.c_void_p()
         _lib.check(self.lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
         self.tc_handles.append(h)
@@ -266,6 +268,82 @@ class StepProgram:
             return False
         _lib.check(rc)
         return True
+
+    # ---- plan-time autotuning of the GEMM tiling -----------------------------------------------
+    _tune_cache: Dict[tuple, tuple] = {}
+
+    def _autotune(self, d, a_tensor, cs):
+        """Time the candidate (block_n, split-K) tilings of this layer shape on the device, in the state the step sees them:
+        weights cold (each step streams 1.7 GB of them through a 126 MB L2), activations warm.  The library's cost model picks
+        the starting point; this replaces modelled by measured time.  One measurement per distinct shape per process."""
+        key = (d.B, d.H, d.W, d.N, d.nseg, d.C[0], d.ksize[0], d.C[1], d.geglu, d.out_dtype, bool(d.residual), bool(d.tbias),
+               cs is not None, torch.cuda.get_device_name(self.device))
+        hit = StepProgram._tune_cache.get(key)
+        if hit is not None:
+            return hit
+        lib = self.lib
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if not hasattr(self, "_tune_flush"):
+            self._tune_flush = torch.empty(192 << 20, dtype=torch.uint8, device=self.device)
+        total_kb = (d.C[0] // 64) * d.ksize[0] * d.ksize[0] + ((d.C[1] // 64) if d.nseg > 1 else 0)
+        cands = [(0, 0)]
+        for bn in (32, 64, 128, 160, 256):
+            if d.N % bn != 0 and d.N > bn:
+                continue
+            if d.N <= bn // 2 and bn > 32:
+                continue
+            for sp in (1, 2, 3, 4, 6, 8, 12, 16, 24):
+                if sp > 1 and total_kb // sp < 4:
+                    continue
+                cands.append((bn, sp))
+        best, best_t, auto_t = (0, 0), float("inf"), None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        REPS = 6
+
+        def timed(launch):
+            """REPS x (evict the weights from L2, pull the activations back in, launch) in one event-timed region: the event
+            clock ticks in ~2 us steps, far too coarse for one 15 us launch."""
+            e0.record()
+            for _ in range(REPS):
+                self._tune_flush.zero_()
+                a_tensor.view(torch.int16).max()
+                if launch is not None and launch() != 0:
+                    return None
+            e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1) / REPS
+
+        timed(None)
+        base = min(timed(None), timed(None))                 # cost of the eviction + touch alone
+        for bn, sp in cands:
+            d.block_n, d.splits = bn, sp
+            h = C.c_void_p()
+            if lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)) != 0:
+                continue
+            ws = torch.empty(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=self.device)
+            ok = lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr()) == 0
+            if ok and cs is not None:
+                ok = lib.sdk_tc_gemm_set_stats(h, cs.data_ptr()) in (0, -3)
+            tmin = None
+            if ok:
+                ts = [timed(lambda: lib.sdk_tc_gemm_launch(h, stream)) for _ in range(3)]
+                if None not in ts:
+                    tmin = min(ts) - base
+            torch.cuda.synchronize(self.device)
+            lib.sdk_tc_gemm_destroy(h)
+            if tmin is not None:
+                if (bn, sp) == (0, 0):
+                    auto_t = tmin
+                if tmin < best_t:
+                    best, best_t = (bn, sp), tmin
+        # keep the model's choice unless a candidate is clearly (> 4 %) faster: timing noise must not flip tilings
+        if auto_t is not None and best_t > 0.96 * auto_t:
+            best = (0, 0)
+        StepProgram._tune_cache[key] = best
+        if self.net.tc_autotune > 1:
+            print(f"autotune B{d.B} {d.H}x{d.W} C{d.C[0]} k{d.ksize[0]} N{d.N}: model {auto_t * 1e3 if auto_t else -1:.1f} us -> "
+                  f"{best} {best_t * 1e3:.1f} us", flush=True)
+        return best
 
     def _gn(self, srcs, B, HW, g, b, eps, silu, want_raw=False):
         """GroupNorm(32)(+SiLU) over the concat of srcs -> operand-typed tensor [B*HW, C]."""
@@ -593,6 +671,7 @@ class UNet(nn.Module):
         self.precision = os.environ.get("SDB200_PRECISION", "bf16")
         self.tc_block_n = int(os.environ.get("SDB200_TC_BLOCK_N", "0"))      # 0 = auto; tuning / test overrides
         self.tc_splits = int(os.environ.get("SDB200_TC_SPLITS", "0"))
+        self.tc_autotune = int(os.environ.get("SDB200_TC_AUTOTUNE", "1"))     # 1: measure tilings at plan time; 2: and print them
         self.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention for head_dim 40 / 64
         self.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
         # sums: statistics from per-channel sums reduced in the producing GEMM's epilogue (bf16 program; fastest measured) |
