@@ -270,14 +270,41 @@ class StepProgram:
         return True
 
     # ---- plan-time autotuning of the GEMM tiling -----------------------------------------------
-    _tune_cache: Dict[tuple, tuple] = {}
+    _tune_cache: Dict[str, tuple] = {}
+    _tune_file = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tune_cache.json")
+    _tune_loaded = False
+
+    @classmethod
+    def _tune_load(cls):
+        """Tilings measured earlier on this GPU model (committed with the package for the benchmark configurations; extended
+        in place when a new shape is met; SDB200_TC_TUNE_FILE overrides the location)."""
+        if cls._tune_loaded:
+            return
+        cls._tune_loaded = True
+        cls._tune_file = os.environ.get("SDB200_TC_TUNE_FILE", cls._tune_file)
+        try:
+            with open(cls._tune_file) as f:
+                cls._tune_cache.update({k: tuple(v) for k, v in json.load(f).items()})
+        except (OSError, ValueError):
+            pass
+
+    @classmethod
+    def _tune_save(cls):
+        try:
+            tmp = cls._tune_file + f".{os.getpid()}.tmp"
+            with open(tmp, "w") as f:
+                json.dump({k: list(v) for k, v in sorted(cls._tune_cache.items())}, f, indent=0)
+            os.replace(tmp, cls._tune_file)
+        except OSError:
+            pass                                             # read-only install: keep the in-process cache only
 
     def _autotune(self, d, a_tensor, cs):
         """Time the candidate (block_n, split-K) tilings of this layer shape on the device, in the state the step sees them:
         weights cold (each step streams 1.7 GB of them through a 126 MB L2), activations warm.  The library's cost model picks
         the starting point; this replaces modelled by measured time.  One measurement per distinct shape per process."""
-        key = (d.B, d.H, d.W, d.N, d.nseg, d.C[0], d.ksize[0], d.C[1], d.geglu, d.out_dtype, bool(d.residual), bool(d.tbias),
-               cs is not None, torch.cuda.get_device_name(self.device))
+        StepProgram._tune_load()
+        key = "|".join(str(x) for x in (torch.cuda.get_device_name(self.device), d.B, d.H, d.W, d.N, d.nseg, d.C[0], d.ksize[0], d.C[1],
+                                        d.geglu, d.out_dtype, int(bool(d.residual)), int(bool(d.tbias)), int(cs is not None)))
         hit = StepProgram._tune_cache.get(key)
         if hit is not None:
             return hit
@@ -340,6 +367,7 @@ class StepProgram:
         if auto_t is not None and best_t > 0.96 * auto_t:
             best = (0, 0)
         StepProgram._tune_cache[key] = best
+        StepProgram._tune_save()
         if self.net.tc_autotune > 1:
             print(f"autotune B{d.B} {d.H}x{d.W} C{d.C[0]} k{d.ksize[0]} N{d.N}: model {auto_t * 1e3 if auto_t else -1:.1f} us -> "
                   f"{best} {best_t * 1e3:.1f} us", flush=True)
