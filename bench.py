@@ -356,7 +356,7 @@ def main():
                 for label, fns in (("tc_gemm", ["sdk_tc_gemm_launch"]), ("attention", ["sdk_attention_bf16", "sdk_attention_tc_launch"]),
                                    ("groupnorm", ["sdk_groupnorm_stats", "sdk_groupnorm_apply", "sdk_groupnorm_fused", "sdk_groupnorm_apply_cs", "sdk_channel_stats"]),
                                    ("layernorm", ["sdk_layernorm"]),
-                                   ("other", ["sdk_cast_upsample", "sdk_im2col_s2", "sdk_nchw_to_nhwc", "sdk_gemv", "sdk_time_sinusoid", "sdk_conv_gemm_f32"])):
+                                   ("other", ["sdk_cast_upsample", "sdk_im2col_s2", "sdk_nchw_to_nhwc", "sdk_gemv", "sdk_time_sinusoid", "sdk_conv_gemm_f32", "sdk_conv_in"])):
                     ms, n = time_gemm_family(loop, fns=fns)
                     breakdown[label] = {"ms": ms, "launches": n}
 

@@ -78,7 +78,7 @@ int sdk_groupnorm_apply(const float* src0, int C0, const float* src1, int C1, in
 int sdk_groupnorm_apply_cs(const float* src0, int C0, const double* cs0, const float* src1, int C1, const double* cs1,
                            int B, int HW, float eps, const float* gamma, const float* beta, int silu,
                            void* out, void* raw_out, int out_dtype, void* stream);
-/* per-channel (sum, sum of squares) of an fp32 [B][HW][C] tensor -> out [B][C][2] (double, overwritten) */
+/* per-channel (sum, sum of squares) of an fp32 [B][HW][C] tensor, ACCUMULATED into out [B][C][2] (double; zero it first) */
 int sdk_channel_stats(const float* src, int B, int HW, int C, double* out, void* stream);
 /* statistics + apply in ONE cooperative launch; same workspace as sdk_groupnorm_stats */
 int sdk_groupnorm_fused(const float* src0, int C0, const float* src1, int C1, int B, int HW, float eps,
@@ -126,6 +126,10 @@ typedef struct SdkConvParams {
 } SdkConvParams;
 /* exact fp32 path (FFMA); also serves shapes the tensor-core path does not take (Cin = 4). in_dtype must be fp32. */
 int sdk_conv_gemm_f32(const SdkConvParams* p, void* stream);
+/* conv_in (unet.py:256): 3x3 / pad 1 / Cin = 4 on the fp32 NHWC latent x [B][H][W][4], w [N][3][3][4], out fp32 [B][H][W][N];
+ * chan_stats (optional, zeroed by the caller) accumulates the per-channel (sum, sum of squares) table of the output. */
+int sdk_conv_in(const float* x, const float* w, const float* bias, float* out, double* chan_stats,
+                int B, int H, int W, int N, void* stream);
 
 /* ---- attention (models/unet/attention.py:29-50): out = softmax(q k^T * scale) v per head ------
  * q/k/v/out element strides: row stride (between tokens) and batch stride; head h occupies columns

@@ -36,6 +36,7 @@ SIGNATURES = {
     "sdk_groupnorm_apply": [P, I32, P, I32, I32, I32, P, P, P, I32, P, P, I32, P],
     "sdk_groupnorm_apply_cs": [P, I32, P, P, I32, P, I32, I32, F32, P, P, I32, P, P, I32, P],
     "sdk_channel_stats": [P, I32, I32, I32, P, P],
+    "sdk_conv_in": [P, P, P, P, P, I32, I32, I32, I32, P],
     "sdk_groupnorm_fused": [P, I32, P, I32, I32, I32, F32, P, P, I32, P, P, I32, P, P],
     "sdk_groupnorm_cluster": [P, I32, P, I32, I32, I32, F32, P, P, I32, P, P, I32, P],
     "sdk_layernorm": [P, P, P, F32, P, I32, I64, I32, P],

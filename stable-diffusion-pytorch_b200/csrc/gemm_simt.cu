@@ -211,3 +211,91 @@ extern "C" int sdk_conv_gemm_f32(const SdkConvParams* p, void* stream) {
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
+
+
+// -------------------------------------------------------------------------------------------------
+// conv_in (unet.py:256): 3x3, pad 1, Cin = 4 -> N channels on the fp32 NHWC latent.  K = 36 is far too short for a GEMM
+// pipeline: the whole weight matrix (36 x N floats) sits in shared memory, a thread owns 4 output channels and walks the
+// CTA's pixels with the 9 taps (one float4 each) in registers.  Also accumulates the per-channel (sum, sum of squares)
+// table of the first GroupNorm (double atomics, as the tensor-core epilogue does).
+// -------------------------------------------------------------------------------------------------
+namespace {
+constexpr int CI_PIX = 64, CI_THREADS = 256;
+
+__global__ void __launch_bounds__(CI_THREADS)
+conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+               double2* __restrict__ cstat, int B, int H, int W, int N) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ float sm[];
+    float* w_s = sm;                                   // [36][N]
+    float* s_red = sm + 36 * N;                        // [px_lanes][N][2] column partials
+    const int quads = N >> 2, px_lanes = CI_THREADS / quads;
+    const int pl = threadIdx.x / quads, qd = threadIdx.x - pl * quads;
+    for (int i = threadIdx.x; i < 36 * N; i += CI_THREADS) {
+        const int n = i / 36, k = i - n * 36;          // coalesced read of w[n][k], transposed store
+        w_s[k * N + n] = __ldg(w + i);
+    }
+    __syncthreads();
+    const int HW = H * W;
+    const long long p0 = (long long)blockIdx.x * CI_PIX;      // CTA pixel range inside sample blockIdx.y
+    const int b = blockIdx.y;
+    float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pl < px_lanes) {
+        const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias) + qd) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int pi = pl; pi < CI_PIX; pi += px_lanes) {
+            const long long pix = p0 + pi;
+            if (pix >= HW) break;
+            const int oy = (int)(pix / W), ox = (int)(pix - (long long)oy * W);
+            float4 acc = bv;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int iy = oy + t / 3 - 1, ix = ox + t % 3 - 1;
+                if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + iy) * W + ix) * 4));
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 ww = *reinterpret_cast<const float4*>(w_s + (t * 4 + c) * N + (qd << 2));
+                    acc.x = fmaf(vv[c], ww.x, acc.x); acc.y = fmaf(vv[c], ww.y, acc.y);
+                    acc.z = fmaf(vv[c], ww.z, acc.z); acc.w = fmaf(vv[c], ww.w, acc.w);
+                }
+            }
+            *reinterpret_cast<float4*>(out + ((size_t)b * HW + pix) * N + (qd << 2)) = acc;
+            sa[0] += acc.x; sa[1] += acc.y; sa[2] += acc.z; sa[3] += acc.w;
+            qa[0] = fmaf(acc.x, acc.x, qa[0]); qa[1] = fmaf(acc.y, acc.y, qa[1]); qa[2] = fmaf(acc.z, acc.z, qa[2]); qa[3] = fmaf(acc.w, acc.w, qa[3]);
+        }
+    }
+    if (!cstat) return;
+    if (pl < px_lanes) {
+        float* d = s_red + ((size_t)pl * N + (qd << 2)) * 2;
+        *reinterpret_cast<float4*>(d) = make_float4(sa[0], qa[0], sa[1], qa[1]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(sa[2], qa[2], sa[3], qa[3]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * N; i += CI_THREADS) {         // i = channel * 2 + which
+        double acc = 0.0;
+        for (int l = 0; l < px_lanes; ++l) acc += (double)s_red[(size_t)l * N * 2 + i];
+        atomicAdd(reinterpret_cast<double*>(cstat + (size_t)b * N) + i, acc);
+    }
+}
+}  // namespace
+
+extern "C" int sdk_conv_in(const float* x, const float* w, const float* bias, float* out, double* chan_stats,
+                           int B, int H, int W, int N, void* stream) {
+    SDK_CHECK_ARG(x && w && out && B > 0 && B < 65536 && H > 0 && W > 0, "sdk_conv_in: bad args");
+    SDK_CHECK_ARG(N % 4 == 0 && N >= 4 && N / 4 <= CI_THREADS, "sdk_conv_in: N=%d must be a multiple of 4, at most %d", N, 4 * CI_THREADS);
+    const int px_lanes = CI_THREADS / (N / 4);
+    const size_t smem = sizeof(float) * ((size_t)36 * N + (size_t)px_lanes * N * 2);
+    SDK_CHECK_ARG(smem <= 200 * 1024, "sdk_conv_in: N=%d needs too much shared memory", N);
+    static size_t configured = 0;
+    if (smem > configured) {
+        SDK_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int chunks = (H * W + CI_PIX - 1) / CI_PIX;
+    SDK_CUDA(sdk_launch(conv_in_kernel, dim3(chunks, B), dim3(CI_THREADS), smem, (cudaStream_t)stream, x, w, bias, out,
+                        reinterpret_cast<double2*>(chan_stats), B, H, W, N));
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}

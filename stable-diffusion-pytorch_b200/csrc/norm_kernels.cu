@@ -692,19 +692,23 @@ extern "C" int sdk_groupnorm_apply_cs(const float* src0, int C0, const double* c
     return launch_gn_apply(a, out_dtype, (cudaStream_t)stream);
 }
 
-// Per-channel (sum, sum of squares) of an fp32 [B][HW][C] tensor -> out [B][C][2] (double, overwritten); for GroupNorm inputs whose producer cannot
-// deliver them (conv_in's FFMA kernel, unusual tilings).  CTA = (32 channels, sample); fixed-order fold (deterministic).
+// Per-channel (sum, sum of squares) of an fp32 [B][HW][C] tensor, ACCUMULATED into out [B][C][2] (double; the caller zeroes it,
+// as for sdk_tc_gemm_set_stats); for GroupNorm inputs whose producer cannot deliver them (conv_in's FFMA kernel, unusual tilings).
+// CTA = (32 channels, up to 256 rows of one sample): shared-memory fold over the 32 row lanes, then 64 double atomics.
 namespace {
+constexpr int CS_ROWS = 256;
 __global__ void __launch_bounds__(256)
 channel_stats_kernel(const float* __restrict__ src, int HW, int C, double2* __restrict__ out) {
     pdl_trigger();
     pdl_wait();
     __shared__ float s_red[32][8][8];
-    const int b = blockIdx.y, rl = threadIdx.x >> 3, q = threadIdx.x & 7, c = blockIdx.x * 32 + (q << 2);
+    const int b = blockIdx.z, rl = threadIdx.x >> 3, q = threadIdx.x & 7, c = blockIdx.x * 32 + (q << 2);
+    const int r0 = blockIdx.y * CS_ROWS, r1 = min(HW, r0 + CS_ROWS);
     float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < C) {
         const float* p = src + (size_t)b * HW * C + c;
-        for (int r = rl; r < HW; r += 32) {
+#pragma unroll 4
+        for (int r = r0 + rl; r < r1; r += 32) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)r * C));
             sa[0] += v.x; sa[1] += v.y; sa[2] += v.z; sa[3] += v.w;
             qa[0] = fmaf(v.x, v.x, qa[0]); qa[1] = fmaf(v.y, v.y, qa[1]); qa[2] = fmaf(v.z, v.z, qa[2]); qa[3] = fmaf(v.w, v.w, qa[3]);
@@ -713,19 +717,23 @@ channel_stats_kernel(const float* __restrict__ src, int HW, int C, double2* __re
     *reinterpret_cast<float4*>(&s_red[rl][q][0]) = make_float4(sa[0], sa[1], sa[2], sa[3]);
     *reinterpret_cast<float4*>(&s_red[rl][q][4]) = make_float4(qa[0], qa[1], qa[2], qa[3]);
     __syncthreads();
-    if (threadIdx.x < 32 && blockIdx.x * 32 + threadIdx.x < C) {
-        const int qq = threadIdx.x >> 2, j = threadIdx.x & 3;
-        double sum = 0.0, sq = 0.0;
+    if (threadIdx.x < 64) {
+        const int col = threadIdx.x & 31, which = threadIdx.x >> 5;        // which: 0 = sum, 1 = sum of squares
+        if (blockIdx.x * 32 + col < C) {
+            const int qq = col >> 2, j = (col & 3) + 4 * which;
+            double acc = 0.0;
 #pragma unroll 8
-        for (int l = 0; l < 32; ++l) { sum += (double)s_red[l][qq][j]; sq += (double)s_red[l][qq][4 + j]; }
-        out[(size_t)b * C + blockIdx.x * 32 + threadIdx.x] = make_double2(sum, sq);
+            for (int l = 0; l < 32; ++l) acc += (double)s_red[l][qq][j];
+            atomicAdd(reinterpret_cast<double*>(out + (size_t)b * C + blockIdx.x * 32 + col) + which, acc);
+        }
     }
 }
 }  // namespace
 
 extern "C" int sdk_channel_stats(const float* src, int B, int HW, int C, double* out, void* stream) {
     SDK_CHECK_ARG(src && out && B > 0 && B < 65536 && HW > 0 && C > 0 && C % 4 == 0, "sdk_channel_stats: bad args");
-    SDK_CUDA(sdk_launch(channel_stats_kernel, dim3((C + 31) / 32, B), dim3(256), (size_t)0, (cudaStream_t)stream, src, HW, C, reinterpret_cast<double2*>(out)));
+    SDK_CUDA(sdk_launch(channel_stats_kernel, dim3((C + 31) / 32, (HW + CS_ROWS - 1) / CS_ROWS, B), dim3(256), (size_t)0, (cudaStream_t)stream, src, HW, C,
+                        reinterpret_cast<double2*>(out)));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }

@@ -547,8 +547,17 @@ class StepProgram:
         # conv_in (unet.py:256): NCHW latent -> NHWC, then 3x3 conv with Cin = 4 (FFMA kernel: K = 36)
         xin = self.pool.get(B * H * W, a.in_channels, F32_T)
         self._emit(lib.sdk_nchw_to_nhwc, self.x_in.data_ptr(), xin.data_ptr(), self.b_src, B, a.in_channels, H * W)
-        x, _, _ = self._conv([(xin, a.in_channels)], t["conv_in.w"], t["conv_in.b"], B, H, W, BLOCK_OUT[0], k=3,
-                             in_code=F32_T, force_simt=True, want_stats=True)
+        if a.in_channels == 4:
+            # dedicated K = 36 kernel; also accumulates the statistics table of the first GroupNorm
+            x = self.pool.get(B * H * W, BLOCK_OUT[0], F32_T)
+            cs = self._stat_table(B, BLOCK_OUT[0]) if self.gn_from_sums else None
+            self._emit(lib.sdk_conv_in, xin.data_ptr(), t["conv_in.w"].data_ptr(), t["conv_in.b"].data_ptr(), x.data_ptr(),
+                       cs.data_ptr() if cs is not None else 0, B, H, W, BLOCK_OUT[0])
+            if cs is not None:
+                x._cstats = cs
+        else:
+            x, _, _ = self._conv([(xin, a.in_channels)], t["conv_in.w"], t["conv_in.b"], B, H, W, BLOCK_OUT[0], k=3,
+                                 in_code=F32_T, force_simt=True, want_stats=True)
         self.pool.put(xin)
         skips = [(x, BLOCK_OUT[0], H, W)]
         h, w = H, W

@@ -377,8 +377,8 @@ def test_groupnorm_from_channel_sums(dev, shape):
     s1 = gen((B, HW, C1), 42, dev) if C1 else None
     Ct = C0 + C1
     gamma, beta = gen((Ct,), 43, dev) * 0.1 + 1, gen((Ct,), 44, dev) * 0.1
-    cs0 = torch.full((B, C0, 2), float("nan"), device=dev, dtype=torch.float64)
-    cs1 = torch.full((B, max(C1, 1), 2), float("nan"), device=dev, dtype=torch.float64)
+    cs0 = torch.zeros((B, C0, 2), device=dev, dtype=torch.float64)             # the kernel accumulates into a zeroed table
+    cs1 = torch.zeros((B, max(C1, 1), 2), device=dev, dtype=torch.float64)
     _lib.check(lib.sdk_channel_stats(s0.data_ptr(), B, HW, C0, cs0.data_ptr(), stream()))
     if C1:
         _lib.check(lib.sdk_channel_stats(s1.data_ptr(), B, HW, C1, cs1.data_ptr(), stream()))
@@ -392,6 +392,23 @@ def test_groupnorm_from_channel_sums(dev, shape):
                                               B, HW, 1e-5, gamma.data_ptr(), beta.data_ptr(), 1, out.data_ptr(), raw.data_ptr(), odt, stream()))
         assert rel_l2(out.float(), want) < tol
         assert rel_l2(raw.float(), x) < (1e-7 if odt == F32_T else 4e-3)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 320), (3, 24, 40, 320), (1, 8, 8, 64)])
+def test_conv_in(dev, shape):
+    """conv_in kernel (3x3, Cin=4, fp32) and its statistics table vs F.conv2d."""
+    B, H, W, N = shape
+    lib = _lib.lib()
+    x = gen((B, H, W, 4), 71, dev)
+    w = gen((N, 3, 3, 4), 72, dev, 1.0 / 6.0)
+    bias = gen((N,), 73, dev, 0.1)
+    out = torch.full((B, H, W, N), float("nan"), device=dev)
+    cs = torch.zeros((B, N, 2), device=dev, dtype=torch.float64)
+    _lib.check(lib.sdk_conv_in(x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), cs.data_ptr(), B, H, W, N, stream()))
+    want = Fn.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
+    assert rel_l2(out, want) < 2e-6
+    flat = out.view(B, H * W, N).double()
+    assert rel_l2(cs[..., 0], flat.sum(1)) < 1e-6 and rel_l2(cs[..., 1], (flat * flat).sum(1)) < 1e-6
 
 
 TC_STATS_CASES = [
