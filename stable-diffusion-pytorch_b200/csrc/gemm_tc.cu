@@ -399,7 +399,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                     if (glu) {                         // (value, gate) column pairs -> 16 bf16 outputs (models/activation_fn.py:17-20)
                         float o[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf_f(v[2 * j + 1]);
+                        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf_bf16out(v[2 * j + 1]);
 #pragma unroll
                         for (int j = 0; j < 2; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob + ((j ^ swz) << 4)), o + 8 * j);
                     } else if (rowbytes == 64) {       // bf16 output
@@ -566,6 +566,266 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         ptx::tc_fence_after();
         if (TWO) ptx::tmem_dealloc2(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Persistent form for multi-wave grids (large batch): one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ... (n-tile
+// fastest, so neighbouring CTAs share the A tile in L2).  The fp32 accumulator is DOUBLE-BUFFERED in TMEM: while the four
+// epilogue warps drain tile i (bias / residual / GEGLU / statistics -> swizzled smem -> TMA store), the producer and MMA
+// warps already run the main loop of tile i+1 into the other buffer; barriers, TMEM and descriptors are set up once per
+// CTA.  Short-K layers (q/k/v, attention out, GEGLU-in at K = 320...1280) are epilogue-bound at UNet batch 16: their tile
+// time drops from prologue + main loop + epilogue to max(main loop, epilogue).
+// Supports the direct TMA epilogue only (single CTA, no split-K); everything else runs conv_gemm_tc_kernel.
+// -------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
+    constexpr int B_STAGE_BYTES = BN * BK * 2;
+    constexpr int NCH = BN / 32;
+    constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM, BN);
+    const int STAGES = p.stages;
+
+    // shared memory: [A stages][B stages][3 output chunks][2 residual chunks (only with a TMA residual)][barriers][s_add][s_stat]
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint8_t* sOut = sB + STAGES * B_STAGE_BYTES;
+    uint8_t* sRes = sOut + EPI_BUFS * p.epi_buf_stride;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (p.epi_res ? 2 * RES_BUF_BYTES : 0));
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* acc_full = empty + MAX_STAGES;          // [2] MMA -> epilogue: accumulator buffer complete
+    uint64_t* acc_empty = acc_full + 2;               // [2] epilogue -> MMA: accumulator buffer drained
+    uint64_t* res_full = acc_empty + 2;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+    float* s_add = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
+    float2* s_stat = reinterpret_cast<float2*>(s_add + ADD_ROWS * BN);        // [2][4][32]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = p.N / BN;
+    const int total = p.tiles_w * p.tiles_h * p.tiles_b * n_tiles;
+    const int n_it = p.total_kb;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 1); ptx::mbar_init(&res_full[i], 1); }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tmap(&p.tmA[0]);
+        ptx::prefetch_tmap(&p.tmB[0]);
+        if (p.nseg > 1) { ptx::prefetch_tmap(&p.tmA[1]); ptx::prefetch_tmap(&p.tmB[1]); }
+        ptx::prefetch_tmap(&p.tmOut);
+        if (p.epi_res) ptx::prefetch_tmap(&p.tmRes);
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 2 * TMEM_COLS); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
+
+    // tile id -> (pixel-tile origin, first output column, tile indices inside the image)
+    auto coords = [&](int t, int& w0, int& h0, int& b0, int& n0) {
+        const int ni = t % n_tiles; int m = t / n_tiles;
+        const int tw = m % p.tiles_w; m /= p.tiles_w;
+        const int th = m % p.tiles_h; m /= p.tiles_h;
+        w0 = tw * p.TW; h0 = th * p.TH; b0 = m * p.TB; n0 = ni * BN;
+    };
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            const uint32_t stage_bytes = (uint32_t)p.rows * (BK * 2) + (uint32_t)B_STAGE_BYTES;
+            const int seg0_its = p.seg_taps[0] * p.seg_kb[0];
+            int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                int w0, h0, b0, n0;
+                coords(t, w0, h0, b0, n0);
+                for (int i = 0; i < n_it; ++i) {
+                    int it = i, seg = 0;
+                    if (it >= seg0_its) { it -= seg0_its; seg = 1; }
+                    const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
+                    int dx = 0, dy = 0;
+                    if (p.seg_ksize[seg] == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
+                    ptx::mbar_wait(&empty[s], ph ^ 1u);
+                    ptx::mbar_expect_tx(&full[s], stage_bytes);
+                    ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 + dx, h0 + dy, b0);
+                    if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, tap * p.seg_kb[seg] + kb);
+                    else ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, n0);
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            int lt = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+                const int ab = lt & 1;
+                ptx::mbar_wait(&acc_empty[ab], ((uint32_t)(lt >> 1) & 1u) ^ 1u);     // epilogue of tile lt-2 has drained this buffer
+                ptx::tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)ab * TMEM_COLS;
+                for (int i = 0; i < n_it; ++i) {
+                    ptx::mbar_wait(&full[s], ph);
+                    ptx::tc_fence_after();
+                    const uint64_t da = ptx::umma_smem_desc_sw128(ptx::smem_u32(sA + s * A_STAGE_BYTES));
+                    const uint64_t db = ptx::umma_smem_desc_sw128(ptx::smem_u32(sB + s * B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        ptx::umma_bf16(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (i > 0 || k > 0) ? 1u : 0u);
+                    ptx::umma_commit(&empty[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                }
+                ptx::umma_commit(&acc_full[ab]);
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                    // tile row == TMEM lane
+        const int et = threadIdx.x - 64;                // 0..127 within the epilogue warps
+        const int tb_i = r / (p.TW * p.TH);
+        const int rowbytes = p.epi_rowbytes;
+        const uint32_t swz = ((uint32_t)(r * rowbytes) >> 7) & (uint32_t)p.epi_swz;
+        const bool in_box = r < p.rows;
+        const float* my_add = s_add + (in_box ? tb_i : 0) * BN;
+        const bool glu = p.geglu != 0;
+        const bool do_stats = p.cstat_out != nullptr;
+        uint32_t res_use0 = 0, res_use1 = 0;             // completed uses of the two residual buffers (mbarrier parity)
+        uint32_t gc = 0;                                // output chunks issued so far (ring position)
+        int lt = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            int w0, h0, b0, n0;
+            coords(t, w0, h0, b0, n0);
+            const int ab = lt & 1;
+            const uint32_t taddr = tmem_base + (uint32_t)ab * TMEM_COLS + ((uint32_t)(q * 32) << 16);
+            // residual chunks 0 and 1 of this tile (buffers are free: every thread passed the last barrier of the previous tile)
+            if (p.epi_res && et == 0) {
+#pragma unroll
+                for (int c = 0; c < (NCH < 2 ? NCH : 2); ++c) {
+                    ptx::mbar_expect_tx(&res_full[c], (uint32_t)p.rows * 128u);
+                    ptx::tma_load_4d(sRes + c * RES_BUF_BYTES, &p.tmRes, &res_full[c], n0 + c * 32, w0, h0, b0);
+                }
+            }
+            // s_add[tb][j] = bias[n0+j] + tbias[b0+tb][n0+j] (previous tile's readers are past their last barrier)
+            for (int i = et; i < p.TB * BN; i += 128) {
+                const int tbi = i / BN, j = i - tbi * BN;
+                float x = 0.f;
+                if (p.bias) x = __ldg(p.bias + n0 + j);
+                if (p.tbias && b0 + tbi < p.B) x += __ldg(p.tbias + (long long)(b0 + tbi) * p.tb_stride + n0 + j);
+                s_add[i] = x;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int stat_rows = p.TB > 1 ? p.rows : p.TW * min(p.TH, p.H - h0);
+            auto cstat_flush = [&](int cc) {
+                const int rps = p.TW * p.TH;
+                const int smp = et >> 5;
+                if (smp < p.TB && b0 + smp < p.B) {
+                    const int p_lo = p.TB > 1 ? smp * (rps >> 5) : 0, p_n = p.TB > 1 ? (rps >> 5) : 4;
+                    double sum = 0.0, sq = 0.0;
+                    for (int i = 0; i < p_n; ++i) {
+                        const float2 v2 = s_stat[((cc & 1) * 4 + p_lo + i) * 32 + lane];
+                        sum += (double)v2.x; sq += (double)v2.y;
+                    }
+                    double* dst = reinterpret_cast<double*>(p.cstat_out + (size_t)(b0 + smp) * p.N + n0 + cc * 32 + lane);
+                    atomicAdd(dst, sum);
+                    atomicAdd(dst + 1, sq);
+                }
+            };
+            const int ocol0 = glu ? (n0 >> 1) : n0;
+
+            ptx::mbar_wait(&acc_full[ab], (uint32_t)(lt >> 1) & 1u);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c, ++gc) {
+                uint32_t u[32];
+                ptx::tmem_ld32(taddr + c * 32, u);
+                uint8_t* obuf = sOut + (gc % EPI_BUFS) * p.epi_buf_stride;
+                uint8_t* ob = obuf + r * rowbytes;
+                ptx::tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 a = *reinterpret_cast<const float4*>(my_add + c * 32 + j);     // warp-wide broadcast
+                    v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+                }
+                if (p.epi_res) {
+                    const uint32_t par = (c & 1) ? (res_use1++ & 1u) : (res_use0++ & 1u);
+                    ptx::mbar_wait(&res_full[c & 1], par);
+                    const uint8_t* rb = sRes + (c & 1) * RES_BUF_BYTES + r * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 a = *reinterpret_cast<const float4*>(rb + ((j ^ (r & 7)) << 4));
+                        v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                    }
+                }
+                if (in_box) {
+                    if (glu) {
+                        float o[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf_bf16out(v[2 * j + 1]);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob + ((j ^ swz) << 4)), o + 8 * j);
+                    } else if (rowbytes == 64) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob + ((j ^ swz) << 4)), v + 8 * j);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(ob + ((j ^ swz) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+                ptx::fence_proxy_async();
+                if (c == NCH - 1) ptx::tc_fence_before();   // last TMEM read of this accumulator buffer is done
+                if (et == 0) ptx::bulk_wait_read<1>();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    if (c == NCH - 1) ptx::mbar_arrive(&acc_empty[ab]);      // the MMA warp may overwrite this buffer (tile lt+2)
+                    ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
+                    ptx::bulk_commit();
+                    if (p.epi_res && c + 2 < NCH) {
+                        ptx::mbar_expect_tx(&res_full[c & 1], (uint32_t)p.rows * 128u);
+                        ptx::tma_load_4d(sRes + (c & 1) * RES_BUF_BYTES, &p.tmRes, &res_full[c & 1], n0 + (c + 2) * 32, w0, h0, b0);
+                    }
+                }
+                if (do_stats) {
+                    if (c > 0) cstat_flush(c - 1);
+                    const uint8_t* cb = obuf + ((lane & 3) << 2);
+                    const int r_lo = (et >> 5) * 32, r_n = min(32, stat_rows - r_lo), jq = lane >> 2;
+                    float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (r_n == 32) {
+#pragma unroll
+                        for (int i0 = 0; i0 < 32; i0 += 8) {
+                            float x[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) x[k] = *reinterpret_cast<const float*>(cb + (r_lo + i0 + k) * 128 + ((jq ^ k) << 4));
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) { sa[k & 3] += x[k]; qa[k & 3] = fmaf(x[k], x[k], qa[k & 3]); }
+                        }
+                    } else {
+                        for (int i = 0; i < r_n; ++i) {
+                            const int rr = r_lo + i;
+                            const float x = *reinterpret_cast<const float*>(cb + rr * 128 + ((jq ^ (rr & 7)) << 4));
+                            sa[0] += x; qa[0] = fmaf(x, x, qa[0]);
+                        }
+                    }
+                    s_stat[((c & 1) * 4 + (et >> 5)) * 32 + lane] = make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
+                }
+            }
+            if (do_stats) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cstat_flush(NCH - 1);
+            }
+        }
+        if (et == 0) ptx::bulk_wait_read<0>();         // shared memory must outlive the last store's read
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 2 * TMEM_COLS); }
 }
 
 // Split-K second pass: one thread = one output row x 4 columns; consecutive threads take consecutive float4s
@@ -745,7 +1005,7 @@ int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims,
 struct TcGemm {
     TcParams prm;
     int block_n, smem_bytes;
-    bool co_resident, two_cta;
+    bool co_resident, two_cta, persistent;
     dim3 grid;
     int64_t ws_bytes;
 };
@@ -753,6 +1013,18 @@ struct TcGemm {
 // shared memory outside the pipeline stages: 1 KiB alignment slack, barriers + TMEM slot, staged bias rows, residual chunks
 int fixed_smem(int bn, bool res) { return 1024 + 256 + ADD_ROWS * bn * 4 + 2 * 4 * 32 * 8 + 32 + (res ? 2 * RES_BUF_BYTES : 0); }
 int stage_smem(int bn, bool two) { return A_STAGE_BYTES + (two ? bn / 2 : bn) * BK * 2; }
+
+template <int BN>
+int launch_persistent(const TcGemm* g, cudaStream_t s) {
+    static int configured = 0;
+    if (g->smem_bytes > configured) {
+        SDK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->smem_bytes));
+        configured = g->smem_bytes;
+    }
+    SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN>, dim3(g->grid), dim3(TC_THREADS), (size_t)(g->smem_bytes), s, g->prm));
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
 
 template <int BN, bool TWO = false>
 int launch_cfg(const TcGemm* g, cudaStream_t s) {
@@ -849,8 +1121,8 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
             // pair == 1: cta_group::2 (256-row CTA pairs): needs an even number of m-tiles
             // Measured on B200 (profiles/r01_gemm_pairs.txt): the pair form is 1-5 % SLOWER than two independent CTAs on every
             // UNet shape (the 1-CTA kernel is not bound by the B-tile fill), so auto (0) never picks it; 2 forces it.
-            if (pair == 1 && (d->two_cta != 2 || (m_tiles & 1) || m_tiles < 2)) continue;
-            if (pair == 0 && d->two_cta == 2 && !(m_tiles & 1) && m_tiles >= 2) continue;
+            if (pair == 1 && (d->two_cta != 2 || (m_tiles & 1) || m_tiles < 2 || d->N < 128)) continue;
+            if (pair == 0 && d->two_cta == 2 && !(m_tiles & 1) && m_tiles >= 2 && d->N >= 128) continue;   // narrow outputs stay single-CTA
             for (int i = 0; i < 5; ++i) {
                 const int c = cands[i];
                 if (pair == 1 && c < 128) continue;
@@ -948,6 +1220,27 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     // ---- pipeline depth (run-time): as many stages as fit, at most MAX_STAGES and not many more than the k-blocks of a CTA.
     // short K per CTA: the fixed prologue/epilogue cost dominates -> shallow pipeline so that 2 CTAs share an SM and
     // one CTA's epilogue overlaps the other's main loop
+    // ---- persistent form (one CTA per SM, TMEM double buffer) for multi-wave grids with the direct TMA epilogue
+    {
+        const char* e = getenv("SDB200_TC_PERSISTENT");
+        const int mode = e ? atoi(e) : 1;                 // 0 never, 1 when the grid has >= 2 waves, 2 whenever eligible
+        const long long tiles = (long long)m_tiles * n_tiles;
+        g->persistent = mode > 0 && !two && splits == 1 && p.epi_tma && (mode > 1 || tiles >= 2LL * sms);
+        if (g->persistent) {
+            const int fixed_p = fixed_smem(bn, p.epi_res != 0) + EPI_BUFS * p.epi_buf_stride;
+            int st = (232448 - fixed_p) / stage_smem(bn, false);
+            if (st > MAX_STAGES) st = MAX_STAGES;
+            if (st < 3) g->persistent = false;
+            else {
+                p.stages = st;
+                g->smem_bytes = fixed_p + st * stage_smem(bn, false);
+                g->co_resident = false;
+                g->grid = dim3((unsigned)(tiles < sms ? tiles : sms), 1, 1);
+                *handle = g;
+                return SDK_OK;
+            }
+        }
+    }
     const int fixed = fixed_smem(bn, p.epi_res != 0), per_stage = stage_smem(bn, two);
     const int min_stages = p.epi_tma ? (EPI_BUFS * p.epi_buf_stride + per_stage - 1) / per_stage : 2;   // chunk buffers alias the stages
     const int SMEM_1 = 232448, SMEM_2 = 115712;       // opt-in limit per CTA; per CTA when two share an SM (1 KiB reserved each)
@@ -1034,6 +1327,16 @@ extern "C" int sdk_tc_gemm_launch(void* handle, void* stream) {
     TcGemm* g = (TcGemm*)handle;
     SDK_CHECK_ARG(g->prm.splits == 1 || g->prm.partial, "sdk_tc_gemm_launch: workspace not set for split-K");
     cudaStream_t s = (cudaStream_t)stream;
+    if (g->persistent) {
+        switch (g->block_n) {
+            case 32: return launch_persistent<32>(g, s);
+            case 64: return launch_persistent<64>(g, s);
+            case 128: return launch_persistent<128>(g, s);
+            case 160: return launch_persistent<160>(g, s);
+            case 256: return launch_persistent<256>(g, s);
+        }
+        return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_launch: persistent block_n %d", g->block_n);
+    }
     if (g->two_cta) {
         switch (g->block_n) {
             case 128: return launch_cfg<128, true>(g, s);
