@@ -188,6 +188,8 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_BUFS = 3;                          // output staging ring (one named barrier per chunk needs three buffers)
 constexpr int RES_BUF_BYTES = BM * 128;              // one residual chunk: <= 128 rows x 32 fp32
+constexpr int PERS_THREADS = 64 + 256;               // persistent form: TMA warp, MMA warp, two epilogue groups of four warps
+constexpr int PERS_EPI_BUFS = 4;                     // two output buffers per epilogue group
 
 template <int BN, bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, TWO ? 1 : 2)
@@ -578,7 +580,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
 // Supports the direct TMA epilogue only (single CTA, no split-K); everything else runs conv_gemm_tc_kernel.
 // -------------------------------------------------------------------------------------------------
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(PERS_THREADS, 1)
 conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
     constexpr int B_STAGE_BYTES = BN * BK * 2;
     constexpr int NCH = BN / 32;
@@ -586,13 +588,13 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM, BN);
     const int STAGES = p.stages;
 
-    // shared memory: [A stages][B stages][3 output chunks][2 residual chunks (only with a TMA residual)][barriers][s_add][s_stat]
+    // shared memory: [A stages][B stages][2 x 2 output chunks][2 residual chunks (only with a TMA residual)][barriers][2 x s_add][2 x s_stat]
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
     uint8_t* sOut = sB + STAGES * B_STAGE_BYTES;
-    uint8_t* sRes = sOut + EPI_BUFS * p.epi_buf_stride;
+    uint8_t* sRes = sOut + PERS_EPI_BUFS * p.epi_buf_stride;
     uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (p.epi_res ? 2 * RES_BUF_BYTES : 0));
     uint64_t* empty = full + MAX_STAGES;
     uint64_t* acc_full = empty + MAX_STAGES;          // [2] MMA -> epilogue: accumulator buffer complete
@@ -600,7 +602,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
     uint64_t* res_full = acc_empty + 2;               // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
     float* s_add = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
-    float2* s_stat = reinterpret_cast<float2*>(s_add + ADD_ROWS * BN);        // [2][4][32]
+    float2* s_stat_all = reinterpret_cast<float2*>(s_add + 2 * ADD_ROWS * BN);  // s_add is double-buffered by tile parity; [2 groups][2][4][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = p.N / BN;
@@ -609,7 +611,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 1); ptx::mbar_init(&res_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 2); ptx::mbar_init(&res_full[i], 1); }
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmA[0]);
         ptx::prefetch_tmap(&p.tmB[0]);
@@ -682,42 +684,49 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
             }
         }
     } else {
-        // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
+        // ================= epilogue: TWO groups of four warps (warps 2..5 and 6..9, each covering the four TMEM lane quarters) ====
+        // Group g drains the chunks c = g, g+2, ... of every tile with its own named barrier, output ring (2 buffers), residual
+        // buffer and TMA-store bulk groups, so a tile's epilogue takes ceil(NCH/2) chunk times instead of NCH.
+        const int grp = (warp - 2) >> 2;
         const int q = warp & 3;
         const int r = q * 32 + lane;                    // tile row == TMEM lane
-        const int et = threadIdx.x - 64;                // 0..127 within the epilogue warps
+        const int et = (threadIdx.x - 64) & 127;        // 0..127 within the group
+        const int et2 = threadIdx.x - 64;               // 0..255 over both groups
         const int tb_i = r / (p.TW * p.TH);
         const int rowbytes = p.epi_rowbytes;
         const uint32_t swz = ((uint32_t)(r * rowbytes) >> 7) & (uint32_t)p.epi_swz;
         const bool in_box = r < p.rows;
-        const float* my_add = s_add + (in_box ? tb_i : 0) * BN;
         const bool glu = p.geglu != 0;
         const bool do_stats = p.cstat_out != nullptr;
-        uint32_t res_use0 = 0, res_use1 = 0;             // completed uses of the two residual buffers (mbarrier parity)
-        uint32_t gc = 0;                                // output chunks issued so far (ring position)
+        float2* s_stat = s_stat_all + grp * (2 * 4 * 32);
+        uint8_t* my_out = sOut + grp * 2 * p.epi_buf_stride;
+        uint8_t* my_res = sRes + grp * RES_BUF_BYTES;
+        uint64_t* my_res_full = &res_full[grp];
+        uint32_t res_use = 0;                           // completed uses of this group's residual buffer (mbarrier parity)
+        uint32_t gc = 0;                                // output chunks this group has issued so far (ring position)
         int lt = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
             int w0, h0, b0, n0;
             coords(t, w0, h0, b0, n0);
             const int ab = lt & 1;
             const uint32_t taddr = tmem_base + (uint32_t)ab * TMEM_COLS + ((uint32_t)(q * 32) << 16);
-            // residual chunks 0 and 1 of this tile (buffers are free: every thread passed the last barrier of the previous tile)
-            if (p.epi_res && et == 0) {
-#pragma unroll
-                for (int c = 0; c < (NCH < 2 ? NCH : 2); ++c) {
-                    ptx::mbar_expect_tx(&res_full[c], (uint32_t)p.rows * 128u);
-                    ptx::tma_load_4d(sRes + c * RES_BUF_BYTES, &p.tmRes, &res_full[c], n0 + c * 32, w0, h0, b0);
-                }
+            // this group's first residual chunk (the buffer is free: the group passed its last barrier of the previous tile)
+            if (p.epi_res && et == 0 && grp < NCH) {
+                ptx::mbar_expect_tx(my_res_full, (uint32_t)p.rows * 128u);
+                ptx::tma_load_4d(my_res, &p.tmRes, my_res_full, n0 + grp * 32, w0, h0, b0);
             }
-            // s_add[tb][j] = bias[n0+j] + tbias[b0+tb][n0+j] (previous tile's readers are past their last barrier)
-            for (int i = et; i < p.TB * BN; i += 128) {
+            // s_add[tb][j] = bias[n0+j] + tbias[b0+tb][n0+j], double-buffered by tile parity (the other group may still read the
+            // previous tile's rows); the 256-thread barrier keeps the groups within one tile of each other
+            float* s_add_t = s_add + (lt & 1) * ADD_ROWS * BN;
+            for (int i = et2; i < p.TB * BN; i += 256) {
                 const int tbi = i / BN, j = i - tbi * BN;
                 float x = 0.f;
                 if (p.bias) x = __ldg(p.bias + n0 + j);
                 if (p.tbias && b0 + tbi < p.B) x += __ldg(p.tbias + (long long)(b0 + tbi) * p.tb_stride + n0 + j);
-                s_add[i] = x;
+                s_add_t[i] = x;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            const float* my_add = s_add_t + (in_box ? tb_i : 0) * BN;
             const int stat_rows = p.TB > 1 ? p.rows : p.TW * min(p.TH, p.H - h0);
             auto cstat_flush = [&](int cc) {
                 const int rps = p.TW * p.TH;
@@ -726,7 +735,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                     const int p_lo = p.TB > 1 ? smp * (rps >> 5) : 0, p_n = p.TB > 1 ? (rps >> 5) : 4;
                     double sum = 0.0, sq = 0.0;
                     for (int i = 0; i < p_n; ++i) {
-                        const float2 v2 = s_stat[((cc & 1) * 4 + p_lo + i) * 32 + lane];
+                        const float2 v2 = s_stat[(((cc >> 1) & 1) * 4 + p_lo + i) * 32 + lane];
                         sum += (double)v2.x; sq += (double)v2.y;
                     }
                     double* dst = reinterpret_cast<double*>(p.cstat_out + (size_t)(b0 + smp) * p.N + n0 + cc * 32 + lane);
@@ -739,10 +748,13 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
             ptx::mbar_wait(&acc_full[ab], (uint32_t)(lt >> 1) & 1u);
             ptx::tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < NCH; ++c, ++gc) {
+            int last_c = grp;
+            if (grp >= NCH && et == 0) ptx::mbar_arrive(&acc_empty[ab]);   // BN = 32: the second group has nothing to drain
+            for (int c = grp; c < NCH; c += 2, ++gc) {
+                last_c = c;
                 uint32_t u[32];
                 ptx::tmem_ld32(taddr + c * 32, u);
-                uint8_t* obuf = sOut + (gc % EPI_BUFS) * p.epi_buf_stride;
+                uint8_t* obuf = my_out + (gc & 1u) * p.epi_buf_stride;
                 uint8_t* ob = obuf + r * rowbytes;
                 ptx::tmem_ld_wait();
                 float v[32];
@@ -754,9 +766,8 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                     v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
                 }
                 if (p.epi_res) {
-                    const uint32_t par = (c & 1) ? (res_use1++ & 1u) : (res_use0++ & 1u);
-                    ptx::mbar_wait(&res_full[c & 1], par);
-                    const uint8_t* rb = sRes + (c & 1) * RES_BUF_BYTES + r * 128;
+                    ptx::mbar_wait(my_res_full, res_use++ & 1u);
+                    const uint8_t* rb = my_res + r * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 a = *reinterpret_cast<const float4*>(rb + ((j ^ (r & 7)) << 4));
@@ -780,20 +791,21 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                     }
                 }
                 ptx::fence_proxy_async();
-                if (c == NCH - 1) ptx::tc_fence_before();   // last TMEM read of this accumulator buffer is done
-                if (et == 0) ptx::bulk_wait_read<1>();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const bool last = c + 2 >= NCH;             // this group's last chunk of the tile: its TMEM reads are done
+                if (last) ptx::tc_fence_before();
+                if (et == 0) ptx::bulk_wait_read<0>();      // 2-buffer ring: the previous store has read the other buffer... and this one's predecessor
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (et == 0) {
-                    if (c == NCH - 1) ptx::mbar_arrive(&acc_empty[ab]);      // the MMA warp may overwrite this buffer (tile lt+2)
+                    if (last) ptx::mbar_arrive(&acc_empty[ab]);          // (2 arrivals: both groups) the MMA warp may overwrite this buffer
                     ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
                     ptx::bulk_commit();
                     if (p.epi_res && c + 2 < NCH) {
-                        ptx::mbar_expect_tx(&res_full[c & 1], (uint32_t)p.rows * 128u);
-                        ptx::tma_load_4d(sRes + (c & 1) * RES_BUF_BYTES, &p.tmRes, &res_full[c & 1], n0 + (c + 2) * 32, w0, h0, b0);
+                        ptx::mbar_expect_tx(my_res_full, (uint32_t)p.rows * 128u);
+                        ptx::tma_load_4d(my_res, &p.tmRes, my_res_full, n0 + (c + 2) * 32, w0, h0, b0);
                     }
                 }
                 if (do_stats) {
-                    if (c > 0) cstat_flush(c - 1);
+                    if (c >= 2) cstat_flush(c - 2);
                     const uint8_t* cb = obuf + ((lane & 3) << 2);
                     const int r_lo = (et >> 5) * 32, r_n = min(32, stat_rows - r_lo), jq = lane >> 2;
                     float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
@@ -813,12 +825,12 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                             sa[0] += x; qa[0] = fmaf(x, x, qa[0]);
                         }
                     }
-                    s_stat[((c & 1) * 4 + (et >> 5)) * 32 + lane] = make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
+                    s_stat[(((c >> 1) & 1) * 4 + (et >> 5)) * 32 + lane] = make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
                 }
             }
-            if (do_stats) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                cstat_flush(NCH - 1);
+            if (do_stats && grp < NCH) {
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                cstat_flush(last_c);
             }
         }
         if (et == 0) ptx::bulk_wait_read<0>();         // shared memory must outlive the last store's read
@@ -1021,7 +1033,7 @@ int launch_persistent(const TcGemm* g, cudaStream_t s) {
         SDK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->smem_bytes));
         configured = g->smem_bytes;
     }
-    SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN>, dim3(g->grid), dim3(TC_THREADS), (size_t)(g->smem_bytes), s, g->prm));
+    SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
@@ -1227,7 +1239,7 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         const long long tiles = (long long)m_tiles * n_tiles;
         g->persistent = mode > 0 && !two && splits == 1 && p.epi_tma && (mode > 1 || tiles >= 2LL * sms);
         if (g->persistent) {
-            const int fixed_p = fixed_smem(bn, p.epi_res != 0) + EPI_BUFS * p.epi_buf_stride;
+            const int fixed_p = fixed_smem(bn, p.epi_res != 0) + PERS_EPI_BUFS * p.epi_buf_stride + ADD_ROWS * bn * 4 + 2 * 4 * 32 * 8;
             int st = (232448 - fixed_p) / stage_smem(bn, false);
             if (st > MAX_STAGES) st = MAX_STAGES;
             if (st < 3) g->persistent = false;
