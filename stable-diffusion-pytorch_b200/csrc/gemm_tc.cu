@@ -1235,7 +1235,9 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     // ---- persistent form (one CTA per SM, TMEM double buffer) for multi-wave grids with the direct TMA epilogue
     {
         const char* e = getenv("SDB200_TC_PERSISTENT");
-        const int mode = e ? atoi(e) : 1;                 // 0 never, 1 when the grid has >= 2 waves, 2 whenever eligible
+        // 0 never, 1 when the grid has >= 2 waves, 2 whenever eligible (default: the two epilogue groups also pay for single-wave
+        // grids -- UNet batch 2: 4.57 -> 4.47 ms/step)
+        const int mode = e ? atoi(e) : 2;
         const long long tiles = (long long)m_tiles * n_tiles;
         g->persistent = mode > 0 && !two && splits == 1 && p.epi_tma && (mode > 1 || tiles >= 2LL * sms);
         if (g->persistent) {
