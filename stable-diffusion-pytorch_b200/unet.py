@@ -254,7 +254,7 @@ class StepProgram:
         d.out_dtype, d.geglu, d.out_nchw = p.out_dtype, p.geglu, p.out_nchw
         d.block_n, d.splits, d.w_kmajor, d.two_cta = self.net.tc_block_n, self.net.tc_splits, 1, self.net.tc_two_cta
         if self.net.tc_autotune and not d.block_n and not d.splits:
-            d.block_n, d.splits = self._autotune(d, srcs[0][0], cs)
+            d.block_n, d.splits, d.two_cta = self._autotune(d, srcs[0][0], cs)
         h = C.c_void_p()
         _lib.check(self.lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
         self.tc_handles.append(h)
@@ -307,13 +307,14 @@ class StepProgram:
                                         d.geglu, d.out_dtype, int(bool(d.residual)), int(bool(d.tbias)), int(cs is not None)))
         hit = StepProgram._tune_cache.get(key)
         if hit is not None:
-            return hit
+            return tuple(hit) if len(hit) == 3 else (hit[0], hit[1], d.two_cta)
         lib = self.lib
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         if not hasattr(self, "_tune_flush"):
             self._tune_flush = torch.empty(192 << 20, dtype=torch.uint8, device=self.device)
         total_kb = (d.C[0] // 64) * d.ksize[0] * d.ksize[0] + ((d.C[1] // 64) if d.nseg > 1 else 0)
-        cands = [(0, 0)]
+        cands = [(0, 0, 0)]
+        pairs_ok = self.net.tc_tune_pairs and (d.B * d.H * d.W) >= 256 and d.N >= 128
         for bn in (32, 64, 128, 160, 256):
             if d.N % bn != 0 and d.N > bn:
                 continue
@@ -322,8 +323,10 @@ class StepProgram:
             for sp in (1, 2, 3, 4, 6, 8, 12, 16, 24):
                 if sp > 1 and total_kb // sp < 4:
                     continue
-                cands.append((bn, sp))
-        best, best_t, auto_t = (0, 0), float("inf"), None
+                cands.append((bn, sp, 0))
+                if pairs_ok and bn >= 128 and sp <= 8:
+                    cands.append((bn, sp, 2))               # cta_group::2 CTA pairs (halves the B-tile bytes each SM ingests)
+        best, best_t, auto_t = (0, 0, 0), float("inf"), None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         REPS = 6
 
@@ -342,8 +345,8 @@ class StepProgram:
 
         timed(None)
         base = min(timed(None), timed(None))                 # cost of the eviction + touch alone
-        for bn, sp in cands:
-            d.block_n, d.splits = bn, sp
+        for bn, sp, two in cands:
+            d.block_n, d.splits, d.two_cta = bn, sp, two
             h = C.c_void_p()
             if lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)) != 0:
                 continue
@@ -359,13 +362,13 @@ class StepProgram:
             torch.cuda.synchronize(self.device)
             lib.sdk_tc_gemm_destroy(h)
             if tmin is not None:
-                if (bn, sp) == (0, 0):
+                if (bn, sp, two) == (0, 0, 0):
                     auto_t = tmin
                 if tmin < best_t:
-                    best, best_t = (bn, sp), tmin
+                    best, best_t = (bn, sp, two), tmin
         # keep the model's choice unless a candidate is clearly (> 4 %) faster: timing noise must not flip tilings
         if auto_t is not None and best_t > 0.96 * auto_t:
-            best = (0, 0)
+            best = (0, 0, 0)
         StepProgram._tune_cache[key] = best
         StepProgram._tune_save()
         if self.net.tc_autotune > 1:
@@ -708,6 +711,7 @@ class UNet(nn.Module):
         self.precision = os.environ.get("SDB200_PRECISION", "bf16")
         self.tc_block_n = int(os.environ.get("SDB200_TC_BLOCK_N", "0"))      # 0 = auto; tuning / test overrides
         self.tc_splits = int(os.environ.get("SDB200_TC_SPLITS", "0"))
+        self.tc_tune_pairs = int(os.environ.get("SDB200_TC_TUNE_PAIRS", "0"))   # also try cta_group::2 pairs when measuring tilings
         self.tc_autotune = int(os.environ.get("SDB200_TC_AUTOTUNE", "1"))     # 1: measure tilings at plan time; 2: and print them
         self.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention for head_dim 40 / 64
         self.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
