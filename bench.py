@@ -37,6 +37,8 @@ CONFIGS = {
             name="SD1.5-arch UNet 512^2, DDIM-50, CFG 7.5, batch 64 over 8 GPUs (8 per GPU)"),
     4: dict(arch="sd21", hw=96, steps=50, cfg=True, batch=2, ptype="v_prediction", dctx=1024,
             name="SD2.1-arch UNet 768^2 (96x96 latent), DDIM-50, v-prediction, batch 16 over 8 GPUs (2 per GPU)"),
+    5: dict(arch="sd21", hw=64, steps=1, cfg=False, batch=32, ptype="epsilon", dctx=1024,
+            name="SwiftBrush one-step: SD2.1-arch UNet 512^2, ONE forward at t=999, no CFG, batch 256 over 8 GPUs (32 per GPU)"),
 }
 
 
@@ -224,6 +226,62 @@ def torch_eager_on_gpu(cfg, sd, arch, dev, steps=8):
     return out
 
 
+def run_one_step(args, cfg):
+    """BASELINE config 5 (models/diffusion.py:106-113): images/s of UNet forward (no CFG, context batch 1 broadcast) + x0 update."""
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from stable_diffusion_pytorch_b200 import DDIMSampler, UNet
+    from stable_diffusion_pytorch_b200.pipeline import one_step
+    B = cfg["batch"]
+    arch, sd, latent_all, ctx_all = build_oracle_inputs(cfg, B * world)
+    net = UNet(attention_head_dim=arch["attention_head_dim"], cross_attention_dim=arch["cross_attention_dim"])
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval().set_precision(args.precision)
+    lat = latent_all[rank * B:(rank + 1) * B].to(dev)
+    ctx = ctx_all[:1].to(dev)                                # one prompt, broadcast (diffusion.py:102)
+    smp = DDIMSampler()
+    K, Wm = args.steps, max(args.warmup, 3)
+    with torch.no_grad():
+        for _ in range(Wm):
+            out = one_step(net, smp, lat, ctx)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            out = one_step(net, smp, lat, ctx)
+        e1.record()
+        torch.cuda.synchronize()
+        sampler.stop_flag = True
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / K
+        finite = bool(torch.isfinite(out).all().item())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    _, _, tf_sus, peak_src = peaks()
+    gf = GFLOP_PER_SAMPLE[(cfg["arch"], cfg["hw"])] * B
+    print(json.dumps({
+        "metric": "images_per_sec", "value": B * world / (ms_step * 1e-3), "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": cfg["name"], "images_per_gpu": B, "unet_batch_per_gpu": B, "latent": [cfg["hw"], cfg["hw"]], "finite": finite,
+                   "l2_policy": "inputs larger than L2: each forward streams 1.73 GB of bf16 weights", "api": "pipeline.one_step (UNet.forward + x0 kernel)"},
+        "step_tflops": gf / ms_step, "step_frac_of_peak": gf / ms_step / tf_sus, "peak_source": peak_src,
+        "clocks": sampler.summary()}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -243,6 +301,8 @@ def main():
         cfg["batch"] = args.batch_per_gpu
     if args.impl == "reference":
         return run_reference_arm(args, cfg)
+    if args.config == 5:
+        return run_one_step(args, cfg)
     if args.warmup < 3:
         args.warmup = 3
 
