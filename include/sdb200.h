@@ -51,6 +51,14 @@ int sdk_ddim_step(const float* x, const float* eps_u, const float* eps_c, float 
 int sdk_ddpm_step(const float* x, const float* eps_u, const float* eps_c, float cfg_scale,
                   const float* noise, float* out, int64_t n, const float* coef_table, int T,
                   const int64_t* t_dev, int64_t t_host, void* stream);
+/* Inpainting loop body after the UNet (models/diffusion.py:387-398) in one pass: model output ordered [cond ; uncond] and blended as
+ * s*(c-u)+c (eps_u == NULL: no CFG), orig = VAE-encoded image re-noised to the step's timestep with that prediction
+ * (forward_process, ddim.py:46-55; orig_batch 1 broadcasts), kept wherever mask[pixel] == 0, then the DDIM update.
+ * x, out: [batch][channels][hw] fp32 (may alias); mask: [hw] bytes, non-zero = region to repaint. */
+int sdk_ddim_inpaint_step(const float* x, const float* eps_c, const float* eps_u, float cfg_scale,
+                          const float* orig, int64_t orig_batch, const uint8_t* mask, float* out,
+                          int64_t batch, int64_t channels, int64_t hw, const float* coef_table, int T,
+                          const int64_t* t_dev, int64_t t_host, int prediction_type, void* stream);
 /* models/scheduler/ddim.py:46-55 — per-sample timesteps t_dev[batch] */
 int sdk_forward_process(const float* x0, const float* noise, float* out, int64_t batch, int64_t per_sample,
                         const float* coef_table, int T, const int64_t* t_dev, void* stream);

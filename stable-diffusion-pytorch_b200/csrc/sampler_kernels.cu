@@ -104,6 +104,33 @@ step_kernel(const float* x, const float* __restrict__ eu, const float* __restric
     }
 }
 
+// Inpainting step (models/diffusion.py:387-398), one pass, reference op order:
+//   e      = s*(c - u) + c                      CFG in the inpaint loop's own form, model output ordered [cond ; uncond]
+//   noised = sqrt(a_hat_t)*orig + sqrt(1 - a_hat_t)*e        forward_process(encoded_img, t, e)   (ddim.py:46-55)
+//   xin    = mask ? x : noised                  torch.where(~mask, noised, latent); mask is per pixel, shared by batch and channels
+//   x'     = DDIM(xin, e)                       reverse_process
+template <int PRED>
+__global__ void __launch_bounds__(256)
+inpaint_step_kernel(const float* x, const float* __restrict__ ec, const float* __restrict__ eu, float scale,
+                    const float* __restrict__ orig, long long orig_batch_stride, const unsigned char* __restrict__ mask,
+                    float* out, long long n, long long chw, long long hw,
+                    const float* __restrict__ table, int T, const long long* __restrict__ t_dev, long long t_host) {
+    pdl_trigger();
+    pdl_wait();
+    Coef k;
+    const bool ok = load_coef(table, T, t_dev, t_host, k);
+    const float qnan = __int_as_float(0x7fc00000);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / chw, r = i - b * chw;
+        float e = ec[i];
+        if (eu) e = __fadd_rn(__fmul_rn(scale, __fsub_rn(e, eu[i])), e);
+        const float noised = __fadd_rn(__fmul_rn(k.c[5], __ldg(orig + b * orig_batch_stride + r)), __fmul_rn(k.c[6], e));
+        const float xin = mask[r % hw] ? x[i] : noised;
+        const float y = ddim_one<PRED>(xin, e, k, false, 0.f);
+        out[i] = ok ? y : qnan;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 forward_process_kernel(const float* __restrict__ x0, const float* __restrict__ noise, float* __restrict__ out,
                        long long per_sample, const float* __restrict__ table, int T, const long long* __restrict__ t) {
@@ -156,6 +183,29 @@ extern "C" int sdk_ddim_step(const float* x, const float* eps_u, const float* ep
         SDK_CUDA(sdk_launch(step_kernel<0>, dim3(grid), dim3(256), (size_t)(0), s, x, eps_u, eps_c, cfg_scale, noise, out, n, coef_table, T, (const long long*)t_dev, t_host, vec_ok));
     else
         SDK_CUDA(sdk_launch(step_kernel<1>, dim3(grid), dim3(256), (size_t)(0), s, x, eps_u, eps_c, cfg_scale, noise, out, n, coef_table, T, (const long long*)t_dev, t_host, vec_ok));
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
+extern "C" int sdk_ddim_inpaint_step(const float* x, const float* eps_c, const float* eps_u, float cfg_scale,
+                                     const float* orig, int64_t orig_batch, const uint8_t* mask, float* out,
+                                     int64_t batch, int64_t channels, int64_t hw, const float* coef_table, int T,
+                                     const int64_t* t_dev, int64_t t_host, int prediction_type, void* stream) {
+    SDK_CHECK_ARG(x && eps_c && orig && mask && out && coef_table, "sdk_ddim_inpaint_step: null pointer");
+    SDK_CHECK_ARG(batch >= 0 && channels > 0 && hw > 0 && T > 0, "sdk_ddim_inpaint_step: bad sizes");
+    SDK_CHECK_ARG(orig_batch == 1 || orig_batch == batch, "sdk_ddim_inpaint_step: orig batch %lld must be 1 or %lld", (long long)orig_batch, (long long)batch);
+    SDK_CHECK_ARG(prediction_type == 0 || prediction_type == 1, "sdk_ddim_inpaint_step: prediction_type %d", prediction_type);
+    const long long chw = channels * hw, n = batch * chw;
+    if (n == 0) return SDK_OK;
+    const long long ostride = orig_batch == 1 ? 0 : chw;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = grid_for(n, 256);
+    if (prediction_type == 0)
+        SDK_CUDA(sdk_launch(inpaint_step_kernel<0>, dim3(grid), dim3(256), (size_t)0, s, x, eps_c, eps_u, cfg_scale, orig, ostride, mask, out, n, chw,
+                            (long long)hw, coef_table, T, (const long long*)t_dev, (long long)t_host));
+    else
+        SDK_CUDA(sdk_launch(inpaint_step_kernel<1>, dim3(grid), dim3(256), (size_t)0, s, x, eps_c, eps_u, cfg_scale, orig, ostride, mask, out, n, chw,
+                            (long long)hw, coef_table, T, (const long long*)t_dev, (long long)t_host));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }

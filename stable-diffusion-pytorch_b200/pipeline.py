@@ -55,6 +55,24 @@ class DenoiseLoop:
         self._grid_key = None
         self._cond_ref, self._cond_version = None, -1
         self.launches_per_step = len(self.prog.ops) + 2
+        self.inpaint_orig, self.inpaint_mask = None, None     # set_inpaint(): the step becomes the inpainting loop body
+
+    def set_inpaint(self, encoded_img: Optional[torch.Tensor], mask: Optional[torch.Tensor]):
+        """Turn the loop into the inpainting loop of models/diffusion.py:379-398 (context rows [cond ; uncond], CFG form
+        s*(c-u)+c, known region re-noised from ``encoded_img`` every step); ``None, None`` restores plain sampling."""
+        if encoded_img is None:
+            self.inpaint_orig, self.inpaint_mask = None, None
+        else:
+            if not isinstance(self.sampler, DDIMSampler):
+                raise RuntimeError("the inpainting loop is defined for the DDIM sampler")
+            o = encoded_img.to(self.device, torch.float32).contiguous()
+            if o.shape[0] not in (1, self.B) or tuple(o.shape[1:]) != tuple(self.latent.shape[1:]):
+                raise RuntimeError(f"encoded_img {tuple(o.shape)} does not broadcast against the latent {tuple(self.latent.shape)}")
+            if mask.numel() != self.H * self.W:
+                raise RuntimeError(f"mask must hold one value per latent pixel ({self.H}x{self.W})")
+            self.inpaint_orig = o
+            self.inpaint_mask = mask.to(self.device).reshape(self.H * self.W).ne(0).to(torch.uint8).contiguous()
+        self.graph = None                                      # pointers are baked into the captured launches
 
     # ---- one step = [next timestep] + UNet program + [CFG + scheduler update in place] -------------------
     def _enqueue_step(self):
@@ -70,6 +88,13 @@ class DenoiseLoop:
         if isinstance(s, DDPMSampler):
             _lib.check(lib.sdk_ddpm_step(self.latent.data_ptr(), eps_u, eps_c, self.cfg_scale, self.noise.data_ptr(),
                                          self.latent.data_ptr(), n, self.coef.data_ptr(), s.noise_step, p.t_in.data_ptr(), 0, stream))
+        elif self.inpaint_orig is not None:
+            pred = PRED_V if s.prediction_type == "v_prediction" else PRED_EPS
+            ch = self.latent.shape[1]
+            _lib.check(lib.sdk_ddim_inpaint_step(self.latent.data_ptr(), eps_u, eps_c, self.cfg_scale, self.inpaint_orig.data_ptr(),
+                                                 self.inpaint_orig.shape[0], self.inpaint_mask.data_ptr(), self.latent.data_ptr(),
+                                                 self.B, ch, self.H * self.W, self.coef.data_ptr(), s.noise_step, p.t_in.data_ptr(), 0,
+                                                 pred, stream))          # rows are [cond ; uncond] here: eps_u/eps_c name the halves
         else:
             pred = PRED_V if s.prediction_type == "v_prediction" else PRED_EPS
             _lib.check(lib.sdk_ddim_step(self.latent.data_ptr(), eps_u, eps_c, self.cfg_scale, 0, self.latent.data_ptr(), n,
@@ -133,6 +158,28 @@ def denoise(unet: UNet, sampler, latent: torch.Tensor, context: torch.Tensor, *,
     b, _, h, w = latent.shape
     loop = DenoiseLoop(unet, sampler, b, h, w, do_cfg=do_cfg, cfg_scale=cfg_scale, context_len=context.shape[1],
                        context_batch=context.shape[0], device=latent.device)
+    return loop.run(latent, context)
+
+
+@torch.no_grad()
+def img2img(unet: UNet, sampler, encoded_img: torch.Tensor, noise: torch.Tensor, context: torch.Tensor, strength: float, *,
+            do_cfg: bool = True, cfg_scale: float = 7.5) -> torch.Tensor:
+    """Image-to-image loop of models/diffusion.py:204-236 after the VAE encode: ``set_strength`` shortens the grid, the
+    encoded image is noised to its first timestep (forward_process), then the ordinary loop runs."""
+    sampler.set_strength(strength=strength)
+    latent, _ = sampler.forward_process(encoded_img, sampler.timesteps[0].unsqueeze(0), noise)
+    return denoise(unet, sampler, latent, context, do_cfg=do_cfg, cfg_scale=cfg_scale)
+
+
+@torch.no_grad()
+def inpaint(unet: UNet, sampler, latent: torch.Tensor, context: torch.Tensor, encoded_img: torch.Tensor, mask: torch.Tensor, *,
+            do_cfg: bool = True, cfg_scale: float = 7.5) -> torch.Tensor:
+    """Inpainting loop of models/diffusion.py:379-398 (``latent`` = the already masked/noised start of :365-369; context rows
+    [cond ; uncond]); one CUDA-graph replay per step like ``denoise``."""
+    b, _, h, w = latent.shape
+    loop = DenoiseLoop(unet, sampler, b, h, w, do_cfg=do_cfg, cfg_scale=cfg_scale, context_len=context.shape[1],
+                       context_batch=context.shape[0], device=latent.device)
+    loop.set_inpaint(encoded_img, mask)
     return loop.run(latent, context)
 
 

@@ -95,6 +95,20 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))
 
 
+@pytest.mark.parametrize("ptype", ["epsilon", "v_prediction"])
+def test_inpaint_step_bit_exact(sg, golden_dir, ptype):
+    """Oracle restatement of the inpainting loop body vs the reference's own statements (tests/golden/make_golden_inpaint.py)."""
+    g = np.load(os.path.join(golden_dir, "inpaint_golden.npz"))
+    ts = g[f"{ptype}_ts"]
+    assert np.array_equal(ts, SO.strength_slice(SO.ddim_timesteps(1000, 50), 50, 0.8))
+    mask = g["mask"][0, 0]
+    for t in (int(ts[0]), int(ts[17]), int(ts[-1])):
+        y = SO.inpaint_step(g["latent"], t, g["pred2"], g["encoded"], mask, 7.5, sg["alphas"], sg["alphas_hat"], 1000, 50, ptype)
+        assert np.array_equal(y, g[f"{ptype}_{t}_cfg"]), (ptype, t)
+        y = SO.inpaint_step(g["latent"], t, g["pred2"][:2], g["encoded"], mask, None, sg["alphas"], sg["alphas_hat"], 1000, 50, ptype)
+        assert np.array_equal(y, g[f"{ptype}_{t}_nocfg"]), (ptype, t)
+
+
 def test_param_inventory():
     n15 = sum(int(np.prod(s)) for _, s in UO.param_spec(**UO.SD15))
     n21 = sum(int(np.prod(s)) for _, s in UO.param_spec(**UO.SD21))

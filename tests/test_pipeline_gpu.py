@@ -8,7 +8,8 @@ import torch
 
 from oracle import unet_oracle as UO
 from stable_diffusion_pytorch_b200 import DDIMSampler, DDPMSampler, UNet
-from stable_diffusion_pytorch_b200.pipeline import DenoiseLoop, denoise, one_step
+from oracle import sampler_oracle as SO
+from stable_diffusion_pytorch_b200.pipeline import DenoiseLoop, denoise, img2img, inpaint, one_step
 
 pytestmark = pytest.mark.gpu
 
@@ -146,3 +147,50 @@ def test_config4_sd21_768_ddim50_vpred_full(golden_dir, dev):
     assert res[("bf16", 50)] < 1e-2
     del net
     torch.cuda.empty_cache()
+
+
+def test_inpaint_and_img2img_loops(net15, dev):
+    """Inpainting loop (models/diffusion.py:379-398) as graph replays == step-by-step drop-in API == CPU oracle loop; img2img
+    (set_strength + forward_process + loop, :204-236) == its step-by-step form."""
+    net15.set_precision("fp32")
+    B, h, w = 1, 16, 16
+    g = torch.Generator().manual_seed(21)
+    lat = torch.randn((B, 4, h, w), generator=g)
+    ctx = torch.randn((2 * B, 77, 768), generator=g)              # rows [cond ; uncond] in the inpaint loop
+    enc = torch.randn((1, 4, h, w), generator=g)
+    mask = torch.rand((1, 1, h, w), generator=g) > 0.5
+    d = DDIMSampler()
+    d._set_inference_steps(10)
+    d.set_strength(0.4)                                           # 4 steps
+    with torch.no_grad():
+        got = inpaint(net15, d, lat.to(dev), ctx.to(dev), enc.to(dev), mask.to(dev), do_cfg=True, cfg_scale=7.5)
+        x = lat.to(dev)
+        for ts in d.timesteps.to(dev):
+            ts = ts.unsqueeze(0)
+            x = d.inpaint_step(x, ts, net15(x.repeat(2, 1, 1, 1), ts, ctx.to(dev)), enc.to(dev), mask.to(dev), cfg_scale=7.5)
+        assert torch.equal(got, x)
+    # CPU oracle: the reference's statements with the oracle UNet
+    sd = UO.make_state_dict(0, **UO.SD15)
+    _, alphas, a_hat = SO.schedule_fp32()
+    xo = lat.clone()
+    for t in d.timesteps.tolist():
+        pred = UO.unet_forward(sd, xo.repeat(2, 1, 1, 1), torch.tensor([t]), ctx, **UO.SD15)
+        xo = torch.from_numpy(SO.inpaint_step(xo.numpy(), t, pred.numpy(), enc.numpy(), mask[0, 0].numpy(), 7.5, alphas, a_hat, 1000, 10))
+    e = rel_l2(got.cpu().numpy(), xo.numpy())
+    print(f"inpaint loop fp32 vs oracle: rel-L2 {e:.3e}")
+    assert e < 1e-4
+    # img2img
+    d2 = DDIMSampler()
+    d2._set_inference_steps(10)
+    noise = torch.randn((B, 4, h, w), generator=g).to(dev)
+    ctx2 = torch.randn((2 * B, 77, 768), generator=g).to(dev)
+    with torch.no_grad():
+        got = img2img(net15, d2, enc.to(dev), noise, ctx2, 0.6)
+        d3 = DDIMSampler()
+        d3._set_inference_steps(10)
+        d3.set_strength(0.6)
+        x, _ = d3.forward_process(enc.to(dev), d3.timesteps[0].unsqueeze(0), noise)
+        for ts in d3.timesteps.to(dev):
+            ts = ts.unsqueeze(0)
+            x = d3.reverse_process(x, ts, net15(x.repeat(2, 1, 1, 1), ts, ctx2), cfg_scale=7.5)
+        assert torch.equal(got, x)

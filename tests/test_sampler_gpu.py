@@ -108,6 +108,26 @@ def test_ddim_vs_oracle_shapes(dev, shape):
         assert got.shape == tuple(shape) and np.array_equal(got, want)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("ptype", ["epsilon", "v_prediction"])
+def test_inpaint_step_golden_bit_exact(sg, golden_dir, dev, ptype):
+    """Fused inpainting step (CFG in the inpaint form + re-noise + mask select + DDIM) == the reference's statements, bit for bit."""
+    g = np.load(os.path.join(golden_dir, "inpaint_golden.npz"))
+    s = DDIMSampler(prediction_type=ptype)
+    _use_golden_tables(s, sg)
+    s._set_inference_steps(50)
+    s.set_strength(0.8)
+    assert np.array_equal(s.timesteps.numpy(), g[f"{ptype}_ts"])
+    lat, pred2, enc = (torch.from_numpy(g[k]).to(dev) for k in ("latent", "pred2", "encoded"))
+    mask = torch.from_numpy(g["mask"]).to(dev)
+    for t in (s.timesteps[0], s.timesteps[17], s.timesteps[-1]):
+        tt = t.unsqueeze(0).to(dev)
+        got = s.inpaint_step(lat, tt, pred2, enc, mask, cfg_scale=7.5)
+        assert np.array_equal(got.cpu().numpy(), g[f"{ptype}_{int(t)}_cfg"])
+        got = s.inpaint_step(lat, int(t), pred2[:2], enc.expand(2, -1, -1, -1), mask[0, 0])
+        assert np.array_equal(got.cpu().numpy(), g[f"{ptype}_{int(t)}_nocfg"])
+
+
 def test_out_of_range_timestep_poisons(dev):
     s = DDIMSampler()
     s._set_inference_steps(10)
