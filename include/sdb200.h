@@ -134,9 +134,9 @@ typedef struct SdkConvParams {
 } SdkConvParams;
 /* exact fp32 path (FFMA); also serves shapes the tensor-core path does not take (Cin = 4). in_dtype must be fp32. */
 int sdk_conv_gemm_f32(const SdkConvParams* p, void* stream);
-/* conv_in (unet.py:256): 3x3 / pad 1 / Cin = 4 on the fp32 NHWC latent x [B][H][W][4], w [N][3][3][4], out fp32 [B][H][W][N];
+/* conv_in (unet.py:256): 3x3 / pad 1 / Cin = 4 on the fp32 NHWC latent x [B][H][W][4], w_t [3][3][4][N] (transposed), out fp32 [B][H][W][N];
  * chan_stats (optional, zeroed by the caller) accumulates the per-channel (sum, sum of squares) table of the output. */
-int sdk_conv_in(const float* x, const float* w, const float* bias, float* out, double* chan_stats,
+int sdk_conv_in(const float* x, const float* w_t, const float* bias, float* out, double* chan_stats,
                 int B, int H, int W, int N, void* stream);
 
 /* ---- attention (models/unet/attention.py:29-50): out = softmax(q k^T * scale) v per head ------

@@ -220,10 +220,10 @@ extern "C" int sdk_conv_gemm_f32(const SdkConvParams* p, void* stream) {
 // table of the first GroupNorm (double atomics, as the tensor-core epilogue does).
 // -------------------------------------------------------------------------------------------------
 namespace {
-constexpr int CI_PIX = 64, CI_THREADS = 256;
+constexpr int CI_PIX = 16, CI_THREADS = 256;      // small pixel chunks: ~4 CTAs per SM hide the FFMA dependency chains
 
 __global__ void __launch_bounds__(CI_THREADS)
-conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /* [3][3][4][N] */, const float* __restrict__ bias, float* __restrict__ out,
                double2* __restrict__ cstat, int B, int H, int W, int N) {
     pdl_trigger();
     pdl_wait();
@@ -232,10 +232,8 @@ conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
     float* s_red = sm + 36 * N;                        // [px_lanes][N][2] column partials
     const int quads = N >> 2, px_lanes = CI_THREADS / quads;
     const int pl = threadIdx.x / quads, qd = threadIdx.x - pl * quads;
-    for (int i = threadIdx.x; i < 36 * N; i += CI_THREADS) {
-        const int n = i / 36, k = i - n * 36;          // coalesced read of w[n][k], transposed store
-        w_s[k * N + n] = __ldg(w + i);
-    }
+    for (int i = threadIdx.x; i < 9 * N; i += CI_THREADS)          // w_t is already [36][N]: straight 16-byte copies
+        reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
     __syncthreads();
     const int HW = H * W;
     const long long p0 = (long long)blockIdx.x * CI_PIX;      // CTA pixel range inside sample blockIdx.y
@@ -281,9 +279,10 @@ conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
 }
 }  // namespace
 
-extern "C" int sdk_conv_in(const float* x, const float* w, const float* bias, float* out, double* chan_stats,
+extern "C" int sdk_conv_in(const float* x, const float* w_t, const float* bias, float* out, double* chan_stats,
                            int B, int H, int W, int N, void* stream) {
-    SDK_CHECK_ARG(x && w && out && B > 0 && B < 65536 && H > 0 && W > 0, "sdk_conv_in: bad args");
+    SDK_CHECK_ARG(x && w_t && out && B > 0 && B < 65536 && H > 0 && W > 0, "sdk_conv_in: bad args");
+    SDK_CHECK_ARG((((uintptr_t)x | (uintptr_t)w_t | (uintptr_t)out) & 15) == 0, "sdk_conv_in: pointers must be 16-byte aligned");
     SDK_CHECK_ARG(N % 4 == 0 && N >= 4 && N / 4 <= CI_THREADS, "sdk_conv_in: N=%d must be a multiple of 4, at most %d", N, 4 * CI_THREADS);
     const int px_lanes = CI_THREADS / (N / 4);
     const size_t smem = sizeof(float) * ((size_t)36 * N + (size_t)px_lanes * N * 2);
@@ -294,7 +293,7 @@ extern "C" int sdk_conv_in(const float* x, const float* w, const float* bias, fl
         configured = smem;
     }
     const int chunks = (H * W + CI_PIX - 1) / CI_PIX;
-    SDK_CUDA(sdk_launch(conv_in_kernel, dim3(chunks, B), dim3(CI_THREADS), smem, (cudaStream_t)stream, x, w, bias, out,
+    SDK_CUDA(sdk_launch(conv_in_kernel, dim3(chunks, B), dim3(CI_THREADS), smem, (cudaStream_t)stream, x, w_t, bias, out,
                         reinterpret_cast<double2*>(chan_stats), B, H, W, N));
     SDK_LAUNCH_CHECK();
     return SDK_OK;

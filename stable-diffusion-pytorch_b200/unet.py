@@ -554,7 +554,9 @@ class StepProgram:
             # dedicated K = 36 kernel; also accumulates the statistics table of the first GroupNorm
             x = self.pool.get(B * H * W, BLOCK_OUT[0], F32_T)
             cs = self._stat_table(B, BLOCK_OUT[0]) if self.gn_from_sums else None
-            self._emit(lib.sdk_conv_in, xin.data_ptr(), t["conv_in.w"].data_ptr(), t["conv_in.b"].data_ptr(), x.data_ptr(),
+            w_t = t["conv_in.w"].float().reshape(BLOCK_OUT[0], 36).t().contiguous()        # [kh][kw][cin][N]
+            self.keep.append(w_t)
+            self._emit(lib.sdk_conv_in, xin.data_ptr(), w_t.data_ptr(), t["conv_in.b"].data_ptr(), x.data_ptr(),
                        cs.data_ptr() if cs is not None else 0, B, H, W, BLOCK_OUT[0])
             if cs is not None:
                 x._cstats = cs

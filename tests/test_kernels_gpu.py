@@ -404,7 +404,8 @@ def test_conv_in(dev, shape):
     bias = gen((N,), 73, dev, 0.1)
     out = torch.full((B, H, W, N), float("nan"), device=dev)
     cs = torch.zeros((B, N, 2), device=dev, dtype=torch.float64)
-    _lib.check(lib.sdk_conv_in(x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), cs.data_ptr(), B, H, W, N, stream()))
+    w_t = w.reshape(N, 36).t().contiguous()                      # [kh][kw][cin][N]
+    _lib.check(lib.sdk_conv_in(x.data_ptr(), w_t.data_ptr(), bias.data_ptr(), out.data_ptr(), cs.data_ptr(), B, H, W, N, stream()))
     want = Fn.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
     assert rel_l2(out, want) < 2e-6
     flat = out.view(B, H * W, N).double()
