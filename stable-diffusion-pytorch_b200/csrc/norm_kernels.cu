@@ -654,7 +654,8 @@ int launch_gn_apply(GNApplyArgs& a, int out_dtype, cudaStream_t stream) {
     static const int ppt = getenv("SDB200_GN_PPT") ? atoi(getenv("SDB200_GN_PPT")) : 16;   // pixels per thread (batch 16: 8 -> 2.08 ms, 16 -> 1.98 ms, 32 -> 2.01 ms of GroupNorm per step)
     int ppc = ppt * px_lanes;
     int chunks = (HW + ppc - 1) / ppc;
-    const int want = (sdk_num_sms() * 2 + B - 1) / B;
+    static const int ctas_per_sm = getenv("SDB200_GN_CTAS") ? atoi(getenv("SDB200_GN_CTAS")) : 4;   // small tensors: CTAs per SM (UNet batch 2: 2 -> 0.57, 4 -> 0.51, 8 -> 0.64 ms of GroupNorm per step)
+    const int want = (sdk_num_sms() * ctas_per_sm + B - 1) / B;
     if (chunks < want) { chunks = want < HW ? want : HW; ppc = (HW + chunks - 1) / chunks; }
     chunks = (HW + ppc - 1) / ppc;
     SDK_CHECK_ARG(B < 65536, "sdk_groupnorm_apply: batch too large");
