@@ -918,7 +918,7 @@ splitk_reduce_kernel(const __grid_constant__ TcParams p) {
 
 // Split-K second pass that also produces the per-channel statistics: CTA = 32 rows x 32 columns of one sample; thread =
 // (row, float4 column).  Column sums: one shared-memory fold over the 32 rows, then 64 double atomics per CTA.
-// Sums the splits in the same order as splitk_reduce_kernel (identical values).  fp32 NHWC output, no GEGLU; H*W % 32 == 0.
+// Sums the splits in index order (deterministic).  fp32 NHWC output, no GEGLU; H*W % 32 == 0.
 __global__ void __launch_bounds__(256)
 splitk_reduce_stats_kernel(const __grid_constant__ TcParams p) {
     pdl_trigger();
@@ -940,13 +940,19 @@ splitk_reduce_stats_kernel(const __grid_constant__ TcParams p) {
         const size_t off = (size_t)grow * N + n;
         const float* src = p.partial + off;
         int sp = 0;
+        for (; sp + 8 <= p.splits; sp += 8) {                  // 8 partial planes in flight: one L2 round trip per 8 splits
+            float4 t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + i) * plane));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[0] += t[i].x; v[1] += t[i].y; v[2] += t[i].z; v[3] += t[i].w; }
+        }
         for (; sp + 4 <= p.splits; sp += 4) {
-            const float4 a = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sp * plane));
-            const float4 b4 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 1) * plane));
-            const float4 c = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 2) * plane));
-            const float4 d = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 3) * plane));
-            v[0] = (((v[0] + a.x) + b4.x) + c.x) + d.x; v[1] = (((v[1] + a.y) + b4.y) + c.y) + d.y;
-            v[2] = (((v[2] + a.z) + b4.z) + c.z) + d.z; v[3] = (((v[3] + a.w) + b4.w) + c.w) + d.w;
+            float4 t[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + i) * plane));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { v[0] += t[i].x; v[1] += t[i].y; v[2] += t[i].z; v[3] += t[i].w; }
         }
         for (; sp < p.splits; ++sp) {
             const float4 a = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sp * plane));
