@@ -1120,7 +1120,7 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     }
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     p.M = (long long)d->B * d->H * d->W;
-    SDK_CHECK_ARG(p.M < (1ll << 24), "sdk_tc_gemm_create: B*H*W = %lld output rows exceeds 2^24", p.M);
+    if (p.M >= (1ll << 24)) { delete g; return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_create: B*H*W = %lld output rows exceeds 2^24", p.M); }
     p.w_kmajor = d->w_kmajor;
     // ---- N tile and split-K: pick the (block_n, splits) pair with the lowest modelled time.
     // Model (SM clocks), constants measured on B200 (profiles/): a CTA's k-block is bound by the L2->smem feed of

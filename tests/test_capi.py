@@ -67,3 +67,20 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.ExtensionMissing, match="no CPU/PyTorch fallback"):
         _lib.lib()
+
+
+def test_tune_cache_roundtrip(tmp_path, monkeypatch):
+    """Measured GEMM tilings persist as JSON keyed by GPU model + layer shape; 2-element entries of older files still load."""
+    import json
+    from stable_diffusion_pytorch_b200.unet import StepProgram
+    f = tmp_path / "tune.json"
+    f.write_text(json.dumps({"NVIDIA B200|2|64|64|320|1|320|3|0|0|0|0|1|1": [160, 1], "NVIDIA B200|1|1|8192|960|1|320|1|0|0|1|0|0|0": [128, 3, 0]}))
+    monkeypatch.setenv("SDB200_TC_TUNE_FILE", str(f))
+    monkeypatch.setattr(StepProgram, "_tune_loaded", False)
+    monkeypatch.setattr(StepProgram, "_tune_cache", {})
+    monkeypatch.setattr(StepProgram, "_tune_file", str(f))
+    StepProgram._tune_load()
+    assert StepProgram._tune_cache["NVIDIA B200|2|64|64|320|1|320|3|0|0|0|0|1|1"] == (160, 1)
+    StepProgram._tune_cache["k"] = (64, 2, 0)
+    StepProgram._tune_save()
+    assert json.loads(f.read_text())["k"] == [64, 2, 0]
