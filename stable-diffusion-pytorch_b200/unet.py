@@ -86,6 +86,7 @@ class PackedWeights:
             if r.has_proj:
                 t[f"{p}.proj.w"], t[f"{p}.proj.b"] = conv_w(f"{p}.proj_input.weight"), dev(sd[f"{p}.proj_input.bias"])
                 t[f"{p}.conv2_proj.b"] = dev(sd[f"{p}.conv_2.bias"].float() + sd[f"{p}.proj_input.bias"].float())
+        kv_list = []
         for tr in a.transformers:
             p, b, c = tr.prefix, f"{tr.prefix}.transformer_block", tr.c
             t[f"{p}.gn.g"], t[f"{p}.gn.b"] = dev(sd[f"{p}.groupnorm.weight"]), dev(sd[f"{p}.groupnorm.bias"])
@@ -96,7 +97,11 @@ class PackedWeights:
             t[f"{p}.qkv.w"] = dev(torch.cat([sd[f"{b}.attn1.{n}_proj.weight"] for n in "qkv"], 0), wdt)
             t[f"{p}.o1.w"], t[f"{p}.o1.b"] = dev(sd[f"{b}.attn1.out_proj.weight"], wdt), dev(sd[f"{b}.attn1.out_proj.bias"])
             t[f"{p}.q2.w"] = dev(sd[f"{b}.attn2.q_proj.weight"], wdt)
-            t[f"{p}.kv2.w"] = dev(torch.cat([sd[f"{b}.attn2.k_proj.weight"], sd[f"{b}.attn2.v_proj.weight"]], 0), wdt)
+            kv_w = torch.cat([sd[f"{b}.attn2.k_proj.weight"], sd[f"{b}.attn2.v_proj.weight"]], 0)
+            if precision == "fp32":
+                t[f"{p}.kv2.w"] = dev(kv_w, wdt)
+            else:
+                kv_list.append((tr.index, kv_w))           # bf16: all 16 context projections become ONE GEMM (see kv2_all.w)
             t[f"{p}.o2.w"], t[f"{p}.o2.b"] = dev(sd[f"{b}.attn2.out_proj.weight"], wdt), dev(sd[f"{b}.attn2.out_proj.bias"])
             w0, b0 = sd[f"{b}.ffn.0.proj.weight"], sd[f"{b}.ffn.0.proj.bias"]      # [8C, C]: rows [value(4C) ; gate(4C)]
             t[f"{p}.ff0.w"] = dev(torch.stack([w0[:4 * c], w0[4 * c:]], 1).reshape(8 * c, c), wdt)
@@ -106,6 +111,14 @@ class PackedWeights:
             if st.resample is not None:
                 p = st.resample.prefix
                 t[f"{p}.w"], t[f"{p}.b"] = conv_w(f"{p}.weight"), dev(sd[f"{p}.bias"])
+        # cross-attention K/V projections of every transformer, rows concatenated: the context program is one [Bc*77, dctx] x
+        # [sum 2C, dctx]^T GEMM (24960 output columns for SD1.5) instead of 16 launches; kv_off[index] = first column of a layer
+        self.kv_off, self.kv_total = {}, 0
+        if kv_list:
+            for idx, w in kv_list:
+                self.kv_off[idx] = self.kv_total
+                self.kv_total += w.shape[0]
+            t["kv2_all.w"] = dev(torch.cat([w for _, w in kv_list], 0), wdt)
         t["out.gn.g"], t["out.gn.b"] = dev(sd["output.0.weight"]), dev(sd["output.0.bias"])
         t["out.w"], t["out.b"] = conv_w("output.2.weight", wdt), dev(sd["output.2.bias"])
         self.t = t
@@ -489,13 +502,18 @@ class StepProgram:
         n2 = self._ln(h2, t[f"{p}.ln2.g"], t[f"{p}.ln2.b"], M, Cc)
         q2, _, _ = self._conv([(n2, Cc)], t[f"{p}.q2.w"], None, 1, 1, M, Cc, out_code=self.act)
         self.pool.put(n2)
-        kv = torch.empty((self.Bc * self.Sk, 2 * Cc), dtype=_DT[self.act], device=self.device)
-        self.kv[tr.index] = kv
-        self._conv([(self.cond_act, tr.dctx)], t[f"{p}.kv2.w"], None, 1, 1, self.Bc * self.Sk, 2 * Cc,
-                   out_code=self.act, out=kv, ctx=True)
-        kvb = kv.data_ptr()
-        kv_batch = self.Sk * 2 * Cc if self.Bc == B else 0
-        ao2 = self._attention(q2.data_ptr(), Cc, S * Cc, kvb, 2 * Cc, kv_batch, kvb + Cc * es, 2 * Cc, kv_batch,
+        if self.kv_all is not None:                               # one GEMM for all layers (context program, emitted in _build)
+            kv_row = self.pw.kv_total
+            kvb = self.kv_all.data_ptr() + self.pw.kv_off[tr.index] * es
+        else:
+            kv_row = 2 * Cc
+            kv = torch.empty((self.Bc * self.Sk, 2 * Cc), dtype=_DT[self.act], device=self.device)
+            self.kv[tr.index] = kv
+            self._conv([(self.cond_act, tr.dctx)], t[f"{p}.kv2.w"], None, 1, 1, self.Bc * self.Sk, 2 * Cc,
+                       out_code=self.act, out=kv, ctx=True)
+            kvb = kv.data_ptr()
+        kv_batch = self.Sk * kv_row if self.Bc == B else 0
+        ao2 = self._attention(q2.data_ptr(), Cc, S * Cc, kvb, kv_row, kv_batch, kvb + Cc * es, kv_row, kv_batch,
                               B, tr.heads, S, self.Sk, D, Cc)
         self.pool.put(q2)
         h3, _, _ = self._conv([(ao2, Cc)], t[f"{p}.o2.w"], t[f"{p}.o2.b"], 1, 1, M, Cc, residual=h2)
@@ -547,6 +565,11 @@ class StepProgram:
             self._emit(lib.sdk_cast_upsample, self.cond_in.data_ptr(), self.cond_act.data_ptr(), self.act,
                        1, 1, self.Bc * self.Sk, a.dctx, 1, ctx=True)
 
+        self.kv_all = None
+        if self.pw.kv_total:
+            self.kv_all = torch.empty((self.Bc * self.Sk, self.pw.kv_total), dtype=_DT[self.act], device=dev)
+            self._conv([(self.cond_act, a.dctx)], t["kv2_all.w"], None, 1, 1, self.Bc * self.Sk, self.pw.kv_total,
+                       out_code=self.act, out=self.kv_all, ctx=True)
         # conv_in (unet.py:256): NCHW latent -> NHWC, then 3x3 conv with Cin = 4 (FFMA kernel: K = 36)
         xin = self.pool.get(B * H * W, a.in_channels, F32_T)
         self._emit(lib.sdk_nchw_to_nhwc, self.x_in.data_ptr(), xin.data_ptr(), self.b_src, B, a.in_channels, H * W)
