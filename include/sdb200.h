@@ -67,6 +67,9 @@ int sdk_x0_from_eps(const float* x, const float* eps, float sigma, float alpha, 
 
 /* device-side walk of the (host-built) timestep grid: t_out[0] = table[counter[0]++]  (models/diffusion.py:223) */
 int sdk_next_timestep(const int64_t* table, int n, int* counter, int64_t* t_out, void* stream);
+/* out[0:row_elems] = table[counter[0] + delta][:] (NaN when out of range): per-step row of a table precomputed for the whole
+ * timestep grid -- the loop uses it for the time-embedding projections, which depend only on the timestep (unet.py:182-183,209-220) */
+int sdk_gather_row(const float* table, int64_t row_elems, int n_rows, const int* counter, int delta, float* out, void* stream);
 
 /* ---- normalisation / layout (models/unet/unet.py:66,102-108,157,160,250,343,399) ------------- */
 int64_t sdk_groupnorm_workspace_bytes(int B, int HW);

@@ -31,6 +31,7 @@ SIGNATURES = {
     "sdk_forward_process": [P, P, P, I64, I64, P, I32, P, P],
     "sdk_x0_from_eps": [P, P, F32, F32, P, I64, P],
     "sdk_next_timestep": [P, I32, P, P, P],
+    "sdk_gather_row": [P, I64, I32, P, I32, P, P],
     # --- norm_kernels.cu
     "sdk_groupnorm_workspace_bytes": [I32, I32],
     "sdk_groupnorm_stats": [P, I32, P, I32, I32, I32, F32, P, P, P],

@@ -263,3 +263,28 @@ extern "C" int sdk_next_timestep(const int64_t* table, int n, int* counter, int6
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
+
+
+// out[0:row_elems] = table[counter[0] + delta][:]  -- lets the step graph fetch per-step rows of a table that was
+// precomputed for the whole timestep grid (the time-embedding projections depend only on the timestep: unet.py:209-220,182-183)
+namespace {
+__global__ void __launch_bounds__(256)
+gather_row_kernel(const float* __restrict__ table, long long row_elems, int n_rows, const int* __restrict__ counter, int delta,
+                  float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    const int row = counter[0] + delta;
+    const bool ok = row >= 0 && row < n_rows;
+    const float* src = table + (long long)(ok ? row : 0) * row_elems;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < row_elems; i += (long long)gridDim.x * blockDim.x)
+        out[i] = ok ? __ldg(src + i) : __int_as_float(0x7fc00000);
+}
+}  // namespace
+
+extern "C" int sdk_gather_row(const float* table, int64_t row_elems, int n_rows, const int* counter, int delta, float* out, void* stream) {
+    SDK_CHECK_ARG(table && counter && out && row_elems > 0 && n_rows > 0, "sdk_gather_row: bad args");
+    SDK_CUDA(sdk_launch(gather_row_kernel, dim3(grid_for(row_elems, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, table, (long long)row_elems, n_rows,
+                        counter, delta, out));
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}

@@ -550,6 +550,7 @@ class StepProgram:
         te2 = torch.empty((self.nt, a.temb), dtype=f32, device=dev)
         self.tb = torch.empty((self.nt, a.tb_total), dtype=f32, device=dev)
         self.keep += [te0, te1, te2]
+        t_first = len(self.ops)
         self._emit(lib.sdk_time_sinusoid, self.t_in.data_ptr(), self.nt, a.t_embed_dim, te0.data_ptr())
         self._emit(lib.sdk_gemv, t["time_embedding.ffn.0.weight"].data_ptr(), F32_T, t["time_embedding.ffn.0.bias"].data_ptr(),
                    te0.data_ptr(), te1.data_ptr(), self.nt, a.temb, a.t_embed_dim, 0, 1)
@@ -557,6 +558,8 @@ class StepProgram:
                    te1.data_ptr(), te2.data_ptr(), self.nt, a.temb, a.temb, 0, 0)
         self._emit(lib.sdk_gemv, t["tb.w"].data_ptr(), self.pw.wcode, t["tb.b"].data_ptr(),
                    te2.data_ptr(), self.tb.data_ptr(), self.nt, a.tb_total, a.temb, 1, 0)
+        self.time_ops = self.ops[t_first:]       # timestep -> self.tb; a sampling loop precomputes them for its whole grid
+        self._time_range = (t_first, len(self.ops))
         # context operand (context program)
         if self.act == F32_T:
             self.cond_act = self.cond_in.view(self.Bc * self.Sk, a.dctx)
@@ -675,8 +678,12 @@ class StepProgram:
         self.tc_ws = torch.zeros(max(need, 256), dtype=torch.uint8, device=self.device)
         for h in self.tc_handles:
             _lib.check(self.lib.sdk_tc_gemm_set_workspace(h, self.tc_ws.data_ptr()))
+        t0, t1 = self._time_range
+        self.body_ops = self.ops[:t0] + self.ops[t1:]       # the step without the time-embedding chain
         if self.gn_from_sums:                               # first op of the step: zero every statistics table at once
-            self.ops.insert(0, (self.lib.sdk_zero, (self.stat_arena.data_ptr(), self.stat_used)))
+            zero = (self.lib.sdk_zero, (self.stat_arena.data_ptr(), self.stat_used))
+            self.ops.insert(0, zero)
+            self.body_ops.insert(0, zero)
             self.n_launch = len(self.ops)
 
     def tc_info(self):
