@@ -104,6 +104,7 @@ def cpu_loop_body_seconds(cfg, sd, arch, hw, n_timed, budget_s):
     """Seconds per loop-body step of the ORACLE port on the host cores (UNet batch 2B=2 + CFG + DDIM)."""
     from oracle import sampler_oracle as SO
     from oracle import unet_oracle as UO
+    UO.USE_SDPA = True                                     # the reference's stock attention path (models/unet/attention.py:37-43)
     torch.set_num_threads(os.cpu_count())
     g = torch.Generator().manual_seed(1234)
     lat = torch.randn((1, 4, hw, hw), generator=g)
@@ -129,6 +130,7 @@ def cpu_loop_body_seconds(cfg, sd, arch, hw, n_timed, budget_s):
                 times.append(dt)
             if time.time() - t_start > budget_s and len(times) >= 1:
                 break
+    UO.USE_SDPA = False
     return sum(times) / len(times), len(times)
 
 
@@ -141,7 +143,7 @@ def run_reference_arm(args, cfg):
     total = args.steps + args.warmup
     hw = cfg["hw"]
     est_full = 6.0 * (GFLOP_PER_SAMPLE[(cfg["arch"], hw)] / 803.25)
-    sample = f"full loop-body steps at {hw}x{hw} latent, UNet batch {2 if cfg['cfg'] else 1}"
+    sample = f"full loop-body steps (oracle port, SDPA attention) at {hw}x{hw} latent, UNet batch {2 if cfg['cfg'] else 1}"
     scale = 1.0
     if total * est_full > 240 and (cfg["arch"], 32) in GFLOP_PER_SAMPLE:
         scale = GFLOP_PER_SAMPLE[(cfg["arch"], hw)] / GFLOP_PER_SAMPLE[(cfg["arch"], 32)]
@@ -155,7 +157,7 @@ def run_reference_arm(args, cfg):
     line = {"impl": "reference", "metric": "images_per_sec", "value": img_s, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "timed_steps": used},
+            "config": make_config(cfg, cfg["batch"], (2 if cfg["cfg"] else 1) * cfg["batch"]), "timed_steps": used,
             "cpu_baseline": {"value": img_s, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": img_s, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -282,11 +284,59 @@ def run_one_step(args, cfg):
         "clocks": sampler.summary()}))
 
 
+def make_config(cfg, B, ub):
+    """The `config` object of the JSON line: the workload only, IDENTICAL for our arm and for the reference arm."""
+    return {"workload": cfg["name"], "images_per_gpu": B, "unet_batch_per_gpu": ub, "latent": [cfg["hw"], cfg["hw"]],
+            "sampler_steps_per_image": cfg["steps"], "cfg_scale": 7.5 if cfg["cfg"] else None,
+            "l2_policy": "inputs larger than L2: each step streams 1.72 GB of bf16 weights (L2 = 126 MB)"}
+
+
+def timed_steps(loop, smp, K, Wm, repeats, dev, world, dist, lat_d, ctx_d):
+    """W warm-up steps, then `repeats` regions of EXACTLY K steps each, every region bracketed by barrier + synchronize and
+    timed with CUDA events; per-region time = MAX over ranks.  Returns the sorted per-step times (ms) of the regions."""
+    n_grid = len(smp.timesteps)
+    pos = [0]
+
+    def run_steps(n):
+        done = 0
+        while done < n:                                      # walk the sampler grid; restart the walk when it ends
+            m = min(n - done, n_grid - pos[0])
+            for _ in range(m):
+                loop.step()
+            pos[0] += m
+            done += m
+            if pos[0] >= n_grid:
+                loop.counter.zero_()
+                pos[0] = 0
+
+    loop.reset(lat_d, ctx_d)
+    run_steps(Wm)
+    out = []
+    for _ in range(repeats):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        run_steps(K)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out.append(float(t.item()) / K)
+    return sorted(out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of --steps steps each; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--batch-per-gpu", type=int, default=0)
@@ -295,6 +345,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also time each kernel class of one step as its own graph")
     ap.add_argument("--no-torch-eager", action="store_true", help="skip timing the reference op sequence in stock PyTorch eager on this GPU")
+    ap.add_argument("--no-config3", action="store_true", help="N > 1: skip the batch-64-sharded (BASELINE config 3) measurement")
+    ap.add_argument("--no-fp32", action="store_true", help="N = 1: skip the one-off fp32-mode ms/step figure")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch_per_gpu:
@@ -332,42 +384,12 @@ def main():
     K, Wm = args.steps, args.warmup
     n_grid = len(smp.timesteps)
 
-    def run_steps(n):
-        done = 0
-        while done < n:                                      # walk the 50-step grid; restart the walk when it ends
-            m = min(n - done, n_grid - int(loop_pos[0]))
-            for _ in range(m):
-                loop.step()
-            loop_pos[0] += m
-            done += m
-            if loop_pos[0] >= n_grid:
-                loop.counter.zero_()
-                loop_pos[0] = 0
-
-    loop_pos = [0]
     with torch.no_grad():
-        loop.reset(lat_d, ctx_d)
-        run_steps(Wm)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        run_steps(K)
-        e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        regions = timed_steps(loop, smp, K, Wm, max(1, args.repeats), dev, world, dist, lat_d, ctx_d)
         sampler.stop_flag = True
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        ms_step = ms_total / K
+        ms_step = regions[len(regions) // 2]                  # median region
         finite = bool(torch.isfinite(loop.latent).all().item())
 
         # ---- e2e through the public drop-in API with HOST buffers (UNet.forward + sampler.reverse_process)
@@ -391,18 +413,21 @@ def main():
         for i in range(3):
             e2e_step(i)
         k2 = max(3, min(K, 20))
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for i in range(k2):
-            e2e_step(3 + i)
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / k2
-        t = torch.tensor([e2e_ms], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        e2e_regions = []
+        for rep in range(max(1, min(args.repeats, 3))):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for i in range(k2):
+                e2e_step(3 + i)
+            torch.cuda.synchronize()
+            t = torch.tensor([(time.perf_counter() - t0) * 1e3 / k2], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_regions.append(float(t.item()))
+        e2e_regions.sort()
+        e2e_ms = e2e_regions[len(e2e_regions) // 2]
         h2d = lat_h.numel() * 4 + ctx_h.numel() * 4 + 8
         d2h = res_h.numel() * 4
 
@@ -420,9 +445,69 @@ def main():
                     ms, n = time_gemm_family(loop, fns=fns)
                     breakdown[label] = {"ms": ms, "launches": n}
 
-        # the path's only collective: gather final latents (not timed; checked)
+        # the path's only collective: ONE all-gather of the final latents per generation -- timed once, outside the step loop
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
         final = gather_latents(loop.latent.clone(), B * world)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
         assert final.shape[0] == B * world
+        launches_per_step = loop.launches_per_step
+
+        # ---- N > 1: BASELINE config 3 (batch 64 SHARDED over the N GPUs: strong scaling) in the same run
+        config3 = None
+        if world > 1 and args.config == 2 and not args.no_config3 and 64 % world == 0:
+            try:
+                del loop
+                net.invalidate()
+                torch.cuda.empty_cache()
+                c3 = dict(CONFIGS[3])
+                B3 = 64 // world
+                _, _, lat3_all, ctx3_all = build_oracle_inputs(c3, 64)          # full batch from ONE generator, then sliced
+                l3, x3 = shard_inputs(lat3_all, ctx3_all, rank, world, do_cfg=True)
+                loop3 = DenoiseLoop(net, smp, B3, 64, 64, do_cfg=True, cfg_scale=7.5, use_cuda_graph=not args.no_graph)
+                k3 = max(3, min(K, 10))
+                reg3 = timed_steps(loop3, smp, k3, 3, max(1, min(args.repeats, 3)), dev, world, dist, l3.to(dev), x3.to(dev))
+                ms3 = reg3[len(reg3) // 2]
+                fin3 = bool(torch.isfinite(loop3.latent).all().item())
+                torch.cuda.synchronize()
+                dist.barrier()
+                g0.record()
+                final3 = gather_latents(loop3.latent.clone(), 64)
+                g1.record()
+                torch.cuda.synchronize()
+                _, _, tf_sus3, _ = peaks()
+                gf3 = GFLOP_PER_SAMPLE[("sd15", 64)] * 2 * B3                     # per GPU per step
+                config3 = {"workload": "SD1.5-arch UNet 512^2, DDIM-50, CFG 7.5, batch 64 sharded over %d GPUs (%d images, UNet batch %d per GPU)" % (world, B3, 2 * B3),
+                           "scaling": "strong", "ms_per_step": ms3, "ms_per_step_min": reg3[0], "ms_per_step_max": reg3[-1], "timed_steps": k3,
+                           "images_per_s": 64 / (50 * ms3 * 1e-3), "step_tflops_per_gpu": gf3 / ms3, "frac": gf3 / ms3 / tf_sus3,
+                           "gather_latents_ms": g0.elapsed_time(g1), "gathered": list(final3.shape), "finite": fin3}
+                del loop3
+            except Exception as ex:                                               # never take the headline line down
+                config3 = {"error": repr(ex)}
+
+        # ---- N = 1: what the exact-fp32 mode (the 1e-4 parity gate) costs per step, reported once
+        fp32_ms = None
+        if world == 1 and args.precision == "bf16" and not args.no_fp32 and args.config == 2:
+            try:
+                if "loop" in dir():
+                    del loop
+                net.invalidate()
+                torch.cuda.empty_cache()
+                net.set_precision("fp32")
+                loopf = DenoiseLoop(net, smp, B, cfg["hw"], cfg["hw"], do_cfg=cfg["cfg"], cfg_scale=7.5, use_cuda_graph=not args.no_graph)
+                regf = timed_steps(loopf, smp, 3, 3, 1, dev, 1, dist, lat_d, ctx_d)
+                fp32_ms = regf[0]
+                del loopf
+                net.invalidate()
+                net.set_precision(args.precision)
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                fp32_ms = repr(ex)
 
     if world > 1:
         dist.barrier()
@@ -441,34 +526,41 @@ def main():
         gemm_gflop = GEMM_GFLOP_B2_SD15_64 * (ub / 2.0) if (cfg["arch"], cfg["hw"]) == ("sd15", 64) else None
         if gemm_gflop:
             ach = gemm_gflop / gemm_ms            # GFLOP / ms == TFLOP/s
-            traffic = None
-            try:
-                with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
-                    tj = json.load(f)
-                if ub == 2:                       # captured for UNet batch 2 only
-                    traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-            except Exception:
-                pass
+            traffic, traffic_src = None, None
+            for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+                try:
+                    with open(os.path.join(ROOT, "profiles", name)) as f:
+                        tj = json.load(f)
+                    if ub == 2:                       # captured for UNet batch 2 only
+                        traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], name
+                    break
+                except Exception:
+                    continue
             roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": traffic,
-                    "traffic_note": "DRAM bytes of all launches of the kernel in one step (ncu, cold L2 per launch): profiles/r01_gemm_traffic.json",
+                    "traffic_note": f"DRAM bytes of all launches of the kernel in one step (ncu, cold L2 per launch): profiles/{traffic_src}",
                     "kernel": "conv_gemm_tc_kernel (tcgen05 implicit GEMM), all launches of one step",
                     "launches_per_step": gemm_launches, "ms_per_step_in_kernel": gemm_ms, "share_of_step": gemm_ms / ms_step,
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"}
     line = {
         "metric": "images_per_sec", "value": imgs_per_s, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_step, "ms_per_step_min": regions[0], "ms_per_step_max": regions[-1], "repeats": len(regions),
+        "timing": "median of `repeats` CUDA-event-timed regions of `steps` steps each (max over ranks per region)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": cfg["name"], "images_per_gpu": B, "unet_batch_per_gpu": ub, "latent": [cfg["hw"], cfg["hw"]],
-                   "sampler_steps_per_image": cfg["steps"], "cfg_scale": 7.5 if cfg["cfg"] else None,
-                   "l2_policy": "inputs larger than L2: each step streams 1.72 GB of bf16 weights (L2 = 126 MB)",
-                   "cuda_graph": not args.no_graph, "finite": finite},
+        "config": make_config(cfg, B, ub), "cuda_graph": not args.no_graph, "finite": finite,
         "step_tflops": step_gflop / ms_step, "step_frac_of_peak": step_gflop / ms_step / tf_sus,
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_imgs, "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": e2e_imgs, "unit": "images/s", "ms_per_step": e2e_ms, "ms_per_step_min": e2e_regions[0], "ms_per_step_max": e2e_regions[-1],
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "UNet.forward + DDIMSampler.reverse_process, pinned host buffers in and out every step"},
-        "gpu_launches": loop.launches_per_step * K,
+        "gpu_launches": launches_per_step * K * len(regions),
+        "gather_latents_ms": gather_ms,
         "roofline": roof,
     }
+    if config3 is not None:
+        line["config3"] = config3
+    if fp32_ms is not None:
+        line["fp32_mode_ms_per_step"] = fp32_ms
     if breakdown:
         line["breakdown_ms_per_step"] = breakdown
     if not args.no_torch_eager and cfg["cfg"] and world == 1:
@@ -480,7 +572,7 @@ def main():
         try:
             sec, used = cpu_loop_body_seconds(cfg, sd, arch, cfg["hw"], 2, budget_s=45)
             line["cpu_baseline"] = {"value": 1.0 / (cfg["steps"] * sec), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"{used} loop-body steps (after 1 warm-up) of the oracle port at {cfg['hw']}x{cfg['hw']}, extrapolated x{cfg['steps']}",
+                                    "sample": f"{used} loop-body steps (after 1 warm-up) of the oracle port (SDPA attention as attention.py:37-43) at {cfg['hw']}x{cfg['hw']}, extrapolated x{cfg['steps']}",
                                     "s_per_step": sec}
         except Exception as ex:                               # the baseline must never take the bench line down
             line["cpu_baseline"] = {"error": repr(ex)}

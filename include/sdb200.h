@@ -31,9 +31,9 @@ extern "C" {
 /* ---- library ------------------------------------------------------------------------------ */
 const char* sdk_last_error(void);
 int sdk_version(void);
-/* out[0]=SM count, out[1..2]=compute capability, out[3]=max opt-in shared memory per block */
 /* stream-ordered memset to zero (graph-capturable) */
 int sdk_zero(void* ptr, int64_t bytes, void* stream);
+/* out[0]=SM count, out[1..2]=compute capability, out[3]=max opt-in shared memory per block (of the current device) */
 int sdk_device_info(int* out, int n);
 /* programmatic dependent launch for all kernels (1 = on; default off): kernel N+1's prologue overlaps kernel N's tail */
 int sdk_set_pdl(int enabled);
@@ -95,7 +95,8 @@ int sdk_channel_stats(const float* src, int B, int HW, int C, double* out, void*
 int sdk_groupnorm_fused(const float* src0, int C0, const float* src1, int C1, int B, int HW, float eps,
                         const float* gamma, const float* beta, int silu, void* out, void* raw_out, int out_dtype,
                         void* workspace, void* stream);
-/* statistics + apply in ONE launch, one thread-block cluster per sample, DSMEM reduction (default of the step program) */
+/* statistics + apply in ONE launch, one thread-block cluster per sample, DSMEM reduction (optional mode SDB200_GN_MODE=cluster;
+ * the bf16 step program takes its statistics from the producing GEMM's epilogue instead: sdk_groupnorm_apply_cs) */
 int sdk_groupnorm_cluster(const float* src0, int C0, const float* src1, int C1, int B, int HW, float eps,
                           const float* gamma, const float* beta, int silu, void* out, void* raw_out, int out_dtype,
                           void* stream);

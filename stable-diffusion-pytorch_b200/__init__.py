@@ -6,7 +6,7 @@ library (include/sdb200.h).  See DESIGN.md / INTEGRATION.md.
 """
 from .scheduler import DDIMSampler, DDPMSampler, x0_from_eps  # noqa: F401
 
-__all__ = ["DDIMSampler", "DDPMSampler", "x0_from_eps", "UNet", "DenoiseLoop"]
+__all__ = ["DDIMSampler", "DDPMSampler", "x0_from_eps", "UNet", "DenoiseLoop", "denoise", "one_step", "img2img", "inpaint"]
 
 
 def __getattr__(name):
@@ -14,7 +14,7 @@ def __getattr__(name):
     if name == "UNet":
         from .unet import UNet
         return UNet
-    if name in ("DenoiseLoop", "denoise", "one_step"):
+    if name in ("DenoiseLoop", "denoise", "one_step", "img2img", "inpaint"):
         from . import pipeline
         return getattr(pipeline, name)
     raise AttributeError(name)

@@ -221,11 +221,7 @@ int launch(const __nv_bfloat16* q, long long q_row, long long q_batch, const __n
            int B, int heads, int Sq, int Sk, float scale, cudaStream_t s) {
     constexpr int DP = (D + 15) / 16 * 16, LD = DP + 8;
     const int smem = (BQ + 4 * BKV) * LD * 2;
-    static bool configured = false;
-    if (!configured) {
-        SDK_CUDA(cudaFuncSetAttribute(attention_bf16_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(attention_bf16_kernel<D>), (int)smem));
     dim3 grid((Sq + BQ - 1) / BQ, B * heads);
     SDK_CUDA(sdk_launch(attention_bf16_kernel<D>, dim3(grid), dim3(THREADS), (size_t)(smem), s, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch, out, o_row, o_batch,
                                                          heads, Sq, Sk, scale * 1.4426950408889634f));

@@ -104,11 +104,7 @@ int launch(const float* q, long long q_row, long long q_batch, const float* k, l
            const float* v, long long v_row, long long v_batch, float* out, long long o_row, long long o_batch,
            int B, int heads, int Sq, int Sk, float scale, cudaStream_t s) {
     const size_t smem = sizeof(float) * ((size_t)(BQ + BKV) * (D + 1) + (size_t)BKV * D + (size_t)BQ * (BKV + 1));
-    static bool configured = false;
-    if (!configured) {
-        SDK_CUDA(cudaFuncSetAttribute(attention_f32_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(attention_f32_kernel<D>), (int)smem));
     dim3 grid((Sq + BQ - 1) / BQ, B * heads);
     SDK_CUDA(sdk_launch(attention_f32_kernel<D>, dim3(grid), dim3(THREADS), (size_t)(smem), s, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch,
                                                         out, o_row, o_batch, heads, Sq, Sk, scale));

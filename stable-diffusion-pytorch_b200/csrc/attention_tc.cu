@@ -307,11 +307,7 @@ struct AttnPlan { AttnParams prm; dim3 grid; int D; };
 template <int D>
 int launch(const AttnPlan* a, cudaStream_t s) {
     constexpr int smem = Q_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES + 1024 + 256 + 2 * 128 * 8;
-    static bool configured = false;
-    if (!configured) {
-        SDK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(attention_tc_kernel<D>), (int)smem));
     SDK_CUDA(sdk_launch(attention_tc_kernel<D>, a->grid, dim3(AT_THREADS), (size_t)smem, s, a->prm));
     return SDK_OK;
 }

@@ -26,11 +26,19 @@ int sdk_fail(int code, const char* fmt, ...);
     do { cudaError_t e_ = cudaPeekAtLastError(); if (e_ != cudaSuccess) \
         return sdk_fail(SDK_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
 static inline int sdk_num_sms() {
-    static int n = 0;
-    if (n == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
-    return n;
+    static int n[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& c = n[dev & 63];
+    if (c == 0) { cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev); if (c <= 0) c = 148; }
+    return c;
 }
+
+// Opt `fn` in for `bytes` of dynamic shared memory on the CURRENT device (cudaFuncAttributeMaxDynamicSharedMemorySize is
+// per device); remembers the largest size set per (device, kernel) so the hot path is one table lookup.
+cudaError_t sdk_ensure_dyn_smem(const void* fn, int bytes);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

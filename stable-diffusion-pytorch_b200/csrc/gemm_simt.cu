@@ -287,11 +287,7 @@ extern "C" int sdk_conv_in(const float* x, const float* w_t, const float* bias, 
     const int px_lanes = CI_THREADS / (N / 4);
     const size_t smem = sizeof(float) * ((size_t)36 * N + (size_t)px_lanes * N * 2);
     SDK_CHECK_ARG(smem <= 200 * 1024, "sdk_conv_in: N=%d needs too much shared memory", N);
-    static size_t configured = 0;
-    if (smem > configured) {
-        SDK_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_in_kernel), (int)smem));
     const int chunks = (H * W + CI_PIX - 1) / CI_PIX;
     SDK_CUDA(sdk_launch(conv_in_kernel, dim3(chunks, B), dim3(CI_THREADS), smem, (cudaStream_t)stream, x, w_t, bias, out,
                         reinterpret_cast<double2*>(chan_stats), B, H, W, N));

@@ -1034,11 +1034,7 @@ int stage_smem(int bn, bool two) { return A_STAGE_BYTES + (two ? bn / 2 : bn) * 
 
 template <int BN>
 int launch_persistent(const TcGemm* g, cudaStream_t s) {
-    static int configured = 0;
-    if (g->smem_bytes > configured) {
-        SDK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->smem_bytes));
-        configured = g->smem_bytes;
-    }
+    SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN>), g->smem_bytes));
     SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
@@ -1046,11 +1042,7 @@ int launch_persistent(const TcGemm* g, cudaStream_t s) {
 
 template <int BN, bool TWO = false>
 int launch_cfg(const TcGemm* g, cudaStream_t s) {
-    static int configured = 0;                       // largest dynamic smem size this instantiation has been opted in for
-    if (g->smem_bytes > configured) {
-        SDK_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, g->smem_bytes));
-        configured = g->smem_bytes;
-    }
+    SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_kernel<BN, TWO>), g->smem_bytes));
     if (TWO) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = g->grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = g->smem_bytes; cfg.stream = s;

@@ -807,11 +807,7 @@ extern "C" int sdk_groupnorm_cluster(const float* src0, int C0, const float* src
     a.src0 = src0; a.src1 = src1; a.C0 = C0; a.C1 = C1; a.HW = HW; a.B = B;
     a.stats = nullptr; a.gamma = gamma; a.beta = beta; a.out = out; a.raw_out = raw_out; a.silu = silu;
     void (*fn)(GNApplyArgs, float, int, int, int) = out_dtype == SDK_F32 ? gn_cluster_kernel<float> : gn_cluster_kernel<__nv_bfloat16>;
-    static bool configured[2] = {false, false};
-    if (!configured[out_dtype]) {
-        SDK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured[out_dtype] = true;
-    }
+    SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(fn), 160 * 1024));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS, B); cfg.blockDim = dim3(GNC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute at[1];

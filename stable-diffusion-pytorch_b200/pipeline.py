@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .scheduler import PRED_EPS, PRED_V, DDIMSampler, DDPMSampler, x0_from_eps
-from .unet import StepProgram, UNet
+from .unet import StepProgram, UNet, same_context, tensor_version
 
 
 class DenoiseLoop:
@@ -49,8 +49,9 @@ class DenoiseLoop:
         self.use_graph = unet.use_cuda_graph if use_cuda_graph is None else use_cuda_graph
         self.graph = None
         self.latent = self.prog.x_in                         # the loop state IS the UNet's input staging buffer
-        self.noise = torch.empty_like(self.latent) if isinstance(sampler, DDPMSampler) else None
-        self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.inference_mode(False), torch.no_grad():     # loop state stays writable when built under inference_mode
+            self.noise = torch.empty_like(self.latent) if isinstance(sampler, DDPMSampler) else None
+            self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.ts_table = None
         self.tb_table = None
         self.hoist_time = True                                # precompute the time-embedding rows of the grid (exactly the per-step values)
@@ -126,32 +127,33 @@ class DenoiseLoop:
                     p.launch(p.time_ops)
                     rows.append(p.tb[0].clone())
                 self.tb_table = torch.stack(rows).contiguous()
-        if context is not self._cond_ref or context._version != self._cond_version:
+        if not same_context(context, self._cond_ref, self._cond_version):
             if tuple(context.shape) != tuple(p.cond_in.shape):
                 raise RuntimeError(f"context shape {tuple(context.shape)} != {tuple(p.cond_in.shape)}")
             p.cond_in.copy_(context, non_blocking=True)
             p.launch(p.ctx_ops)                                # cross-attention K/V once per generation (loop-invariant)
-            self._cond_ref, self._cond_version = context, context._version
+            self._cond_ref, self._cond_version = context, tensor_version(context)
 
     def step(self):
         """Advance the latent state by one sampler step (device-side timestep walk)."""
         if isinstance(self.sampler, DDPMSampler):
             # same global-RNG draw as ddpm.py:80, outside the graph so torch's generator state advances normally
             self.noise.copy_(torch.randn(self.latent.shape, dtype=self.latent.dtype, device=self.device))
-        if not self.use_graph:
-            self._enqueue_step()
-        elif self.graph is None:
-            if not getattr(self, "_warm", False):
+        with torch.cuda.device(self.device):
+            if not self.use_graph:
                 self._enqueue_step()
-                self._warm = True
-            else:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+            elif self.graph is None:
+                if not getattr(self, "_warm", False):
                     self._enqueue_step()
-                self.graph = g
-                g.replay()
-        else:
-            self.graph.replay()
+                    self._warm = True
+                else:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._enqueue_step()
+                    self.graph = g
+                    g.replay()
+            else:
+                self.graph.replay()
 
     def reset(self, latent: torch.Tensor, context: torch.Tensor):
         if tuple(latent.shape) != tuple(self.latent.shape):

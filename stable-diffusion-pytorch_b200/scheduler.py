@@ -153,9 +153,10 @@ class _SamplerBase:
             t = t.expand(n).contiguous()
         tab = self._forward_table(x0.device)
         out = torch.empty_like(x0)
-        _lib.check(_lib.lib().sdk_forward_process(
-            x0.data_ptr(), nz.data_ptr(), out.data_ptr(), n, x0.numel() // max(n, 1),
-            tab.data_ptr(), self.noise_step, t.data_ptr(), _lib.current_stream(x0.device)))
+        with torch.cuda.device(x0.device):              # launches go to the tensor's device, not the caller's current one
+            _lib.check(_lib.lib().sdk_forward_process(
+                x0.data_ptr(), nz.data_ptr(), out.data_ptr(), n, x0.numel() // max(n, 1),
+                tab.data_ptr(), self.noise_step, t.data_ptr(), _lib.current_stream(x0.device)))
         return out, noise
 
     def _forward_table(self, device):
@@ -236,11 +237,12 @@ class DDIMSampler(_SamplerBase):
         out = torch.empty_like(x)
         if n == 0:
             return out
-        _lib.check(_lib.lib().sdk_ddim_step(
-            x.data_ptr(), eps_u, eps_c, scale, noise.data_ptr() if noise is not None else 0,
-            out.data_ptr(), n, tab.data_ptr(), self.noise_step, t_ptr, t_host,
-            PRED_V if self.prediction_type == "v_prediction" else PRED_EPS,
-            _lib.current_stream(x.device)))
+        with torch.cuda.device(x.device):              # launches go to the tensor's device, not the caller's current one
+            _lib.check(_lib.lib().sdk_ddim_step(
+                x.data_ptr(), eps_u, eps_c, scale, noise.data_ptr() if noise is not None else 0,
+                out.data_ptr(), n, tab.data_ptr(), self.noise_step, t_ptr, t_host,
+                PRED_V if self.prediction_type == "v_prediction" else PRED_EPS,
+                _lib.current_stream(x.device)))
         return out
 
     step = reverse_process
@@ -279,10 +281,11 @@ class DDIMSampler(_SamplerBase):
         res = torch.empty_like(x) if out is None else out
         if n == 0:
             return res
-        _lib.check(_lib.lib().sdk_ddim_inpaint_step(
-            x.data_ptr(), eps_c, eps_u, scale, orig.data_ptr(), orig.shape[0], m8.data_ptr(), res.data_ptr(), b, ch, h * w,
-            tab.data_ptr(), self.noise_step, t_ptr, t_host, PRED_V if self.prediction_type == "v_prediction" else PRED_EPS,
-            _lib.current_stream(x.device)))
+        with torch.cuda.device(x.device):              # launches go to the tensor's device, not the caller's current one
+            _lib.check(_lib.lib().sdk_ddim_inpaint_step(
+                x.data_ptr(), eps_c, eps_u, scale, orig.data_ptr(), orig.shape[0], m8.data_ptr(), res.data_ptr(), b, ch, h * w,
+                tab.data_ptr(), self.noise_step, t_ptr, t_host, PRED_V if self.prediction_type == "v_prediction" else PRED_EPS,
+                _lib.current_stream(x.device)))
         return res
 
     @staticmethod
@@ -359,9 +362,10 @@ class DDPMSampler(_SamplerBase):
         out = torch.empty_like(x)
         if n == 0:
             return out
-        _lib.check(_lib.lib().sdk_ddpm_step(
-            x.data_ptr(), eps_u, eps_c, scale, nz.data_ptr(), out.data_ptr(), n,
-            tab.data_ptr(), self.noise_step, t_ptr, t_host, _lib.current_stream(x.device)))
+        with torch.cuda.device(x.device):              # launches go to the tensor's device, not the caller's current one
+            _lib.check(_lib.lib().sdk_ddpm_step(
+                x.data_ptr(), eps_u, eps_c, scale, nz.data_ptr(), out.data_ptr(), n,
+                tab.data_ptr(), self.noise_step, t_ptr, t_host, _lib.current_stream(x.device)))
         return out
 
     step = reverse_process
@@ -385,6 +389,7 @@ def x0_from_eps(latent: torch.Tensor, pred_noise: torch.Tensor, alpha_T: float =
     if e.shape != x.shape:
         raise RuntimeError(f"pred_noise {tuple(e.shape)} vs latent {tuple(x.shape)}")
     out = torch.empty_like(x)
-    _lib.check(_lib.lib().sdk_x0_from_eps(x.data_ptr(), e.data_ptr(), float(sigma_T), float(alpha_T),
-                                          out.data_ptr(), x.numel(), _lib.current_stream(x.device)))
+    with torch.cuda.device(x.device):              # launches go to the tensor's device, not the caller's current one
+        _lib.check(_lib.lib().sdk_x0_from_eps(x.data_ptr(), e.data_ptr(), float(sigma_T), float(alpha_T),
+                                              out.data_ptr(), x.numel(), _lib.current_stream(x.device)))
     return out

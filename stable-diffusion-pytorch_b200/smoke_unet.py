@@ -17,16 +17,18 @@ def run():
     net = UNet()
     net.load_state_dict(sd, strict=True)
     net = net.to(dev).eval()
-    for precision, tol in (("fp32", 1e-4), ("bf16", 1e-2)):
+    # bf16 (tcgen05 / TMEM / TMA path) FIRST: a launch-capped profiler window must list the product kernels, not the fp32 FFMA mode
+    smp = DDIMSampler()
+    smp._set_inference_steps(10)
+    net.set_precision("bf16")
+    with torch.no_grad():
+        out = DenoiseLoop(net, smp, 1, 8, 8).run(lat.to(dev), ctx.to(dev), steps=2)
+    assert torch.isfinite(out).all()
+    print("smoke: 2 graph-replayed DDIM steps (tcgen05 GEMMs + flash attention + fused CFG/DDIM) finite")
+    for precision, tol in (("bf16", 1e-2), ("fp32", 1e-4)):
         net.set_precision(precision)
         with torch.no_grad():
             got = net(lat.repeat(2, 1, 1, 1).to(dev), t.to(dev), ctx.to(dev)).cpu().numpy()
         e = float(np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want))
         assert e < tol, f"UNet {precision} forward rel-L2 {e:.3e} vs oracle"
         print(f"smoke: UNet forward ({precision}) on cuda:0 rel-L2 {e:.2e} vs oracle")
-    smp = DDIMSampler()
-    smp._set_inference_steps(10)
-    with torch.no_grad():
-        out = DenoiseLoop(net, smp, 1, 8, 8).run(lat.to(dev), ctx.to(dev), steps=2)
-    assert torch.isfinite(out).all()
-    print("smoke: 2 graph-replayed DDIM steps (tcgen05 GEMMs + flash attention + fused CFG/DDIM) finite")

@@ -31,6 +31,22 @@ from .arch import BLOCK_OUT, Conv, ResBlock, Transformer, UNetArch, build_arch, 
 _DT = {F32_T: torch.float32, BF16_T: torch.bfloat16}
 
 
+def tensor_version(t: torch.Tensor):
+    """``t._version`` or None for inference tensors (``torch.inference_mode()`` tensors do not track a version counter;
+    the reference's inpaint path runs under it, models/diffusion.py:328).  None never compares equal to a cached version,
+    so such a context is treated as changed on every call."""
+    try:
+        return t._version
+    except RuntimeError:
+        return None
+
+
+def same_context(cond: torch.Tensor, ref, version) -> bool:
+    """True when ``cond`` is the tensor object cached as ``ref`` and has not been written since (``version``)."""
+    v = tensor_version(cond)
+    return cond is ref and v is not None and v == version
+
+
 class _Node(nn.Module):
     """Anonymous container so parameters get the reference's dotted names."""
 
@@ -49,6 +65,11 @@ class PackedWeights:
     """
 
     def __init__(self, net: "UNet", device, precision: str):
+        # normal (non-inference) tensors even when the first forward runs under torch.inference_mode()
+        with torch.inference_mode(False), torch.no_grad():
+            self._pack(net, device, precision)
+
+    def _pack(self, net: "UNet", device, precision: str):
         self.device, self.precision = device, precision
         wdt = torch.float32 if precision == "fp32" else torch.bfloat16
         self.wcode = F32_T if precision == "fp32" else BF16_T
@@ -167,6 +188,17 @@ class StepProgram:
     """One UNet forward for fixed (B, H, W, n_timesteps, cond batch, Sk) as a flat launch list."""
 
     def __init__(self, net: "UNet", pw: PackedWeights, B, H, W, nt, Bc, Sk, b_src=None):
+        if Bc not in (1, B):
+            # anything else would silently broadcast the first context rows to every sample (the reference fails in SDPA)
+            raise RuntimeError(f"context batch {Bc} neither matches nor broadcasts to the UNet batch {B}")
+        if nt not in (1, B):
+            raise RuntimeError(f"timestep count {nt} neither matches nor broadcasts to the UNet batch {B}")
+        # buffers are ordinary tensors (a plan built under torch.inference_mode() must stay writable afterwards) and every
+        # launch / allocation happens with the plan's device current (handles cache per-device state)
+        with torch.inference_mode(False), torch.no_grad(), torch.cuda.device(pw.device):
+            self._plan(net, pw, B, H, W, nt, Bc, Sk, b_src)
+
+    def _plan(self, net, pw, B, H, W, nt, Bc, Sk, b_src):
         self.net, self.pw = net, pw
         self.b_src = B if b_src is None else b_src     # latent rows actually stored: B == 2*b_src folds latent.repeat(2,...)
         self.B, self.H, self.W, self.nt, self.Bc, self.Sk = B, H, W, nt, Bc, Sk
@@ -282,34 +314,57 @@ class StepProgram:
         _lib.check(rc)
         return True
 
-    # ---- plan-time autotuning of the GEMM tiling -----------------------------------------------
+    # ---- GEMM tilings: committed measurements (read-only) + optional plan-time measurement -----------------
+    # SDB200_TC_AUTOTUNE = 0: the library's cost model only
+    #                      1: (default) tilings measured on B200 and COMMITTED with the package (tune_cache.json, never written
+    #                         at run time) for the benchmark configurations; the deterministic cost model on a miss
+    #                      2: additionally MEASURE shapes that miss (cold weights, warm activations) and merge them, under a
+    #                         file lock, into the per-user cache SDB200_TC_TUNE_FILE (default ~/.cache/sdb200/tune_cache.json).
+    # A measured tiling changes block_n / split-K and therefore the fp32 summation order: results of two machines with
+    # different user caches agree to rounding, not bit for bit; modes 0/1 are reproducible everywhere.
     _tune_cache: Dict[str, tuple] = {}
-    _tune_file = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tune_cache.json")
+    _tune_shipped = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tune_cache.json")
     _tune_loaded = False
+
+    @staticmethod
+    def _tune_user_file():
+        return os.environ.get("SDB200_TC_TUNE_FILE") or os.path.join(os.path.expanduser("~"), ".cache", "sdb200", "tune_cache.json")
 
     @classmethod
     def _tune_load(cls):
-        """Tilings measured earlier on this GPU model (committed with the package for the benchmark configurations; extended
-        in place when a new shape is met; SDB200_TC_TUNE_FILE overrides the location)."""
         if cls._tune_loaded:
             return
         cls._tune_loaded = True
-        cls._tune_file = os.environ.get("SDB200_TC_TUNE_FILE", cls._tune_file)
-        try:
-            with open(cls._tune_file) as f:
-                cls._tune_cache.update({k: tuple(v) for k, v in json.load(f).items()})
-        except (OSError, ValueError):
-            pass
+        for path in (cls._tune_shipped, cls._tune_user_file()):     # the user's own measurements win
+            try:
+                with open(path) as f:
+                    cls._tune_cache.update({k: tuple(v) for k, v in json.load(f).items()})
+            except (OSError, ValueError):
+                pass
 
     @classmethod
-    def _tune_save(cls):
+    def _tune_save(cls, key, value):
+        """Merge ONE new measurement into the per-user cache (never the package directory); concurrent ranks serialise on a
+        lock file and re-read before writing, so nobody's entries are lost."""
+        path = cls._tune_user_file()
         try:
-            tmp = cls._tune_file + f".{os.getpid()}.tmp"
-            with open(tmp, "w") as f:
-                json.dump({k: list(v) for k, v in sorted(cls._tune_cache.items())}, f, indent=0)
-            os.replace(tmp, cls._tune_file)
+            import fcntl
+            os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+            with open(path + ".lock", "w") as lk:
+                fcntl.flock(lk, fcntl.LOCK_EX)
+                cur = {}
+                try:
+                    with open(path) as f:
+                        cur = json.load(f)
+                except (OSError, ValueError):
+                    pass
+                cur[key] = list(value)
+                tmp = path + f".{os.getpid()}.tmp"
+                with open(tmp, "w") as f:
+                    json.dump(dict(sorted(cur.items())), f, indent=0)
+                os.replace(tmp, path)
         except OSError:
-            pass                                             # read-only install: keep the in-process cache only
+            pass                                             # unwritable home: keep the in-process cache only
 
     def _autotune(self, d, a_tensor, cs):
         """Time the candidate (block_n, split-K) tilings of this layer shape on the device, in the state the step sees them:
@@ -321,6 +376,8 @@ class StepProgram:
         hit = StepProgram._tune_cache.get(key)
         if hit is not None:
             return tuple(hit) if len(hit) == 3 else (hit[0], hit[1], d.two_cta)
+        if self.net.tc_autotune < 2:
+            return (0, 0, d.two_cta)                           # miss: deterministic cost model, no measurement, no file written
         lib = self.lib
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         if not hasattr(self, "_tune_flush"):
@@ -383,8 +440,8 @@ class StepProgram:
         if auto_t is not None and best_t > 0.96 * auto_t:
             best = (0, 0, 0)
         StepProgram._tune_cache[key] = best
-        StepProgram._tune_save()
-        if self.net.tc_autotune > 1:
+        StepProgram._tune_save(key, best)
+        if self.net.tc_autotune > 2:
             print(f"autotune B{d.B} {d.H}x{d.W} C{d.C[0]} k{d.ksize[0]} N{d.N}: model {auto_t * 1e3 if auto_t else -1:.1f} us -> "
                   f"{best} {best_t * 1e3:.1f} us", flush=True)
         return best
@@ -705,11 +762,12 @@ class StepProgram:
 
     # ---- execution ----------------------------------------------------------------------
     def launch(self, ops):
-        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        for fn, args in ops:
-            rc = fn(*args, stream)
-            if rc != 0:
-                _lib.check(rc)
+        with torch.cuda.device(self.device):                    # the library keys its per-device state on the CURRENT device
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            for fn, args in ops:
+                rc = fn(*args, stream)
+                if rc != 0:
+                    _lib.check(rc)
 
 
 # ======================================================================================
@@ -744,7 +802,7 @@ class UNet(nn.Module):
         self.tc_block_n = int(os.environ.get("SDB200_TC_BLOCK_N", "0"))      # 0 = auto; tuning / test overrides
         self.tc_splits = int(os.environ.get("SDB200_TC_SPLITS", "0"))
         self.tc_tune_pairs = int(os.environ.get("SDB200_TC_TUNE_PAIRS", "0"))   # also try cta_group::2 pairs when measuring tilings
-        self.tc_autotune = int(os.environ.get("SDB200_TC_AUTOTUNE", "1"))     # 1: measure tilings at plan time; 2: and print them
+        self.tc_autotune = int(os.environ.get("SDB200_TC_AUTOTUNE", "1"))     # 0 model | 1 committed cache | 2 measure misses | 3 and print
         self.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention for head_dim 40 / 64
         self.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
         # sums: statistics from per-channel sums reduced in the producing GEMM's epilogue (bf16 program; fastest measured) |
@@ -877,22 +935,23 @@ class _Runner:
         p = self.prog
         p.x_in.copy_(x, non_blocking=True)
         p.t_in.copy_(timestep.to(torch.int64), non_blocking=True)
-        if cond is not self._cond_ref or cond._version != self._cond_version:
+        if not same_context(cond, self._cond_ref, self._cond_version):
             p.cond_in.copy_(cond, non_blocking=True)
             p.launch(p.ctx_ops)                       # cross-attention K/V: once per context, not per step
-            self._cond_ref, self._cond_version = cond, cond._version
+            self._cond_ref, self._cond_version = cond, tensor_version(cond)
         self.calls += 1
-        if not self.use_graph:
-            p.launch(p.ops)
-        elif self.graph is None:
-            if self.calls == 1:
-                p.launch(p.ops)                       # eager warm-up (loads modules, sets func attributes)
+        with torch.cuda.device(p.device):
+            if not self.use_graph:
+                p.launch(p.ops)
+            elif self.graph is None:
+                if self.calls == 1:
+                    p.launch(p.ops)                       # eager warm-up (loads modules, sets func attributes)
+                else:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        p.launch(p.ops)
+                    self.graph = g
+                    g.replay()
             else:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    p.launch(p.ops)
-                self.graph = g
-                g.replay()
-        else:
-            self.graph.replay()
+                self.graph.replay()
         return p.out.clone()

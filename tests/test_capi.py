@@ -70,17 +70,41 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 
 def test_tune_cache_roundtrip(tmp_path, monkeypatch):
-    """Measured GEMM tilings persist as JSON keyed by GPU model + layer shape; 2-element entries of older files still load."""
+    """Measured GEMM tilings persist as JSON keyed by GPU model + layer shape; 2-element entries of older files still load.
+    New measurements are MERGED into the per-user file (never the package's committed cache), keeping other writers' entries."""
+    import hashlib
     import json
     from stable_diffusion_pytorch_b200.unet import StepProgram
-    f = tmp_path / "tune.json"
+    f = tmp_path / "user" / "tune.json"
+    f.parent.mkdir()
     f.write_text(json.dumps({"NVIDIA B200|2|64|64|320|1|320|3|0|0|0|0|1|1": [160, 1], "NVIDIA B200|1|1|8192|960|1|320|1|0|0|1|0|0|0": [128, 3, 0]}))
+    shipped = hashlib.sha1(open(StepProgram._tune_shipped, "rb").read()).hexdigest()
     monkeypatch.setenv("SDB200_TC_TUNE_FILE", str(f))
     monkeypatch.setattr(StepProgram, "_tune_loaded", False)
     monkeypatch.setattr(StepProgram, "_tune_cache", {})
-    monkeypatch.setattr(StepProgram, "_tune_file", str(f))
     StepProgram._tune_load()
-    assert StepProgram._tune_cache["NVIDIA B200|2|64|64|320|1|320|3|0|0|0|0|1|1"] == (160, 1)
-    StepProgram._tune_cache["k"] = (64, 2, 0)
-    StepProgram._tune_save()
-    assert json.loads(f.read_text())["k"] == [64, 2, 0]
+    assert StepProgram._tune_cache["NVIDIA B200|2|64|64|320|1|320|3|0|0|0|0|1|1"] == (160, 1)      # the user file wins over the shipped one
+    # another process added an entry meanwhile: the merge keeps it
+    cur = json.loads(f.read_text())
+    cur["other-rank"] = [32, 4, 0]
+    f.write_text(json.dumps(cur))
+    StepProgram._tune_save("k", (64, 2, 0))
+    after = json.loads(f.read_text())
+    assert after["k"] == [64, 2, 0] and after["other-rank"] == [32, 4, 0]
+    assert hashlib.sha1(open(StepProgram._tune_shipped, "rb").read()).hexdigest() == shipped       # package file untouched
+
+
+def test_context_version_helpers():
+    """inference_mode tensors have no version counter (reference inpaint runs under it, models/diffusion.py:328): the context
+    cache must treat them as changed instead of raising."""
+    import torch
+    from stable_diffusion_pytorch_b200.unet import same_context, tensor_version
+    a = torch.zeros(3)
+    v = tensor_version(a)
+    assert same_context(a, a, v)
+    a.add_(1)
+    assert not same_context(a, a, v)
+    with torch.inference_mode():
+        b = torch.zeros(3)
+    assert tensor_version(b) is None
+    assert not same_context(b, b, None)
