@@ -59,6 +59,23 @@ struct alignas(64) TcParams {
     // partials into 53-bit accumulators is exact for all practical magnitudes, so the result does not depend on tile order.
     double2* cstat_out;
     unsigned long long* dbg;     // optional [8] %globaltimer stamps of CTA (0,0,0) (tools/prof_gemm.py --stamps)
+    // ---- split-K with the reduction INSIDE this kernel (fixup): every split CTA stores its raw partial plane (tmPart), bumps the
+    // tile's arrival counter and -- if it owns output chunks (chunk c belongs to split c % splits) -- waits until all splits of the
+    // tile have arrived, sums the planes in split order (deterministic) and runs the ordinary direct epilogue on the sum.
+    // All CTAs of the grid are co-resident (checked at plan time, launched cooperatively), so the wait cannot deadlock.
+    CUtensorMap tmPart;
+    int fixup, part_tma;
+    unsigned int* tile_cnt;      // [tiles] arrivals ; [1024 + tiles] finished waiters (self-resetting)
+    // ---- second output: bf16 copy of the fp32 NHWC output (A operand of the next GEMM: LayerNorm folded into that GEMM, conv gathers)
+    CUtensorMap tmOut2;
+    int out2, out2_off;          // out2_off: byte offset of the bf16 chunk inside a staging buffer
+    // ---- per-row statistics of the fp32 output for a LayerNorm folded into the consumer: row_stats [M][N/32] (sum, sum of squares)
+    // of each 32-column chunk, written (not accumulated) by the thread that owns the row
+    float2* row_stats;
+    // ---- LayerNorm folded into THIS GEMM: A holds the raw (bf16) rows x, W holds gamma-scaled weights, and
+    //   out = rstd[m] * (acc[m][n] - mean[m] * ln_colsum[n]) + bias'[n]      (bias' = bias + W beta, packed by the host)
+    // mean / rstd come from ln_stats [M][ln_parts] (the producer's row_stats), ln_colsum[n] = sum_k W'[n][k].
+    const float2* ln_stats; const float* ln_colsum; int ln_parts; float ln_eps, ln_inv_c;
 };
 
 __device__ __forceinline__ void stamp(const TcParams& p, int slot) {
@@ -217,6 +234,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     // [ADD_ROWS][BN]: bias + time-bias of the tile's samples (16-byte aligned: read as float4)
     float* s_add = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
     float2* s_stat = reinterpret_cast<float2*>(s_add + ADD_ROWS * BN);        // [2][4][32] column partials of the row quarters
+    float* s_lns = reinterpret_cast<float*>(s_stat + 2 * 4 * 32);             // [BN] column sums of the gamma-scaled weights (folded LayerNorm)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) stamp(p, 0);
@@ -242,6 +260,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         if (p.nseg > 1) { ptx::prefetch_tmap(&p.tmA[1]); ptx::prefetch_tmap(&p.tmB[1]); }
         if (p.epi_tma) ptx::prefetch_tmap(&p.tmOut);
         if (p.epi_res) ptx::prefetch_tmap(&p.tmRes);
+        if (p.part_tma) ptx::prefetch_tmap(&p.tmPart);
+        if (p.out2) ptx::prefetch_tmap(&p.tmOut2);
     }
     if (warp == 1) {
         if (TWO) { ptx::tmem_alloc2(tmem_slot, TMEM_COLS); ptx::tmem_relinquish2(); }
@@ -315,19 +335,24 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         const bool valid = r < p.rows && ox < p.W && oy < p.H && b < p.B;
         const long long grow = ((long long)b * p.H + oy) * p.W + ox;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const bool epi_direct = p.epi_tma && p.splits == 1;    // TMA epilogue with the full bias/residual/activation
+        const bool split = p.splits > 1;
+        const bool fix = split && p.fixup;                     // split-K reduced inside this kernel (see TcParams)
+        const bool epi_direct = p.epi_tma && (!split || fix);  // this CTA runs the full bias/residual/activation epilogue on (some) chunks
+        // output chunks this CTA finishes: all of them (no split-K), or chunk c = z, z + splits, ... of the summed tile (fixup)
+        const int c_first = fix ? (int)blockIdx.z : 0, c_step = fix ? p.splits : 1;
+        const int n_my = !epi_direct ? 0 : (c_first < NCH ? (NCH - c_first + c_step - 1) / c_step : 0);
 
-        // residual chunks 0 and 1 start travelling now (dedicated buffers: the pipeline stages are still in use)
+        // residual chunks of my first two output chunks start travelling now (dedicated buffers: the pipeline stages are still in use)
         if (p.epi_res && et == 0) {
-#pragma unroll
-            for (int c = 0; c < (NCH < 2 ? NCH : 2); ++c) {
-                ptx::mbar_expect_tx(&res_full[c], (uint32_t)p.rows * 128u);
-                ptx::tma_load_4d(sRes + c * RES_BUF_BYTES, &p.tmRes, &res_full[c], n0 + c * 32, w0, h0, b0);
+#pragma unroll 1
+            for (int i = 0; i < (n_my < 2 ? n_my : 2); ++i) {
+                ptx::mbar_expect_tx(&res_full[i], (uint32_t)p.rows * 128u);
+                ptx::tma_load_4d(sRes + i * RES_BUF_BYTES, &p.tmRes, &res_full[i], n0 + (c_first + i * c_step) * 32, w0, h0, b0);
             }
         }
         // While the main loop runs, stage the additive epilogue terms of this tile in shared memory:
         // s_add[tb][j] = bias[n0+j] + tbias[b0+tb][n0+j]  (one row per sample the tile touches, <= ADD_ROWS)
-        const bool staged = epi_direct || (p.splits == 1 && p.TB <= ADD_ROWS && (p.bias || p.tbias));
+        const bool staged = (epi_direct && n_my > 0) || (!split && p.TB <= ADD_ROWS && (p.bias || p.tbias));
         if (staged) {
             for (int i = et; i < p.TB * BN; i += 128) {
                 const int tbi = i / BN, j = i - tbi * BN;
@@ -338,125 +363,244 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 }
                 s_add[i] = x;
             }
+            if (p.ln_colsum)
+                for (int j = et; j < BN; j += 128) s_lns[j] = n0 + j < p.N ? __ldg(p.ln_colsum + n0 + j) : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        // folded LayerNorm: mean / rstd of this thread's A row from the producer's per-chunk (sum, sum of squares) partials
+        float ln_rstd = 1.f, ln_nm = 0.f;                       // out = acc * rstd + (-mean * rstd) * colsum[n] + bias'[n]
+        if (p.ln_stats && valid && n_my > 0) {
+            const float2* rs = p.ln_stats + (size_t)grow * p.ln_parts;
+            double sm = 0.0, sq = 0.0;
+            for (int i = 0; i < p.ln_parts; ++i) { const float2 t2 = __ldcg(rs + i); sm += (double)t2.x; sq += (double)t2.y; }
+            const double mean = sm * (double)p.ln_inv_c;
+            double var = sq * (double)p.ln_inv_c - mean * mean;
+            if (var < 0.0) var = 0.0;
+            ln_rstd = (float)(1.0 / sqrt(var + (double)p.ln_eps));
+            ln_nm = -(float)mean * ln_rstd;
         }
         const bool fast = !p.out_nchw && (n0 + BN <= p.N);               // full tile of an NHWC output: the common case
 
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
         if (threadIdx.x == 64) stamp(p, 4);
-        if (p.epi_tma) {
+        if (p.epi_tma || p.part_tma) {
             // ---- TMA epilogue: registers -> swizzled smem chunk -> one tensor store per 32 accumulator columns.
             // The chunk buffers alias the pipeline stages (idle once the accumulator is complete).
-            const int rowbytes = p.epi_rowbytes;
-            const uint32_t swz = ((uint32_t)(r * rowbytes) >> 7) & (uint32_t)p.epi_swz;
             const bool in_box = r < p.rows;
-            const float* my_add = s_add + (in_box ? tb_i : 0) * BN;
-            // statistics bookkeeping (cstat_out): rows of this tile that exist, and the fold of the four row-quarter partials
-            const bool do_stats = p.cstat_out && epi_direct;       // split-K: the reduce pass owns the statistics
-            const int stat_rows = p.TB > 1 ? p.rows : p.TW * min(p.TH, p.H - h0);
-            auto cstat_flush = [&](int cc) {
-                const int rps = p.TW * p.TH;                          // tile rows per sample
-                const int smp = et >> 5;                              // sample within the tile handled by this warp
-                if (smp < p.TB && b0 + smp < p.B) {
-                    const int p_lo = p.TB > 1 ? smp * (rps >> 5) : 0, p_n = p.TB > 1 ? (rps >> 5) : 4;
-                    double sum = 0.0, sq = 0.0;
-                    for (int i = 0; i < p_n; ++i) {
-                        const float2 v2 = s_stat[((cc & 1) * 4 + p_lo + i) * 32 + lane];
-                        sum += (double)v2.x; sq += (double)v2.y;
-                    }
-                    double* dst = reinterpret_cast<double*>(p.cstat_out + (size_t)(b0 + smp) * p.N + n0 + cc * 32 + lane);
-                    atomicAdd(dst, sum);
-                    atomicAdd(dst + 1, sq);
-                }
-            };
-            const bool glu = p.geglu && epi_direct;                 // split-K partials stay raw fp32: GEGLU runs in the reduce kernel
-            const int ocol0 = glu ? (n0 >> 1) : n0;
+            uint32_t gk = 0;                                   // chunks staged so far (ring position over both phases)
+            if (split) {
+                // ---- phase A: the raw fp32 partial of every chunk -> plane blockIdx.z of the workspace
+                const uint32_t swz_p = (uint32_t)r & 7u;
 #pragma unroll 1
-            for (int c = 0; c < NCH; ++c) {
-                uint32_t u[32];
-                ptx::tmem_ld32(taddr + c * 32, u);
-                uint8_t* ob = smem + (c % EPI_BUFS) * p.epi_buf_stride + r * rowbytes;
-                ptx::tmem_ld_wait();
-                float v[32];
+                for (int c = 0; c < NCH; ++c, ++gk) {
+                    uint32_t u[32];
+                    ptx::tmem_ld32(taddr + c * 32, u);
+                    uint8_t* ob = smem + (gk % EPI_BUFS) * p.epi_buf_stride + r * 128;
+                    ptx::tmem_ld_wait();
+                    if (in_box) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
-                if (epi_direct) {
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4*>(ob + ((j ^ swz_p) << 4)) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+                    }
+                    ptx::fence_proxy_async();
+                    if (et == 0) ptx::bulk_wait_read<1>();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et == 0) {
+                        ptx::tma_store_5d(&p.tmPart, smem + (gk % EPI_BUFS) * p.epi_buf_stride, n0 + c * 32, w0, h0, b0, (int)blockIdx.z);
+                        ptx::bulk_commit();
+                    }
+                }
+                if (fix) {
+                    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+                    if (et == 0) {
+                        ptx::bulk_wait_done<0>();               // the partial plane of this CTA is in global memory ...
+                        ptx::fence_proxy_async_global();
+                        __threadfence();
+                        ptx::red_release_gpu_add(p.tile_cnt + tile, 1u);     // ... before the arrival becomes visible
+                        if (n_my > 0) {
+                            unsigned spins = 0;
+                            while (ptx::ld_acquire_gpu(p.tile_cnt + tile) < (unsigned)p.splits) {
+                                __nanosleep(64);
+                                if (++spins > (1u << 24)) break;   // ~1 s: never hang the GPU on a logic error (the output is then wrong, not late)
+                            }
+                            // the last of the waiting CTAs re-arms the counters for the next launch (stream order separates launches)
+                            const unsigned waiters = (unsigned)(p.splits < NCH ? p.splits : NCH);
+                            if (atomicAdd(p.tile_cnt + 1024 + tile, 1u) == waiters - 1) {
+                                atomicExch(p.tile_cnt + tile, 0u);
+                                atomicExch(p.tile_cnt + 1024 + tile, 0u);
+                            }
+                        }
+                    }
+                    if (n_my > 0) {
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        __threadfence();
+                        ptx::fence_proxy_async_global();
+                    }
+                } else if (et == 0) {
+                    ptx::bulk_wait_read<0>();                   // shared memory must outlive the last store's read
+                }
+            }
+            if (n_my > 0) {
+                const int rowbytes = p.epi_rowbytes;
+                const uint32_t swz = ((uint32_t)(r * rowbytes) >> 7) & (uint32_t)p.epi_swz;
+                const uint32_t swz2 = ((uint32_t)(r * 64) >> 7) & 3u;        // bf16 copy: 64-byte rows, SWIZZLE_64B
+                const float* my_add = s_add + (in_box ? tb_i : 0) * BN;
+                // statistics bookkeeping (cstat_out): rows of this tile that exist, and the fold of the four row-quarter partials
+                const bool do_stats = p.cstat_out != nullptr;
+                const int stat_rows = p.TB > 1 ? p.rows : p.TW * min(p.TH, p.H - h0);
+                auto cstat_flush = [&](int i_prev, int cc) {             // i_prev: my-chunk index (s_stat slot), cc: absolute chunk
+                    const int rps = p.TW * p.TH;                          // tile rows per sample
+                    const int smp = et >> 5;                              // sample within the tile handled by this warp
+                    if (smp < p.TB && b0 + smp < p.B) {
+                        const int p_lo = p.TB > 1 ? smp * (rps >> 5) : 0, p_n = p.TB > 1 ? (rps >> 5) : 4;
+                        double sum = 0.0, sq = 0.0;
+                        for (int i = 0; i < p_n; ++i) {
+                            const float2 v2 = s_stat[((i_prev & 1) * 4 + p_lo + i) * 32 + lane];
+                            sum += (double)v2.x; sq += (double)v2.y;
+                        }
+                        double* dst = reinterpret_cast<double*>(p.cstat_out + (size_t)(b0 + smp) * p.N + n0 + cc * 32 + lane);
+                        atomicAdd(dst, sum);
+                        atomicAdd(dst + 1, sq);
+                    }
+                };
+                const bool glu = p.geglu != 0;
+                const int ocol0 = glu ? (n0 >> 1) : n0;
+                const size_t plane4 = (size_t)p.M * (size_t)p.N / 4;
+#pragma unroll 1
+                for (int i = 0; i < n_my; ++i, ++gk) {
+                    const int c = c_first + i * c_step;
+                    float v[32];
+                    if (fix) {
+                        // sum of the splits' partial planes, in split order (deterministic); L2 reads, two planes in flight
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                        if (valid) {
+                            const float4* s4 = reinterpret_cast<const float4*>(p.partial + (size_t)grow * p.N + n0 + c * 32);
+                            int z = 0;
+                            for (; z + 2 <= p.splits; z += 2) {
+                                float4 a[8], bq[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) { a[j] = __ldcg(s4 + (size_t)z * plane4 + j); bq[j] = __ldcg(s4 + (size_t)(z + 1) * plane4 + j); }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    v[4 * j] = (v[4 * j] + a[j].x) + bq[j].x; v[4 * j + 1] = (v[4 * j + 1] + a[j].y) + bq[j].y;
+                                    v[4 * j + 2] = (v[4 * j + 2] + a[j].z) + bq[j].z; v[4 * j + 3] = (v[4 * j + 3] + a[j].w) + bq[j].w;
+                                }
+                            }
+                            if (z < p.splits) {
+                                float4 a[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) a[j] = __ldcg(s4 + (size_t)z * plane4 + j);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) { v[4 * j] += a[j].x; v[4 * j + 1] += a[j].y; v[4 * j + 2] += a[j].z; v[4 * j + 3] += a[j].w; }
+                            }
+                        }
+                    } else {
+                        uint32_t u[32];
+                        ptx::tmem_ld32(taddr + c * 32, u);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                    }
+                    uint8_t* obuf = smem + (gk % EPI_BUFS) * p.epi_buf_stride;
+                    uint8_t* ob = obuf + r * rowbytes;
+                    if (p.ln_stats) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 cs4 = *reinterpret_cast<const float4*>(s_lns + c * 32 + j);   // warp-wide broadcast
+                            v[j] = fmaf(v[j], ln_rstd, ln_nm * cs4.x); v[j + 1] = fmaf(v[j + 1], ln_rstd, ln_nm * cs4.y);
+                            v[j + 2] = fmaf(v[j + 2], ln_rstd, ln_nm * cs4.z); v[j + 3] = fmaf(v[j + 3], ln_rstd, ln_nm * cs4.w);
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 a = *reinterpret_cast<const float4*>(my_add + c * 32 + j);     // warp-wide broadcast
                         v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
                     }
                     if (p.epi_res) {
-                        ptx::mbar_wait(&res_full[c & 1], (uint32_t)(c >> 1) & 1u);
-                        const uint8_t* rb = sRes + (c & 1) * RES_BUF_BYTES + r * 128;
+                        ptx::mbar_wait(&res_full[i & 1], (uint32_t)(i >> 1) & 1u);
+                        const uint8_t* rb = sRes + (i & 1) * RES_BUF_BYTES + r * 128;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 a = *reinterpret_cast<const float4*>(rb + ((j ^ (r & 7)) << 4));
                             v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
                         }
                     }
-                }
-                if (in_box) {
-                    if (glu) {                         // (value, gate) column pairs -> 16 bf16 outputs (models/activation_fn.py:17-20)
-                        float o[16];
+                    if (in_box) {
+                        if (glu) {                         // (value, gate) column pairs -> 16 bf16 outputs (models/activation_fn.py:17-20)
+                            float o[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf_bf16out(v[2 * j + 1]);
+                            for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf_bf16out(v[2 * j + 1]);
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob + ((j ^ swz) << 4)), o + 8 * j);
-                    } else if (rowbytes == 64) {       // bf16 output
+                            for (int j = 0; j < 2; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob + ((j ^ swz) << 4)), o + 8 * j);
+                        } else if (rowbytes == 64) {       // bf16 output
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob + ((j ^ swz) << 4)), v + 8 * j);
-                    } else {                           // fp32 output / split-K partial
+                            for (int j = 0; j < 4; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob + ((j ^ swz) << 4)), v + 8 * j);
+                        } else {                           // fp32 output
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4*>(ob + ((j ^ swz) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
-                }
-                ptx::fence_proxy_async();              // this thread's smem writes -> visible to the TMA engine
-                // the buffer the NEXT chunk writes was read by the store issued two chunks ago
-                if (et == 0) ptx::bulk_wait_read<1>();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) {
-                    ptx::tma_store_5d(&p.tmOut, smem + (c % EPI_BUFS) * p.epi_buf_stride, ocol0 + c * p.epi_cols, w0, h0, b0, (int)blockIdx.z);
-                    ptx::bulk_commit();
-                    if (p.epi_res && c + 2 < NCH) {    // every thread has consumed residual chunk c: refill its buffer
-                        ptx::mbar_expect_tx(&res_full[c & 1], (uint32_t)p.rows * 128u);
-                        ptx::tma_load_4d(sRes + (c & 1) * RES_BUF_BYTES, &p.tmRes, &res_full[c & 1], n0 + (c + 2) * 32, w0, h0, b0);
-                    }
-                }
-                if (do_stats) {
-                    // GroupNorm statistics of the consumer, for free: column sums of the finished fp32 chunk (still in smem)
-                    if (c > 0) cstat_flush(c - 1);
-                    const uint8_t* cb = smem + (c % EPI_BUFS) * p.epi_buf_stride + ((lane & 3) << 2);
-                    const int r_lo = (et >> 5) * 32, r_n = min(32, stat_rows - r_lo), jq = lane >> 2;
-                    float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (r_n == 32) {                   // full quarter: all loads of a batch in flight, no branches
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4*>(ob + ((j ^ swz) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            if (p.out2) {                  // bf16 copy of the same chunk (second tensor store)
+                                uint8_t* ob2 = obuf + p.out2_off + r * 64;
 #pragma unroll
-                        for (int i0 = 0; i0 < 32; i0 += 8) {
-                            float x[8];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const int rr = r_lo + i0 + k;           // r_lo is a multiple of 32: rr & 7 == k
-                                x[k] = *reinterpret_cast<const float*>(cb + rr * 128 + ((jq ^ k) << 4));
+                                for (int j = 0; j < 4; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob2 + ((j ^ swz2) << 4)), v + 8 * j);
                             }
+                            if (p.row_stats && valid) {    // LayerNorm statistics of the consumer: this row's (sum, sum of squares) over the chunk
+                                float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) { sa[k & 3] += x[k]; qa[k & 3] = fmaf(x[k], x[k], qa[k & 3]); }
-                        }
-                    } else {
-                        for (int i = 0; i < r_n; ++i) {
-                            const int rr = r_lo + i;
-                            const float x = *reinterpret_cast<const float*>(cb + rr * 128 + ((jq ^ (rr & 7)) << 4));
-                            sa[0] += x; qa[0] = fmaf(x, x, qa[0]);
+                                for (int j = 0; j < 32; ++j) { sa[j & 3] += v[j]; qa[j & 3] = fmaf(v[j], v[j], qa[j & 3]); }
+                                p.row_stats[(size_t)grow * (size_t)(p.N >> 5) + (size_t)((n0 >> 5) + c)] =
+                                    make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
+                            }
                         }
                     }
-                    s_stat[((c & 1) * 4 + (et >> 5)) * 32 + lane] = make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
+                    ptx::fence_proxy_async();              // this thread's smem writes -> visible to the TMA engine
+                    // the buffer the NEXT chunk writes was read by the store issued two chunks ago
+                    if (et == 0) ptx::bulk_wait_read<1>();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et == 0) {
+                        ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
+                        if (p.out2) ptx::tma_store_5d(&p.tmOut2, obuf + p.out2_off, n0 + c * 32, w0, h0, b0, 0);
+                        ptx::bulk_commit();
+                        if (p.epi_res && i + 2 < n_my) {   // every thread has consumed residual chunk i: refill its buffer
+                            ptx::mbar_expect_tx(&res_full[i & 1], (uint32_t)p.rows * 128u);
+                            ptx::tma_load_4d(sRes + (i & 1) * RES_BUF_BYTES, &p.tmRes, &res_full[i & 1], n0 + (c + 2 * c_step) * 32, w0, h0, b0);
+                        }
+                    }
+                    if (do_stats) {
+                        // GroupNorm statistics of the consumer, for free: column sums of the finished fp32 chunk (still in smem)
+                        if (i > 0) cstat_flush(i - 1, c - c_step);
+                        const uint8_t* cb = obuf + ((lane & 3) << 2);
+                        const int r_lo = (et >> 5) * 32, r_n = min(32, stat_rows - r_lo), jq = lane >> 2;
+                        float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (r_n == 32) {                   // full quarter: all loads of a batch in flight, no branches
+#pragma unroll
+                            for (int i0 = 0; i0 < 32; i0 += 8) {
+                                float x[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const int rr = r_lo + i0 + k;           // r_lo is a multiple of 32: rr & 7 == k
+                                    x[k] = *reinterpret_cast<const float*>(cb + rr * 128 + ((jq ^ k) << 4));
+                                }
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) { sa[k & 3] += x[k]; qa[k & 3] = fmaf(x[k], x[k], qa[k & 3]); }
+                            }
+                        } else {
+                            for (int ii = 0; ii < r_n; ++ii) {
+                                const int rr = r_lo + ii;
+                                const float x = *reinterpret_cast<const float*>(cb + rr * 128 + ((jq ^ (rr & 7)) << 4));
+                                sa[0] += x; qa[0] = fmaf(x, x, qa[0]);
+                            }
+                        }
+                        s_stat[((i & 1) * 4 + (et >> 5)) * 32 + lane] = make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
+                    }
                 }
-            }
-            if (et == 0) ptx::bulk_wait_read<0>();     // shared memory must outlive the last store's read
-            if (do_stats) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                cstat_flush(NCH - 1);
+                if (et == 0) ptx::bulk_wait_read<0>();     // shared memory must outlive the last store's read
+                if (do_stats) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    cstat_flush(n_my - 1, c_first + (n_my - 1) * c_step);
+                }
             }
         } else if (fast) {
             // ---- fallback 1: coalesced stores through a per-warp 32x32 transpose (4 rows x 128 B per instruction)
