@@ -184,11 +184,21 @@ typedef struct SdkTcGemmDesc {
     int splits;         /* 0 = auto split-K */
     int w_kmajor;       /* 0: weights [N][K] row-major; 1: k-block-major [K/64][N][64] (contiguous B stages) */
     int two_cta;        /* 0 = auto, 1 = never, 2 = always (when the number of m-tiles is even): tcgen05 cta_group::2 CTA pairs */
+    /* --- fusions around LayerNorm (unet.py:102-108,137-149); all optional (NULL / 0), fp32 NHWC outputs only for the first two --- */
+    void* out2;               /* bf16 copy [M][N] of the output, written by the same epilogue (raw A operand of the next GEMM) */
+    float* row_stats;         /* [M][N/32][2]: (sum, sum of squares) of every output row over each 32-column chunk = the LayerNorm
+                                 statistics of the consumer, written by the thread that owns the row (no extra pass over the tensor) */
+    const float* ln_stats;    /* LayerNorm FOLDED into this GEMM: `a` holds the raw rows x (bf16), `w` the gamma-scaled weights W' = W*gamma,
+                                 `bias` = bias + W beta; ln_stats = the producer's row_stats [M][ln_parts][2] (ln_parts*32 = row width C),
+                                 ln_colsum[n] = sum_k W'[n][k].  out = rstd[m]*(x W'^T - mean[m]*ln_colsum) + bias  ==  LN(x) W^T + bias */
+    const float* ln_colsum;
+    int ln_parts;
+    float ln_eps;
 } SdkTcGemmDesc;
 int sdk_tc_gemm_create(const SdkTcGemmDesc* desc, void** handle);
 int64_t sdk_tc_gemm_workspace_bytes(void* handle);
-int sdk_tc_gemm_set_workspace(void* handle, void* workspace);   /* zeroed once by the caller; shared across plans run on one stream */
-int sdk_tc_gemm_info(void* handle, int* out, int n);            /* block_n, splits, grid.x, grid.y, TW, TH, TB, k-blocks [, cta group size if n >= 9] */
+int sdk_tc_gemm_set_workspace(void* handle, void* workspace);   /* zeroed ONCE by the caller (it starts with the split-K tile counters, which the kernels re-arm); shared across plans run on one stream */
+int sdk_tc_gemm_info(void* handle, int* out, int n);            /* block_n, splits, grid.x, grid.y, TW, TH, TB, k-blocks [, cta group size, in-kernel split-K reduction, persistent if n >= 11] */
 int sdk_tc_gemm_launch(void* handle, void* stream);
 int sdk_tc_gemm_destroy(void* handle);
 /* Also ACCUMULATE the per-channel (sum, sum of squares) table chan_stats [B][N][2] (double; input of sdk_groupnorm_apply_cs) of

@@ -89,7 +89,8 @@ class TcGemmDesc(C.Structure):
     _fields_ = [("a", P * 2), ("w", P * 2), ("C", I32 * 2), ("ksize", I32 * 2), ("nseg", I32),
                 ("B", I32), ("H", I32), ("W", I32), ("N", I32),
                 ("bias", P), ("tbias", P), ("tb_stride", I64), ("residual", P), ("out", P),
-                ("out_dtype", I32), ("geglu", I32), ("out_nchw", I32), ("block_n", I32), ("splits", I32), ("w_kmajor", I32), ("two_cta", I32)]
+                ("out_dtype", I32), ("geglu", I32), ("out_nchw", I32), ("block_n", I32), ("splits", I32), ("w_kmajor", I32), ("two_cta", I32),
+                ("out2", P), ("row_stats", P), ("ln_stats", P), ("ln_colsum", P), ("ln_parts", I32), ("ln_eps", F32)]
 
 
 F32_T, BF16_T = 0, 1

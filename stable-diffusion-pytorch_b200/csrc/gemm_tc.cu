@@ -747,6 +747,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
     float* s_add = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
     float2* s_stat_all = reinterpret_cast<float2*>(s_add + 2 * ADD_ROWS * BN);  // s_add is double-buffered by tile parity; [2 groups][2][4][32]
+    float* s_lns = reinterpret_cast<float*>(s_stat_all + 2 * 2 * 4 * 32);       // [2][BN] column sums of the gamma-scaled weights (folded LayerNorm), by tile parity
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = p.N / BN;
@@ -762,6 +763,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
         if (p.nseg > 1) { ptx::prefetch_tmap(&p.tmA[1]); ptx::prefetch_tmap(&p.tmB[1]); }
         ptx::prefetch_tmap(&p.tmOut);
         if (p.epi_res) ptx::prefetch_tmap(&p.tmRes);
+        if (p.out2) ptx::prefetch_tmap(&p.tmOut2);
     }
     if (warp == 1) { ptx::tmem_alloc(tmem_slot, 2 * TMEM_COLS); ptx::tmem_relinquish(); }
     ptx::tc_fence_before();
@@ -836,9 +838,10 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
         const int r = q * 32 + lane;                    // tile row == TMEM lane
         const int et = (threadIdx.x - 64) & 127;        // 0..127 within the group
         const int et2 = threadIdx.x - 64;               // 0..255 over both groups
-        const int tb_i = r / (p.TW * p.TH);
+        const int tw_i = r % p.TW, th_i = (r / p.TW) % p.TH, tb_i = r / (p.TW * p.TH);
         const int rowbytes = p.epi_rowbytes;
         const uint32_t swz = ((uint32_t)(r * rowbytes) >> 7) & (uint32_t)p.epi_swz;
+        const uint32_t swz2 = ((uint32_t)(r * 64) >> 7) & 3u;            // bf16 copy: 64-byte rows, SWIZZLE_64B
         const bool in_box = r < p.rows;
         const bool glu = p.geglu != 0;
         const bool do_stats = p.cstat_out != nullptr;
@@ -862,6 +865,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
             // s_add[tb][j] = bias[n0+j] + tbias[b0+tb][n0+j], double-buffered by tile parity (the other group may still read the
             // previous tile's rows); the 256-thread barrier keeps the groups within one tile of each other
             float* s_add_t = s_add + (lt & 1) * ADD_ROWS * BN;
+            float* s_lns_t = s_lns + (lt & 1) * BN;
             for (int i = et2; i < p.TB * BN; i += 256) {
                 const int tbi = i / BN, j = i - tbi * BN;
                 float x = 0.f;
@@ -869,8 +873,25 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                 if (p.tbias && b0 + tbi < p.B) x += __ldg(p.tbias + (long long)(b0 + tbi) * p.tb_stride + n0 + j);
                 s_add_t[i] = x;
             }
+            if (p.ln_colsum)
+                for (int j = et2; j < BN; j += 256) s_lns_t[j] = __ldg(p.ln_colsum + n0 + j);
             asm volatile("bar.sync 3, 256;" ::: "memory");
             const float* my_add = s_add_t + (in_box ? tb_i : 0) * BN;
+            // output row of this thread (row statistics / folded LayerNorm need the global row index)
+            const int ox = w0 + tw_i, oy = h0 + th_i, bb = b0 + tb_i;
+            const bool valid = in_box && ox < p.W && oy < p.H && bb < p.B;
+            const long long grow = ((long long)bb * p.H + oy) * p.W + ox;
+            float ln_rstd = 1.f, ln_nm = 0.f;                    // out = acc * rstd + (-mean * rstd) * colsum[n] + bias'[n]
+            if (p.ln_stats && valid) {
+                const float2* rs = p.ln_stats + (size_t)grow * p.ln_parts;
+                double sm = 0.0, sq = 0.0;
+                for (int i = 0; i < p.ln_parts; ++i) { const float2 t2 = __ldcg(rs + i); sm += (double)t2.x; sq += (double)t2.y; }
+                const double mean = sm * (double)p.ln_inv_c;
+                double var = sq * (double)p.ln_inv_c - mean * mean;
+                if (var < 0.0) var = 0.0;
+                ln_rstd = (float)(1.0 / sqrt(var + (double)p.ln_eps));
+                ln_nm = -(float)mean * ln_rstd;
+            }
             const int stat_rows = p.TB > 1 ? p.rows : p.TW * min(p.TH, p.H - h0);
             auto cstat_flush = [&](int cc) {
                 const int rps = p.TW * p.TH;
@@ -904,6 +925,14 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
+                if (p.ln_stats) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 cs4 = *reinterpret_cast<const float4*>(s_lns_t + c * 32 + j);   // warp-wide broadcast
+                        v[j] = fmaf(v[j], ln_rstd, ln_nm * cs4.x); v[j + 1] = fmaf(v[j + 1], ln_rstd, ln_nm * cs4.y);
+                        v[j + 2] = fmaf(v[j + 2], ln_rstd, ln_nm * cs4.z); v[j + 3] = fmaf(v[j + 3], ln_rstd, ln_nm * cs4.w);
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 a = *reinterpret_cast<const float4*>(my_add + c * 32 + j);     // warp-wide broadcast
@@ -932,6 +961,18 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             *reinterpret_cast<float4*>(ob + ((j ^ swz) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        if (p.out2) {                      // bf16 copy of the same chunk (second tensor store)
+                            uint8_t* ob2 = obuf + p.out2_off + r * 64;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob2 + ((j ^ swz2) << 4)), v + 8 * j);
+                        }
+                        if (p.row_stats && valid) {        // LayerNorm statistics of the consumer: this row's (sum, sum of squares) over the chunk
+                            float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { sa[j & 3] += v[j]; qa[j & 3] = fmaf(v[j], v[j], qa[j & 3]); }
+                            p.row_stats[(size_t)grow * (size_t)(p.N >> 5) + (size_t)((n0 >> 5) + c)] =
+                                make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
+                        }
                     }
                 }
                 ptx::fence_proxy_async();
@@ -942,6 +983,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                 if (et == 0) {
                     if (last) ptx::mbar_arrive(&acc_empty[ab]);          // (2 arrivals: both groups) the MMA warp may overwrite this buffer
                     ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
+                    if (p.out2) ptx::tma_store_5d(&p.tmOut2, obuf + p.out2_off, n0 + c * 32, w0, h0, b0, 0);
                     ptx::bulk_commit();
                     if (p.epi_res && c + 2 < NCH) {
                         ptx::mbar_expect_tx(my_res_full, (uint32_t)p.rows * 128u);
@@ -1170,10 +1212,13 @@ struct TcGemm {
     bool co_resident, two_cta, persistent;
     dim3 grid;
     int64_t ws_bytes;
+    void* out2;                 // bf16 copy of the output (descriptor field), or null
 };
 
+constexpr int WS_HEADER_BYTES = 8192;               // workspace = [tile counters: 2 x 1024 u32][fp32 partial planes]
+
 // shared memory outside the pipeline stages: 1 KiB alignment slack, barriers + TMEM slot, staged bias rows, residual chunks
-int fixed_smem(int bn, bool res) { return 1024 + 256 + ADD_ROWS * bn * 4 + 2 * 4 * 32 * 8 + 32 + (res ? 2 * RES_BUF_BYTES : 0); }
+int fixed_smem(int bn, bool res) { return 1024 + 256 + ADD_ROWS * bn * 4 + 2 * 4 * 32 * 8 + bn * 4 + 32 + (res ? 2 * RES_BUF_BYTES : 0); }
 int stage_smem(int bn, bool two) { return A_STAGE_BYTES + (two ? bn / 2 : bn) * BK * 2; }
 
 template <int BN>
@@ -1195,10 +1240,20 @@ int launch_cfg(const TcGemm* g, cudaStream_t s) {
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         SDK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, TWO>, g->prm));
+    } else if (g->prm.fixup) {
+        // in-kernel split-K reduction: CTAs wait for their tile's siblings, so the whole grid must be co-resident -> cooperative launch
+        // (the driver rejects a grid that does not fit instead of letting it hang)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = g->grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = g->smem_bytes; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative;
+        at[0].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        SDK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, TWO>, g->prm));
     } else
     SDK_CUDA(sdk_launch(conv_gemm_tc_kernel<BN, TWO>, dim3(g->grid), dim3(TC_THREADS), (size_t)(g->smem_bytes), s, g->prm));
     SDK_LAUNCH_CHECK();
-    if (g->prm.splits > 1) {
+    if (g->prm.splits > 1 && !g->prm.fixup) {
         const long long items = g->prm.M * ((g->prm.N + 3) / 4);
         long long blocks = (items + 255) / 256, cap = (long long)sdk_num_sms() * 8;
         if (blocks > cap) blocks = cap;
@@ -1343,12 +1398,30 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     g->block_n = bn;
     g->grid = dim3(m_tiles, n_tiles, splits);
     g->two_cta = two;
-    g->ws_bytes = splits > 1 ? (int64_t)splits * p.M * d->N * 4 + 256 : 0;
-    // ---- epilogue route.  TMA (tensor store of swizzled 32-column chunks) needs full N tiles, NHWC output and - for the
-    // direct form - the bias rows staged in smem; split-K partial planes qualify too (map encoded in set_workspace).
+    g->ws_bytes = splits > 1 ? (int64_t)WS_HEADER_BYTES + (int64_t)splits * p.M * d->N * 4 + 256 : 0;
+    g->out2 = d->out2;
+    // ---- epilogue route.  TMA (tensor store of swizzled 32-column chunks) needs full N tiles, NHWC output and the bias rows
+    // staged in smem.  With split-K the raw partial planes leave through TMA as well (tmPart, encoded in set_workspace) and the
+    // final epilogue runs either inside this kernel (fixup, decided below once the CTA residency is known) or in the reduce kernel.
     const bool full_tiles = d->N % bn == 0 && !d->out_nchw;
-    if (full_tiles && splits == 1 && p.TB <= ADD_ROWS && !(d->geglu && (d->out_dtype != SDK_BF16 || d->residual)) &&
-        ((uintptr_t)d->out & 15) == 0 && ((uintptr_t)d->residual & 15) == 0) {
+    const bool direct_ok = full_tiles && p.TB <= ADD_ROWS && !(d->geglu && (d->out_dtype != SDK_BF16 || d->residual)) &&
+                           ((uintptr_t)d->out & 15) == 0 && ((uintptr_t)d->residual & 15) == 0;
+    const bool want_extras = d->out2 || d->row_stats || d->ln_stats;
+    if (d->out2 || d->row_stats) {
+        if (d->out_dtype != SDK_F32 || d->geglu || d->out_nchw || d->N % 32 != 0 || ((uintptr_t)d->out2 & 15) != 0) {
+            delete g;
+            return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: out2 / row_stats need an fp32 NHWC output with N %% 32 == 0");
+        }
+    }
+    if (d->ln_stats && !(d->ln_colsum && d->ln_parts > 0 && d->bias)) {
+        delete g;
+        return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_create: folded LayerNorm needs ln_colsum, ln_parts > 0 and the folded bias");
+    }
+    if (want_extras && !direct_ok) {
+        delete g;
+        return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: out2 / row_stats / folded LayerNorm need the direct TMA epilogue (N %% block_n == 0, <= %d samples per tile)", ADD_ROWS);
+    }
+    if (direct_ok) {
         const bool bf = d->out_dtype == SDK_BF16;
         p.epi_tma = 1;
         p.epi_cols = d->geglu ? 16 : 32;
@@ -1366,11 +1439,29 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
             rc = encode_map(&p.tmRes, d->residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 4, rdims, rbox, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
         }
+        if (rc == SDK_OK && d->out2) {
+            p.out2 = 1;
+            const uint64_t o2dims[5] = {(uint64_t)d->N, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B, 1};
+            const uint32_t o2box[5] = {32u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB, 1};
+            rc = encode_map(&p.tmOut2, d->out2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 5, o2dims, o2box, CU_TENSOR_MAP_SWIZZLE_64B,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE);
+        }
         if (rc != SDK_OK) { delete g; return rc; }
-    } else if (full_tiles && splits > 1) {
-        p.epi_tma = 1; p.epi_cols = 32; p.epi_rowbytes = 128; p.epi_swz = 7;      // tmOut: see sdk_tc_gemm_set_workspace
+        p.row_stats = reinterpret_cast<float2*>(d->row_stats);
+        if (d->ln_stats) {
+            p.ln_stats = reinterpret_cast<const float2*>(d->ln_stats); p.ln_colsum = d->ln_colsum; p.ln_parts = d->ln_parts;
+            p.ln_eps = d->ln_eps; p.ln_inv_c = 1.0f / (float)(d->ln_parts * 32);
+        }
     }
-    p.epi_buf_stride = ((p.rows * p.epi_rowbytes + 1023) / 1024) * 1024;
+    p.part_tma = (full_tiles && splits > 1) ? 1 : 0;
+    {
+        // staging buffer of one chunk: [main chunk: output rows (or 128-byte fp32 partial rows with split-K)][bf16 copy rows]
+        int main_bytes = p.rows * (splits > 1 ? 128 : (p.epi_tma ? p.epi_rowbytes : 0));
+        if (splits > 1 && p.epi_tma && p.rows * p.epi_rowbytes > main_bytes) main_bytes = p.rows * p.epi_rowbytes;
+        main_bytes = ((main_bytes + 1023) / 1024) * 1024;
+        p.out2_off = main_bytes;
+        p.epi_buf_stride = main_bytes + (p.out2 ? ((p.rows * 64 + 1023) / 1024) * 1024 : 0);
+    }
     // ---- pipeline depth (run-time): as many stages as fit, at most MAX_STAGES and not many more than the k-blocks of a CTA.
     // short K per CTA: the fixed prologue/epilogue cost dominates -> shallow pipeline so that 2 CTAs share an SM and
     // one CTA's epilogue overlaps the other's main loop
@@ -1383,7 +1474,7 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         const long long tiles = (long long)m_tiles * n_tiles;
         g->persistent = mode > 0 && !two && splits == 1 && p.epi_tma && (mode > 1 || tiles >= 2LL * sms);
         if (g->persistent) {
-            const int fixed_p = fixed_smem(bn, p.epi_res != 0) + PERS_EPI_BUFS * p.epi_buf_stride + ADD_ROWS * bn * 4 + 2 * 4 * 32 * 8;
+            const int fixed_p = fixed_smem(bn, p.epi_res != 0) + PERS_EPI_BUFS * p.epi_buf_stride + ADD_ROWS * bn * 4 + 2 * 4 * 32 * 8 + bn * 4;
             int st = (232448 - fixed_p) / stage_smem(bn, false);
             if (st > MAX_STAGES) st = MAX_STAGES;
             if (st < 3) g->persistent = false;
@@ -1398,7 +1489,7 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         }
     }
     const int fixed = fixed_smem(bn, p.epi_res != 0), per_stage = stage_smem(bn, two);
-    const int min_stages = p.epi_tma ? (EPI_BUFS * p.epi_buf_stride + per_stage - 1) / per_stage : 2;   // chunk buffers alias the stages
+    const int min_stages = (p.epi_tma || p.part_tma) ? (EPI_BUFS * p.epi_buf_stride + per_stage - 1) / per_stage : 2;   // chunk buffers alias the stages
     const int SMEM_1 = 232448, SMEM_2 = 115712;       // opt-in limit per CTA; per CTA when two share an SM (1 KiB reserved each)
     // ... and multi-wave grids: with two CTAs per SM the prologue / epilogue of one tile overlaps the main loop of another
     const long long total_ctas = (long long)m_tiles * n_tiles * splits;
@@ -1422,24 +1513,40 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     if (stages < 2 || stages < min_stages) { delete g; return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: no pipeline fits (block_n %d)", bn); }
     p.stages = stages;
     g->smem_bytes = fixed + stages * per_stage;
+    // ---- split-K: reduce inside the kernel when the final epilogue can run here and every CTA of the grid is resident at once
+    // (a CTA that owns output chunks waits for its tile's other splits); otherwise the second (reduce) kernel finishes the job
+    if (splits > 1) {
+        static const int fix_mode = getenv("SDB200_TC_FIXUP") ? atoi(getenv("SDB200_TC_FIXUP")) : 1;
+        const long long capacity = (long long)sms * (g->co_resident ? 2 : 1);
+        p.fixup = (fix_mode && direct_ok && !two && (long long)m_tiles * n_tiles <= 1024 && total_ctas <= capacity) ? 1 : 0;
+        if (!p.fixup) {
+            if (want_extras) {
+                delete g;
+                return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: split-K x%d (%lld CTAs) cannot be reduced in the kernel; out2 / row_stats / folded LayerNorm need splits = 1 here", splits, total_ctas);
+            }
+            p.epi_tma = 0;                                  // the kernel only writes partial planes; the reduce kernel runs the epilogue
+        }
+    }
     *handle = g;
     return SDK_OK;
 }
 
 extern "C" int64_t sdk_tc_gemm_workspace_bytes(void* handle) { return handle ? ((TcGemm*)handle)->ws_bytes : 0; }
 
-// workspace: fp32 split-K partials [splits][M][N]; may be shared by all GEMMs launched on one stream.
+// workspace: [tile counters (WS_HEADER_BYTES, zeroed ONCE by the caller; the kernels re-arm them)][fp32 split-K partials [splits][M][N]];
+// may be shared by all GEMMs launched on one stream.
 extern "C" int sdk_tc_gemm_set_workspace(void* handle, void* ws) {
     SDK_CHECK_ARG(handle, "sdk_tc_gemm_set_workspace: null handle");
     TcGemm* g = (TcGemm*)handle;
     if (g->prm.splits > 1) {
         SDK_CHECK_ARG(ws && ((uintptr_t)ws & 15) == 0, "sdk_tc_gemm_set_workspace: split-K GEMM needs a 16-byte aligned workspace");
         TcParams& p = g->prm;
-        p.partial = (float*)ws;
-        if (p.epi_tma) {
+        p.tile_cnt = (unsigned int*)ws;
+        p.partial = (float*)((char*)ws + WS_HEADER_BYTES);
+        if (p.part_tma) {
             const uint64_t odims[5] = {(uint64_t)p.N, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B, (uint64_t)p.splits};
             const uint32_t obox[5] = {32u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB, 1u};
-            const int rc = encode_map(&p.tmOut, ws, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 5, odims, obox, CU_TENSOR_MAP_SWIZZLE_128B,
+            const int rc = encode_map(&p.tmPart, p.partial, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 5, odims, obox, CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_NONE);
             if (rc != SDK_OK) return rc;
         }
@@ -1459,7 +1566,7 @@ extern "C" int sdk_tc_gemm_set_stats(void* handle, double* chan_stats) {
     const bool ok_out = p.out_dtype == SDK_F32 && !p.geglu && !p.out_nchw && p.N % 32 == 0;
     if (!ok_out) return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_set_stats: needs an fp32 NHWC output with N %% 32 == 0");
     const int rps = p.TW * p.TH;
-    if (p.splits > 1) {                                  // statistics come from the reduce pass (32-row patches)
+    if (p.splits > 1 && !p.fixup) {                      // statistics come from the reduce pass (32-row patches)
         if ((p.H * p.W) % 32 != 0) return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_set_stats: split-K needs H*W %% 32 == 0");
     } else if (!p.epi_tma || (p.TB == 1 && p.W % p.TW != 0) || (p.TB > 1 && rps % 32 != 0)) {
         return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_set_stats: tile %dx%dx%d of a %dx%d map cannot attribute rows to samples", p.TW, p.TH, p.TB, p.W, p.H);
@@ -1475,6 +1582,8 @@ extern "C" int sdk_tc_gemm_info(void* handle, int* out, int n) {
     out[0] = g->block_n; out[1] = g->prm.splits; out[2] = g->grid.x; out[3] = g->grid.y;
     out[4] = g->prm.TW; out[5] = g->prm.TH; out[6] = g->prm.TB; out[7] = g->prm.total_kb;
     if (n >= 9) out[8] = g->two_cta ? 2 : 1;
+    if (n >= 10) out[9] = g->prm.fixup;
+    if (n >= 11) out[10] = g->persistent ? 1 : 0;
     return SDK_OK;
 }
 

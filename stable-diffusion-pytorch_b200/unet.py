@@ -118,6 +118,20 @@ class PackedWeights:
             t[f"{p}.qkv.w"] = dev(torch.cat([sd[f"{b}.attn1.{n}_proj.weight"] for n in "qkv"], 0), wdt)
             t[f"{p}.o1.w"], t[f"{p}.o1.b"] = dev(sd[f"{b}.attn1.out_proj.weight"], wdt), dev(sd[f"{b}.attn1.out_proj.bias"])
             t[f"{p}.q2.w"] = dev(sd[f"{b}.attn2.q_proj.weight"], wdt)
+            if precision != "fp32":
+                # LayerNorm folded into the projection that consumes it (unet.py:137-149):
+                #   LN(x) W^T + c = rstd * (x W'^T - mean * colsum) + (c + W beta),  W' = W * gamma (bf16), colsum[n] = sum_k W'[n][k]
+                # colsum is taken from the ROUNDED W' so that the mean term cancels exactly against what the tensor core multiplies.
+                def fold(key, w, bias, ln):
+                    w = w.to(device=device, dtype=torch.float32)
+                    gm, bt = sd[f"{b}.layernorm_{ln}.weight"].to(device, torch.float32), sd[f"{b}.layernorm_{ln}.bias"].to(device, torch.float32)
+                    wg = (w * gm[None, :]).to(torch.bfloat16)
+                    t[f"{p}.{key}.lnw"] = dev(wg, torch.bfloat16)
+                    t[f"{p}.{key}.lncs"] = wg.float().sum(1).contiguous()
+                    add = w.double() @ bt.double()
+                    t[f"{p}.{key}.lnb"] = (add + (bias.to(device).double() if bias is not None else 0.0)).float().contiguous()
+                fold("qkv", torch.cat([sd[f"{b}.attn1.{n}_proj.weight"] for n in "qkv"], 0), None, 1)
+                fold("q2", sd[f"{b}.attn2.q_proj.weight"], None, 2)
             kv_w = torch.cat([sd[f"{b}.attn2.k_proj.weight"], sd[f"{b}.attn2.v_proj.weight"]], 0)
             if precision == "fp32":
                 t[f"{p}.kv2.w"] = dev(kv_w, wdt)
@@ -127,6 +141,8 @@ class PackedWeights:
             w0, b0 = sd[f"{b}.ffn.0.proj.weight"], sd[f"{b}.ffn.0.proj.bias"]      # [8C, C]: rows [value(4C) ; gate(4C)]
             t[f"{p}.ff0.w"] = dev(torch.stack([w0[:4 * c], w0[4 * c:]], 1).reshape(8 * c, c), wdt)
             t[f"{p}.ff0.b"] = dev(torch.stack([b0[:4 * c], b0[4 * c:]], 1).reshape(8 * c))
+            if precision != "fp32":
+                fold("ff0", torch.stack([w0[:4 * c], w0[4 * c:]], 1).reshape(8 * c, c), torch.stack([b0[:4 * c], b0[4 * c:]], 1).reshape(8 * c), 3)
             t[f"{p}.ff1.w"], t[f"{p}.ff1.b"] = dev(sd[f"{b}.ffn.1.weight"], wdt), dev(sd[f"{b}.ffn.1.bias"])
         for st in a.down + a.up:
             if st.resample is not None:
@@ -239,9 +255,12 @@ class StepProgram:
 
     def _conv(self, srcs, w, bias, B, Hin, Win, N, *, k=1, stride=1, up=False, tbias=0, tb_stride=0,
               residual=None, geglu=False, out_code=F32_T, out=None, out_nchw=False, in_code=None, ctx=False,
-              force_simt=False, seg2=None, want_stats=False):
+              force_simt=False, seg2=None, want_stats=False, ln_out=False, ln_in=None):
         """srcs: [(tensor[rows, C], C)] (1 or 2).  Returns the output tensor [M, N or N/2].
-        want_stats: the output feeds a GroupNorm -> also produce its per-channel (sum, sum of squares) table (out._cstats)."""
+        want_stats: the output feeds a GroupNorm -> also produce its per-channel (sum, sum of squares) table (out._cstats).
+        ln_out: the output feeds a LayerNorm that is folded into its consumer -> also produce a bf16 copy (out._bf16) and the per-row
+        statistics partials (out._rowstats).  ln_in = (row statistics tensor, column sums of the folded weights): this GEMM applies
+        the LayerNorm of its A rows in its epilogue (tensor-core path only)."""
         upf = 2 if up else 1
         pad = k // 2
         Hout = (Hin * upf + 2 * pad - k) // stride + 1
@@ -270,7 +289,14 @@ class StepProgram:
         if p.in_dtype == F32_T or force_simt:
             self._emit(self.lib.sdk_conv_gemm_f32, C.byref(p), ctx=ctx)
         else:
-            fused = self._emit_tc_conv(p, srcs, w, ctx, seg2, cs)
+            extras = None
+            if ln_out:
+                out._bf16 = self.pool.get(M, N, BF16_T)
+                out._rowstats = self.pool.get(M, 2 * (N // 32), F32_T)
+                extras = dict(out2=out._bf16, row_stats=out._rowstats)
+            if ln_in is not None:
+                extras = dict(extras or {}, ln_stats=ln_in[0], ln_colsum=ln_in[1], ln_parts=srcs[0][1] // 32)
+            fused = self._emit_tc_conv(p, srcs, w, ctx, seg2, cs, extras)
         if want_stats:
             if not fused:                                   # producer cannot reduce its own columns: one extra small launch
                 self._emit(self.lib.sdk_channel_stats, out.data_ptr(), B, Hout * Wout, N, cs.data_ptr(), ctx=ctx)
@@ -286,7 +312,7 @@ class StepProgram:
         self.stat_used += nbytes
         return t
 
-    def _emit_tc_conv(self, p, srcs, w, ctx, seg2=None, cs=None):
+    def _emit_tc_conv(self, p, srcs, w, ctx, seg2=None, cs=None, extras=None):
         """tcgen05 implicit GEMM for a stride-1 conv / linear described by ConvParams ``p``."""
         if len(srcs) != 1 or p.stride != 1 or p.upsample:
             raise RuntimeError("tensor-core conv takes one pre-concatenated, pre-upsampled bf16 source at stride 1")
@@ -300,8 +326,22 @@ class StepProgram:
         d.block_n, d.splits, d.w_kmajor, d.two_cta = self.net.tc_block_n, self.net.tc_splits, 1, self.net.tc_two_cta
         if self.net.tc_autotune and not d.block_n and not d.splits:
             d.block_n, d.splits, d.two_cta = self._autotune(d, srcs[0][0], cs)
+        if extras:
+            if "out2" in extras:
+                d.out2, d.row_stats = extras["out2"].data_ptr(), extras["row_stats"].data_ptr()
+            if "ln_stats" in extras:
+                d.ln_stats, d.ln_colsum = extras["ln_stats"].data_ptr(), extras["ln_colsum"].data_ptr()
+                d.ln_parts, d.ln_eps = extras["ln_parts"], 1e-5
         h = C.c_void_p()
-        _lib.check(self.lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
+        rc = self.lib.sdk_tc_gemm_create(C.byref(d), C.byref(h))
+        if rc == -3 and extras:
+            # the tuned tiling cannot carry the fused LayerNorm work (ragged N tile, or a split-K grid too large to reduce inside the
+            # kernel): an exact N tile without split-K always can
+            d.splits, d.two_cta = 1, 1
+            if d.N % max(d.block_n, 1) != 0:
+                d.block_n = 0
+            rc = self.lib.sdk_tc_gemm_create(C.byref(d), C.byref(h))
+        _lib.check(rc)
         self.tc_handles.append(h)
         self.keep.append(d)
         self._emit(self.lib.sdk_tc_gemm_launch, h, ctx=ctx)
@@ -420,7 +460,7 @@ class StepProgram:
             h = C.c_void_p()
             if lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)) != 0:
                 continue
-            ws = torch.empty(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=self.device)
+            ws = torch.zeros(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=self.device)
             ok = lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr()) == 0
             if ok and cs is not None:
                 ok = lib.sdk_tc_gemm_set_stats(h, cs.data_ptr()) in (0, -3)
@@ -542,23 +582,42 @@ class StepProgram:
         D = Cc // tr.heads
         es = 4 if self.act == F32_T else 2
         a, _ = self._gn([(x, Cc)], B, S, t[f"{p}.gn.g"], t[f"{p}.gn.b"], 1e-6, False)          # eps 1e-6: unet.py:66
-        h, _, _ = self._conv([(a, Cc)], t[f"{p}.in.w"], t[f"{p}.in.b"], 1, 1, M, Cc)
+        # bf16 program: the three LayerNorms (unet.py:137,141,147) are FOLDED into the projections that consume them -- the
+        # producer's epilogue also writes a bf16 copy of the row and its (sum, sum of squares) partials, the consumer multiplies the
+        # raw rows by gamma-scaled weights and normalises in ITS epilogue: no LayerNorm launch, no extra pass over the tensor.
+        fold = self.act != F32_T and self.net.ln_fold
+
+        def drop(tn):                                           # release a LayerNorm producer together with its side outputs
+            for extra in ("_bf16", "_rowstats"):
+                if getattr(tn, extra, None) is not None:
+                    self.pool.put(getattr(tn, extra))
+            self.pool.put(tn)
+
+        h, _, _ = self._conv([(a, Cc)], t[f"{p}.in.w"], t[f"{p}.in.b"], 1, 1, M, Cc, ln_out=fold)
         self.pool.put(a)
         # self-attention
-        n1 = self._ln(h, t[f"{p}.ln1.g"], t[f"{p}.ln1.b"], M, Cc)
-        qkv, _, _ = self._conv([(n1, Cc)], t[f"{p}.qkv.w"], None, 1, 1, M, 3 * Cc, out_code=self.act)
-        self.pool.put(n1)
+        if fold:
+            qkv, _, _ = self._conv([(h._bf16, Cc)], t[f"{p}.qkv.lnw"], t[f"{p}.qkv.lnb"], 1, 1, M, 3 * Cc, out_code=self.act,
+                                   ln_in=(h._rowstats, t[f"{p}.qkv.lncs"]))
+        else:
+            n1 = self._ln(h, t[f"{p}.ln1.g"], t[f"{p}.ln1.b"], M, Cc)
+            qkv, _, _ = self._conv([(n1, Cc)], t[f"{p}.qkv.w"], None, 1, 1, M, 3 * Cc, out_code=self.act)
+            self.pool.put(n1)
         base = qkv.data_ptr()
         ao = self._attention(base, 3 * Cc, S * 3 * Cc, base + Cc * es, 3 * Cc, S * 3 * Cc, base + 2 * Cc * es, 3 * Cc, S * 3 * Cc,
                              B, tr.heads, S, S, D, Cc)
         self.pool.put(qkv)
-        h2, _, _ = self._conv([(ao, Cc)], t[f"{p}.o1.w"], t[f"{p}.o1.b"], 1, 1, M, Cc, residual=h)
+        h2, _, _ = self._conv([(ao, Cc)], t[f"{p}.o1.w"], t[f"{p}.o1.b"], 1, 1, M, Cc, residual=h, ln_out=fold)
         self.pool.put(ao)
-        self.pool.put(h)
+        drop(h)
         # cross-attention: K/V of the context are loop-invariant -> context program
-        n2 = self._ln(h2, t[f"{p}.ln2.g"], t[f"{p}.ln2.b"], M, Cc)
-        q2, _, _ = self._conv([(n2, Cc)], t[f"{p}.q2.w"], None, 1, 1, M, Cc, out_code=self.act)
-        self.pool.put(n2)
+        if fold:
+            q2, _, _ = self._conv([(h2._bf16, Cc)], t[f"{p}.q2.lnw"], t[f"{p}.q2.lnb"], 1, 1, M, Cc, out_code=self.act,
+                                  ln_in=(h2._rowstats, t[f"{p}.q2.lncs"]))
+        else:
+            n2 = self._ln(h2, t[f"{p}.ln2.g"], t[f"{p}.ln2.b"], M, Cc)
+            q2, _, _ = self._conv([(n2, Cc)], t[f"{p}.q2.w"], None, 1, 1, M, Cc, out_code=self.act)
+            self.pool.put(n2)
         if self.kv_all is not None:                               # one GEMM for all layers (context program, emitted in _build)
             kv_row = self.pw.kv_total
             kvb = self.kv_all.data_ptr() + self.pw.kv_off[tr.index] * es
@@ -573,16 +632,20 @@ class StepProgram:
         ao2 = self._attention(q2.data_ptr(), Cc, S * Cc, kvb, kv_row, kv_batch, kvb + Cc * es, kv_row, kv_batch,
                               B, tr.heads, S, self.Sk, D, Cc)
         self.pool.put(q2)
-        h3, _, _ = self._conv([(ao2, Cc)], t[f"{p}.o2.w"], t[f"{p}.o2.b"], 1, 1, M, Cc, residual=h2)
+        h3, _, _ = self._conv([(ao2, Cc)], t[f"{p}.o2.w"], t[f"{p}.o2.b"], 1, 1, M, Cc, residual=h2, ln_out=fold)
         self.pool.put(ao2)
-        self.pool.put(h2)
+        drop(h2)
         # GEGLU feed-forward (activation_fn.py:17-20), GEGLU fused into the first GEMM's epilogue
-        n3 = self._ln(h3, t[f"{p}.ln3.g"], t[f"{p}.ln3.b"], M, Cc)
-        g, _, _ = self._conv([(n3, Cc)], t[f"{p}.ff0.w"], t[f"{p}.ff0.b"], 1, 1, M, 8 * Cc, geglu=True, out_code=self.act)
-        self.pool.put(n3)
+        if fold:
+            g, _, _ = self._conv([(h3._bf16, Cc)], t[f"{p}.ff0.lnw"], t[f"{p}.ff0.lnb"], 1, 1, M, 8 * Cc, geglu=True, out_code=self.act,
+                                 ln_in=(h3._rowstats, t[f"{p}.ff0.lncs"]))
+        else:
+            n3 = self._ln(h3, t[f"{p}.ln3.g"], t[f"{p}.ln3.b"], M, Cc)
+            g, _, _ = self._conv([(n3, Cc)], t[f"{p}.ff0.w"], t[f"{p}.ff0.b"], 1, 1, M, 8 * Cc, geglu=True, out_code=self.act)
+            self.pool.put(n3)
         h4, _, _ = self._conv([(g, 4 * Cc)], t[f"{p}.ff1.w"], t[f"{p}.ff1.b"], 1, 1, M, Cc, residual=h3, out_code=self.act)
         self.pool.put(g)
-        self.pool.put(h3)
+        drop(h3)
         # conv_output + long residual feeds the next GroupNorm: (B, H, W) form so that tiles can be attributed to samples
         out, _, _ = self._conv([(h4, Cc)], t[f"{p}.out.w"], t[f"{p}.out.b"], B, H, W, Cc, residual=x, want_stats=True)
         self.pool.put(h4)
@@ -804,6 +867,7 @@ class UNet(nn.Module):
         self.tc_tune_pairs = int(os.environ.get("SDB200_TC_TUNE_PAIRS", "0"))   # also try cta_group::2 pairs when measuring tilings
         self.tc_autotune = int(os.environ.get("SDB200_TC_AUTOTUNE", "1"))     # 0 model | 1 committed cache | 2 measure misses | 3 and print
         self.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention for head_dim 40 / 64
+        self.ln_fold = os.environ.get("SDB200_LN_FOLD", "1") != "0"          # bf16: LayerNorm folded into the consuming GEMM (0: layernorm kernel)
         self.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
         # sums: statistics from per-channel sums reduced in the producing GEMM's epilogue (bf16 program; fastest measured) |
         # split (stats + apply kernels) | cluster | coop | auto

@@ -469,6 +469,91 @@ def test_tc_gemm_channel_stats(dev, case):
     assert rel_l2(cs[0], cs[1]) < 1e-13                    # atomics in double: order-independent to the last bits
 
 
+LN_FOLD_CASES = [
+    # name, M, C, N_consumer, geglu, producer (block_n, splits), consumer (block_n, splits)
+    ("L0_qkv", 8192, 320, 960, False, (0, 0), (0, 0)),
+    ("L1_geglu", 2048, 640, 5120, True, (0, 0), (0, 0)),
+    ("L2_q2_splitk_both", 512, 1280, 1280, False, (128, 4), (160, 4)),
+    ("mid_ragged_rows", 200, 1280, 3840, False, (256, 5), (0, 0)),
+    ("L1_splitk_many", 2048, 640, 640, False, (128, 2), (128, 2)),
+]
+
+
+@pytest.mark.parametrize("case", LN_FOLD_CASES, ids=[c[0] for c in LN_FOLD_CASES])
+def test_tc_gemm_layernorm_fold(dev, case):
+    """LayerNorm folded across two GEMMs (unet.py:137-149): the PRODUCER (out_proj + residual) also writes a bf16 copy of its fp32
+    rows and their per-chunk (sum, sum of squares); the CONSUMER multiplies the raw bf16 rows by gamma-scaled weights and applies
+    mean / rstd in its epilogue.  Reference: fp32 LayerNorm of the producer's fp32 output, rounded to bf16, times the bf16 weights."""
+    name, M, Cc, N2, geglu, (bn1, sp1), (bn2, sp2) = case
+    lib = _lib.lib()
+    a = gen((1, 1, M, Cc), 31, dev).bfloat16()
+    w1 = gen((Cc, Cc), 32, dev, 1.0 / math.sqrt(Cc)).bfloat16()
+    b1 = gen((Cc,), 33, dev, 0.1)
+    resid = gen((1, 1, M, Cc), 34, dev) * 2 + 0.5                      # non-zero row means
+    gamma, beta = 1 + 0.2 * gen((Cc,), 35, dev), 0.1 * gen((Cc,), 36, dev)
+    w2 = gen((N2, Cc), 37, dev, 1.0 / math.sqrt(Cc))
+    b2 = gen((N2,), 38, dev, 0.1)
+    out1 = torch.full((1, 1, M, Cc), float("nan"), device=dev)
+    out1_bf = torch.full((1, 1, M, Cc), float("nan"), device=dev, dtype=torch.bfloat16)
+    rowst = torch.full((M, Cc // 32, 2), float("nan"), device=dev)
+    Nout = N2 // 2 if geglu else N2
+    out2 = torch.full((1, 1, M, Nout), float("nan"), device=dev, dtype=torch.bfloat16)
+    # host-side folding (what PackedWeights does)
+    wg = (w2 * gamma[None, :]).bfloat16()
+    colsum = wg.float().sum(1).contiguous()
+    bias2 = (w2.double() @ beta.double() + b2.double()).float().contiguous()
+    handles, infos = [], []
+    for which in (0, 1):
+        d = TcGemmDesc()
+        d.w_kmajor = 1
+        if which == 0:
+            wp = kmajor(w1)
+            d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = a.data_ptr(), wp.data_ptr(), Cc, 1, 1
+            d.B, d.H, d.W, d.N = 1, 1, M, Cc
+            d.bias, d.residual, d.out, d.out_dtype = b1.data_ptr(), resid.data_ptr(), out1.data_ptr(), F32_T
+            d.out2, d.row_stats = out1_bf.data_ptr(), rowst.data_ptr()
+            d.block_n, d.splits = bn1, sp1
+        else:
+            wp2 = kmajor(wg)
+            d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = out1_bf.data_ptr(), wp2.data_ptr(), Cc, 1, 1
+            d.B, d.H, d.W, d.N = 1, 1, M, N2
+            d.bias, d.out, d.out_dtype, d.geglu = bias2.data_ptr(), out2.data_ptr(), BF16_T, int(geglu)
+            d.ln_stats, d.ln_colsum, d.ln_parts, d.ln_eps = rowst.data_ptr(), colsum.data_ptr(), Cc // 32, 1e-5
+            d.block_n, d.splits = bn2, sp2
+        h = C.c_void_p()
+        _lib.check(lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
+        info = (C.c_int * 11)()
+        _lib.check(lib.sdk_tc_gemm_info(h, info, 11))
+        handles.append((h, d, wp if which == 0 else wp2))
+        infos.append(tuple(info))
+    ws = torch.zeros(max(max(int(lib.sdk_tc_gemm_workspace_bytes(h)) for h, _, _ in handles), 256), dtype=torch.uint8, device=dev)
+    for h, _, _ in handles:
+        _lib.check(lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr()))
+    for _ in range(3):                                     # repeated: the split-K tile counters must re-arm themselves
+        for h, _, _ in handles:
+            _lib.check(lib.sdk_tc_gemm_launch(h, stream()))
+    torch.cuda.synchronize()
+    for h, _, _ in handles:
+        lib.sdk_tc_gemm_destroy(h)
+    for nm, info, sp in (("producer", infos[0], sp1), ("consumer", infos[1], sp2)):
+        print(f"{name} {nm}: block_n={info[0]} splits={info[1]} grid=({info[2]},{info[3]}) fixup={info[9]} persistent={info[10]}")
+        if sp > 1:
+            assert info[1] == sp and info[9] == 1, "split-K with fused LayerNorm work must be reduced inside the kernel"
+    x = ref_conv([a], w1, b1, 1, 1, False, None, resid, False)            # [1,1,M,C] fp32
+    assert rel_l2(out1, x) < 2e-5
+    assert rel_l2(out1_bf.float(), out1.bfloat16().float()) == 0.0           # the copy is the rounded fp32 output
+    xs = out1.view(M, Cc // 32, 32).double()
+    assert rel_l2(rowst[..., 0].double(), xs.sum(-1)) < 1e-6 and rel_l2(rowst[..., 1].double(), (xs * xs).sum(-1)) < 1e-6
+    ln = Fn.layer_norm(out1.view(M, Cc), (Cc,), gamma, beta, 1e-5)
+    want = ln.bfloat16().float() @ w2.bfloat16().float().t() + b2
+    if geglu:
+        want = want[:, 0::2] * Fn.gelu(want[:, 1::2])
+    e = rel_l2(out2.view(M, Nout).float(), want)
+    print(f"{name}: folded LayerNorm -> GEMM rel-L2 {e:.2e} vs LN-then-bf16-GEMM")
+    assert not torch.isnan(out2.float()).any()
+    assert e < 6e-3
+
+
 @pytest.mark.parametrize("C_", [320, 640, 1280, 768])
 def test_layernorm(dev, C_):
     lib = _lib.lib()
