@@ -62,7 +62,8 @@ struct alignas(64) TcParams {
     // ---- split-K with the reduction INSIDE this kernel (fixup): every split CTA stores its raw partial plane (tmPart), bumps the
     // tile's arrival counter and -- if it owns output chunks (chunk c belongs to split c % splits) -- waits until all splits of the
     // tile have arrived, sums the planes in split order (deterministic) and runs the ordinary direct epilogue on the sum.
-    // All CTAs of the grid are co-resident (checked at plan time, launched cooperatively), so the wait cannot deadlock.
+    // All CTAs of the grid are co-resident (checked at plan time against the driver's occupancy figure for this launch; kernels of
+    // a stream run one after another, so every SM is free when the grid starts), so the wait cannot deadlock; it is bounded anyway.
     CUtensorMap tmPart;
     int fixup, part_tma;
     unsigned int* tile_cnt;      // [tiles] arrivals ; [1024 + tiles] finished waiters (self-resetting)
@@ -422,7 +423,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                             unsigned spins = 0;
                             while (ptx::ld_acquire_gpu(p.tile_cnt + tile) < (unsigned)p.splits) {
                                 __nanosleep(64);
-                                if (++spins > (1u << 24)) break;   // ~1 s: never hang the GPU on a logic error (the output is then wrong, not late)
+                                if (++spins > (1u << 21)) break;   // ~0.2 s: never hang the GPU on a logic error (the output is then wrong, not late)
                             }
                             // the last of the waiting CTAs re-arms the counters for the next launch (stream order separates launches)
                             const unsigned waiters = (unsigned)(p.splits < NCH ? p.splits : NCH);
@@ -1240,16 +1241,6 @@ int launch_cfg(const TcGemm* g, cudaStream_t s) {
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         SDK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, TWO>, g->prm));
-    } else if (g->prm.fixup) {
-        // in-kernel split-K reduction: CTAs wait for their tile's siblings, so the whole grid must be co-resident -> cooperative launch
-        // (the driver rejects a grid that does not fit instead of letting it hang)
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = g->grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = g->smem_bytes; cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeCooperative;
-        at[0].val.cooperative = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        SDK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, TWO>, g->prm));
     } else
     SDK_CUDA(sdk_launch(conv_gemm_tc_kernel<BN, TWO>, dim3(g->grid), dim3(TC_THREADS), (size_t)(g->smem_bytes), s, g->prm));
     SDK_LAUNCH_CHECK();
@@ -1262,6 +1253,26 @@ int launch_cfg(const TcGemm* g, cudaStream_t s) {
         SDK_LAUNCH_CHECK();
     }
     return SDK_OK;
+}
+
+// non-persistent kernel instantiation for a tile width (occupancy queries)
+const void* tc_kernel_ptr(int bn, bool two) {
+    if (two) {
+        switch (bn) {
+            case 128: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<128, true>);
+            case 160: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<160, true>);
+            case 256: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<256, true>);
+        }
+        return nullptr;
+    }
+    switch (bn) {
+        case 32: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<32, false>);
+        case 64: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<64, false>);
+        case 128: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<128, false>);
+        case 160: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<160, false>);
+        case 256: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<256, false>);
+    }
+    return nullptr;
 }
 
 void pick_tile(int W, int H, int B, int* TW, int* TH, int* TB) {
@@ -1517,12 +1528,22 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     // (a CTA that owns output chunks waits for its tile's other splits); otherwise the second (reduce) kernel finishes the job
     if (splits > 1) {
         static const int fix_mode = getenv("SDB200_TC_FIXUP") ? atoi(getenv("SDB200_TC_FIXUP")) : 1;
-        const long long capacity = (long long)sms * (g->co_resident ? 2 : 1);
-        p.fixup = (fix_mode && direct_ok && !two && (long long)m_tiles * n_tiles <= 1024 && total_ctas <= capacity) ? 1 : 0;
+        // CTAs of this kernel that one SM holds at once, as the driver computes it for this launch configuration (the waiting
+        // CTAs of a tile rely on their siblings being resident: never assume more than the driver grants, nor more than 2 = TMEM)
+        int occ = 0;
+        const void* kfn = tc_kernel_ptr(bn, false);
+        if (fix_mode && direct_ok && !two && kfn && sdk_ensure_dyn_smem(kfn, g->smem_bytes) == cudaSuccess)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, TC_THREADS, (size_t)g->smem_bytes);
+        if (occ > (g->co_resident ? 2 : 1)) occ = g->co_resident ? 2 : 1;
+        const long long capacity = (long long)sms * occ;
+        p.fixup = (occ > 0 && (long long)m_tiles * n_tiles <= 1024 && total_ctas <= capacity) ? 1 : 0;
         if (!p.fixup) {
             if (want_extras) {
+                // the fused LayerNorm work needs the final epilogue inside this kernel: fewer splits until the grid is co-resident
+                SdkTcGemmDesc d2 = *d;
+                d2.block_n = bn; d2.splits = splits - 1; d2.two_cta = 1;
                 delete g;
-                return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: split-K x%d (%lld CTAs) cannot be reduced in the kernel; out2 / row_stats / folded LayerNorm need splits = 1 here", splits, total_ctas);
+                return sdk_tc_gemm_create(&d2, handle);
             }
             p.epi_tma = 0;                                  // the kernel only writes partial planes; the reduce kernel runs the epilogue
         }
