@@ -65,7 +65,7 @@ struct alignas(64) TcParams {
     // All CTAs of the grid are co-resident (checked at plan time against the driver's occupancy figure for this launch; kernels of
     // a stream run one after another, so every SM is free when the grid starts), so the wait cannot deadlock; it is bounded anyway.
     CUtensorMap tmPart;
-    int fixup, part_tma;
+    int fixup, part_tma, fix_nb;      // fix_nb: partial planes fetched per batch (what fits behind the output ring)
     unsigned int* tile_cnt;      // [tiles] arrivals ; [1024 + tiles] finished waiters (self-resetting)
     // ---- second output: bf16 copy of the fp32 NHWC output (A operand of the next GEMM: LayerNorm folded into that GEMM, conv gathers)
     CUtensorMap tmOut2;
@@ -198,6 +198,29 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
     }
 }
 
+// Folded LayerNorm: mean / rstd of one row from the producer's per-chunk (sum, sum of squares) partials -- `parts` float2, contiguous
+// and 16-byte aligned (parts is even).  Eight 16-byte loads in flight per batch: the row's statistics cost one or two L2 round
+// trips, not one per partial.
+__device__ __forceinline__ void ln_row_stats(const float2* rs, int parts, float inv_c, float eps, float& rstd, float& nm) {
+    const float4* rs4 = reinterpret_cast<const float4*>(rs);
+    const int nq = parts >> 1;
+    double sm = 0.0, sq = 0.0;
+    for (int i0 = 0; i0 < nq; i0 += 8) {
+        float4 t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = i0 + k < nq ? __ldcg(rs4 + i0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a += t[k].x + t[k].z; b += t[k].y + t[k].w; }
+        sm += (double)a; sq += (double)b;
+    }
+    const double mean = sm * (double)inv_c;
+    double var = sq * (double)inv_c - mean * mean;
+    if (var < 0.0) var = 0.0;
+    rstd = rsqrtf((float)var + eps);
+    nm = -(float)mean * rstd;
+}
+
 // TWO = cta_group::2: a CTA pair (cluster of 2 consecutive m-tiles) runs ONE 256 x BN MMA per K step.  Each CTA loads its
 // own 128 rows of A and HALF of the B tile (BN/2 rows), so a k-block costs 16 KiB + BN*64 B of L2->smem traffic per SM
 // instead of 16 KiB + BN*128 B; accumulator rows of each half live in that CTA's own TMEM.  Only the leader (rank 0)
@@ -231,7 +254,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     uint64_t* empty = full + MAX_STAGES;
     uint64_t* tmem_full = empty + MAX_STAGES;
     uint64_t* res_full = tmem_full + 1;               // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+    uint64_t* fix_bar = res_full + 2;                 // split-K fixup: partial planes landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fix_bar + 1);
     // [ADD_ROWS][BN]: bias + time-bias of the tile's samples (16-byte aligned: read as float4)
     float* s_add = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
     float2* s_stat = reinterpret_cast<float2*>(s_add + ADD_ROWS * BN);        // [2][4][32] column partials of the row quarters
@@ -255,6 +279,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], TWO ? 2 : 1); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(tmem_full, 1);
         ptx::mbar_init(&res_full[0], 1); ptx::mbar_init(&res_full[1], 1);
+        ptx::mbar_init(fix_bar, 1);
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmA[0]);
         ptx::prefetch_tmap(&p.tmB[0]);
@@ -370,16 +395,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         }
         // folded LayerNorm: mean / rstd of this thread's A row from the producer's per-chunk (sum, sum of squares) partials
         float ln_rstd = 1.f, ln_nm = 0.f;                       // out = acc * rstd + (-mean * rstd) * colsum[n] + bias'[n]
-        if (p.ln_stats && valid && n_my > 0) {
-            const float2* rs = p.ln_stats + (size_t)grow * p.ln_parts;
-            double sm = 0.0, sq = 0.0;
-            for (int i = 0; i < p.ln_parts; ++i) { const float2 t2 = __ldcg(rs + i); sm += (double)t2.x; sq += (double)t2.y; }
-            const double mean = sm * (double)p.ln_inv_c;
-            double var = sq * (double)p.ln_inv_c - mean * mean;
-            if (var < 0.0) var = 0.0;
-            ln_rstd = (float)(1.0 / sqrt(var + (double)p.ln_eps));
-            ln_nm = -(float)mean * ln_rstd;
-        }
+        if (p.ln_stats && valid && n_my > 0)
+            ln_row_stats(p.ln_stats + (size_t)grow * p.ln_parts, p.ln_parts, p.ln_inv_c, p.ln_eps, ln_rstd, ln_nm);
         const bool fast = !p.out_nchw && (n0 + BN <= p.N);               // full tile of an NHWC output: the common case
 
         ptx::mbar_wait(tmem_full, 0);
@@ -467,34 +484,34 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 };
                 const bool glu = p.geglu != 0;
                 const int ocol0 = glu ? (n0 >> 1) : n0;
-                const size_t plane4 = (size_t)p.M * (size_t)p.N / 4;
+                uint8_t* sFix = smem + EPI_BUFS * p.epi_buf_stride;       // landing buffers of the partial planes (fixup)
+                uint32_t fix_ph = 0;
 #pragma unroll 1
                 for (int i = 0; i < n_my; ++i, ++gk) {
                     const int c = c_first + i * c_step;
                     float v[32];
                     if (fix) {
-                        // sum of the splits' partial planes, in split order (deterministic); L2 reads, two planes in flight
+                        // sum of the splits' partial planes in split order (deterministic).  The planes of this chunk come back from
+                        // L2 as TMA boxes (up to fix_nb in flight, landing in the idle pipeline stages behind the output ring).
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                        if (valid) {
-                            const float4* s4 = reinterpret_cast<const float4*>(p.partial + (size_t)grow * p.N + n0 + c * 32);
-                            int z = 0;
-                            for (; z + 2 <= p.splits; z += 2) {
-                                float4 a[8], bq[8];
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) { a[j] = __ldcg(s4 + (size_t)z * plane4 + j); bq[j] = __ldcg(s4 + (size_t)(z + 1) * plane4 + j); }
+                        for (int z0 = 0; z0 < p.splits; z0 += p.fix_nb) {
+                            const int nb = min(p.fix_nb, p.splits - z0);
+                            if (z0 > 0) asm volatile("bar.sync 1, 128;" ::: "memory");      // everybody has summed the previous batch
+                            if (et == 0) {
+                                ptx::mbar_expect_tx(fix_bar, (uint32_t)nb * (uint32_t)p.rows * 128u);
+                                for (int k = 0; k < nb; ++k)
+                                    ptx::tma_load_5d(sFix + k * RES_BUF_BYTES, &p.tmPart, fix_bar, n0 + c * 32, w0, h0, b0, z0 + k);
+                            }
+                            ptx::mbar_wait(fix_bar, fix_ph);
+                            fix_ph ^= 1u;
+                            for (int k = 0; k < nb; ++k) {
+                                const uint8_t* pb = sFix + k * RES_BUF_BYTES + r * 128;
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
-                                    v[4 * j] = (v[4 * j] + a[j].x) + bq[j].x; v[4 * j + 1] = (v[4 * j + 1] + a[j].y) + bq[j].y;
-                                    v[4 * j + 2] = (v[4 * j + 2] + a[j].z) + bq[j].z; v[4 * j + 3] = (v[4 * j + 3] + a[j].w) + bq[j].w;
+                                    const float4 a = *reinterpret_cast<const float4*>(pb + ((j ^ (r & 7)) << 4));
+                                    v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
                                 }
-                            }
-                            if (z < p.splits) {
-                                float4 a[8];
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) a[j] = __ldcg(s4 + (size_t)z * plane4 + j);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) { v[4 * j] += a[j].x; v[4 * j + 1] += a[j].y; v[4 * j + 2] += a[j].z; v[4 * j + 3] += a[j].w; }
                             }
                         }
                     } else {
@@ -883,16 +900,8 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
             const bool valid = in_box && ox < p.W && oy < p.H && bb < p.B;
             const long long grow = ((long long)bb * p.H + oy) * p.W + ox;
             float ln_rstd = 1.f, ln_nm = 0.f;                    // out = acc * rstd + (-mean * rstd) * colsum[n] + bias'[n]
-            if (p.ln_stats && valid) {
-                const float2* rs = p.ln_stats + (size_t)grow * p.ln_parts;
-                double sm = 0.0, sq = 0.0;
-                for (int i = 0; i < p.ln_parts; ++i) { const float2 t2 = __ldcg(rs + i); sm += (double)t2.x; sq += (double)t2.y; }
-                const double mean = sm * (double)p.ln_inv_c;
-                double var = sq * (double)p.ln_inv_c - mean * mean;
-                if (var < 0.0) var = 0.0;
-                ln_rstd = (float)(1.0 / sqrt(var + (double)p.ln_eps));
-                ln_nm = -(float)mean * ln_rstd;
-            }
+            if (p.ln_stats && valid)
+                ln_row_stats(p.ln_stats + (size_t)grow * p.ln_parts, p.ln_parts, p.ln_inv_c, p.ln_eps, ln_rstd, ln_nm);
             const int stat_rows = p.TB > 1 ? p.rows : p.TW * min(p.TH, p.H - h0);
             auto cstat_flush = [&](int cc) {
                 const int rps = p.TW * p.TH;
@@ -1488,7 +1497,7 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
             const int fixed_p = fixed_smem(bn, p.epi_res != 0) + PERS_EPI_BUFS * p.epi_buf_stride + ADD_ROWS * bn * 4 + 2 * 4 * 32 * 8 + bn * 4;
             int st = (232448 - fixed_p) / stage_smem(bn, false);
             if (st > MAX_STAGES) st = MAX_STAGES;
-            if (st < 3) g->persistent = false;
+            if (st < 3 && !(st == 2 && p.total_kb <= 8)) g->persistent = false;   // 2 stages only where the whole K loop is a handful of k-blocks
             else {
                 p.stages = st;
                 g->smem_bytes = fixed_p + st * stage_smem(bn, false);
@@ -1536,7 +1545,11 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, TC_THREADS, (size_t)g->smem_bytes);
         if (occ > (g->co_resident ? 2 : 1)) occ = g->co_resident ? 2 : 1;
         const long long capacity = (long long)sms * occ;
-        p.fixup = (occ > 0 && (long long)m_tiles * n_tiles <= 1024 && total_ctas <= capacity) ? 1 : 0;
+        // partial planes come back through TMA into the pipeline stages behind the output ring: at least two 16 KiB landing buffers
+        int fix_nb = (stages * per_stage - EPI_BUFS * p.epi_buf_stride) / RES_BUF_BYTES;
+        if (fix_nb > 8) fix_nb = 8;
+        p.fix_nb = fix_nb;
+        p.fixup = (occ > 0 && fix_nb >= 2 && (long long)m_tiles * n_tiles <= 1024 && total_ctas <= capacity) ? 1 : 0;
         if (!p.fixup) {
             if (want_extras) {
                 // the fused LayerNorm work needs the final epilogue inside this kernel: fewer splits until the grid is co-resident

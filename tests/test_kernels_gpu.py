@@ -537,8 +537,7 @@ def test_tc_gemm_layernorm_fold(dev, case):
         lib.sdk_tc_gemm_destroy(h)
     for nm, info, sp in (("producer", infos[0], sp1), ("consumer", infos[1], sp2)):
         print(f"{name} {nm}: block_n={info[0]} splits={info[1]} grid=({info[2]},{info[3]}) fixup={info[9]} persistent={info[10]}")
-        if sp > 1:
-            assert info[1] > 1 and info[9] == 1, "split-K with fused LayerNorm work must be reduced inside the kernel"
+        assert info[1] == 1 or info[9] == 1, "split-K with fused LayerNorm work must be reduced inside the kernel (or not split)"
     x = ref_conv([a], w1, b1, 1, 1, False, None, resid, False)            # [1,1,M,C] fp32
     assert rel_l2(out1, x) < 2e-5
     assert rel_l2(out1_bf.float(), out1.bfloat16().float()) == 0.0           # the copy is the rounded fp32 output
