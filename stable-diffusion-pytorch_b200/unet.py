@@ -324,14 +324,14 @@ class StepProgram:
         d.bias, d.tbias, d.tb_stride, d.residual, d.out = p.bias, p.tbias, p.tb_stride, p.residual, p.out
         d.out_dtype, d.geglu, d.out_nchw = p.out_dtype, p.geglu, p.out_nchw
         d.block_n, d.splits, d.w_kmajor, d.two_cta = self.net.tc_block_n, self.net.tc_splits, 1, self.net.tc_two_cta
-        if self.net.tc_autotune and not d.block_n and not d.splits:
-            d.block_n, d.splits, d.two_cta = self._autotune(d, srcs[0][0], cs)
         if extras:
             if "out2" in extras:
                 d.out2, d.row_stats = extras["out2"].data_ptr(), extras["row_stats"].data_ptr()
             if "ln_stats" in extras:
                 d.ln_stats, d.ln_colsum = extras["ln_stats"].data_ptr(), extras["ln_colsum"].data_ptr()
                 d.ln_parts, d.ln_eps = extras["ln_parts"], 1e-5
+        if self.net.tc_autotune and not d.block_n and not d.splits:
+            d.block_n, d.splits, d.two_cta = self._autotune(d, srcs[0][0], cs)
         h = C.c_void_p()
         rc = self.lib.sdk_tc_gemm_create(C.byref(d), C.byref(h))
         if rc == -3 and extras:
@@ -375,7 +375,10 @@ class StepProgram:
         if cls._tune_loaded:
             return
         cls._tune_loaded = True
-        for path in (cls._tune_shipped, cls._tune_user_file()):     # the user's own measurements win
+        paths = (cls._tune_shipped, cls._tune_user_file())
+        if os.environ.get("SDB200_TC_TUNE_IGNORE_SHIPPED", "0") == "1":   # re-measuring after a kernel change
+            paths = paths[1:]
+        for path in paths:                                          # the user's own measurements win
             try:
                 with open(path) as f:
                     cls._tune_cache.update({k: tuple(v) for k, v in json.load(f).items()})
@@ -413,6 +416,8 @@ class StepProgram:
         StepProgram._tune_load()
         key = "|".join(str(x) for x in (torch.cuda.get_device_name(self.device), d.B, d.H, d.W, d.N, d.nseg, d.C[0], d.ksize[0], d.C[1],
                                         d.geglu, d.out_dtype, int(bool(d.residual)), int(bool(d.tbias)), int(cs is not None)))
+        if d.out2 or d.ln_stats:                              # fused LayerNorm work changes the epilogue: its own measurements
+            key += f"|ln{int(bool(d.out2))}{int(bool(d.ln_stats))}"
         hit = StepProgram._tune_cache.get(key)
         if hit is not None:
             return tuple(hit) if len(hit) == 3 else (hit[0], hit[1], d.two_cta)
