@@ -1,5 +1,9 @@
-// tcgen05 flash attention for head dims <= 64 (SD-1.5 level 0: D = 40, S = 4096; SD-2.1: D = 64, S up to 9216):
+// tcgen05 flash attention for head dims 40 / 64 / 80 / 160 (SD-1.5: D = 40 at S = 4096, 80 at 1024, 160 at 256 and 64; SD-2.1: D = 64
+// at every level), self-attention and the 77-key cross-attention alike:
 // out = softmax(q k^T * scale) v per (batch, head)   (models/unet/attention.py:29-50).
+// Head dims above 64 span several 64-wide swizzle atoms: every operand tile is NA = ceil(D/64) atoms side by side (one TMA box
+// each, the last one zero-filled past D), Q K^T walks its K steps across the atoms, and P V issues one MMA per atom (N = 64, or
+// the 16 / 32 remaining columns), each into its own TMEM column range -- no descriptor spans more than one atom.
 //
 // CTA = 128 queries x one head; K/V stream in 64-key tiles.  Both contractions run on the 5th-gen tensor cores with
 // TMEM accumulators, operands fetched by TMA straight out of the fused [B][S][3C] qkv buffer:
@@ -30,10 +34,21 @@
 namespace {
 
 constexpr int BQ = 128, BKV = 64, DP = 64, AT_THREADS = 64 + 256;     // TMA warp, MMA warp, 8 softmax warps
-constexpr int Q_BYTES = BQ * DP * 2;                 // 16 KiB: [128][64] bf16
-constexpr int KV_BYTES = BKV * DP * 2;               //  8 KiB: [64][64] bf16
+constexpr int Q_BYTES = BQ * DP * 2;                 // 16 KiB: one [128][64] bf16 atom of Q
+constexpr int KV_BYTES = BKV * DP * 2;               //  8 KiB: one [64][64] bf16 atom of K / V
 constexpr int P_BYTES = BQ * BKV * 2;                // 16 KiB: [128][64] bf16
-constexpr int KV_STAGES = 3;
+
+// per-head-dim geometry
+template <int D> struct AttnGeo {
+    static constexpr int NA = (D + 63) / 64;                       // 64-wide atoms per operand row
+    static constexpr int OW = D <= 64 ? 64 : D;                    // TMEM columns of one stream's P.V accumulator
+    static constexpr int KV_STAGES = NA >= 3 ? 2 : 3;              // K / V ring depth (shared memory budget)
+    static constexpr int TMEM_COLS = 128 + 2 * OW <= 256 ? 256 : 512;
+    static constexpr int SMEM = NA * Q_BYTES + 2 * KV_STAGES * NA * KV_BYTES + 2 * P_BYTES + 1024 + 256 + 2 * 128 * 8;
+    static constexpr int CTAS = (TMEM_COLS <= 256 && SMEM <= 113 * 1024) ? 2 : 1;
+    // columns of the last atom's P.V MMA (a multiple of 16); full atoms use 64
+    static constexpr int N_LAST = D <= 64 ? 64 : ((D - 64 * (NA - 1) + 15) / 16) * 16;
+};
 
 struct alignas(64) AttnParams {
     CUtensorMap tmQ, tmK, tmV;
@@ -57,17 +72,21 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(AT_THREADS, AttnGeo<D>::CTAS)
 attention_tc_kernel(const __grid_constant__ AttnParams p) {
+    using G = AttnGeo<D>;
+    constexpr int NA = G::NA, OW = G::OW, KV_STAGES = G::KV_STAGES;
     constexpr int KS = (D + 15) / 16;                                  // K=16 steps of Q K^T (zero padded past D)
+    constexpr int KV_STAGE_BYTES = NA * KV_BYTES;
     constexpr uint32_t IDESC_S = ptx::umma_idesc_bf16(128, BKV);       // 128 x 64, both operands K-major
-    constexpr uint32_t IDESC_O = ptx::umma_idesc_bf16(128, DP) | (1u << 16);   // 128 x 64, B (= V) MN-major
+    constexpr uint32_t IDESC_O = ptx::umma_idesc_bf16(128, DP) | (1u << 16);            // 128 x 64, B (= V) MN-major
+    constexpr uint32_t IDESC_OL = ptx::umma_idesc_bf16(128, G::N_LAST) | (1u << 16);    // last atom: 128 x (16 | 32 | 64)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + Q_BYTES;                                        // [KV_STAGES]
-    uint8_t* sV = sK + KV_STAGES * KV_BYTES;                           // [KV_STAGES]
-    uint8_t* sP = sV + KV_STAGES * KV_BYTES;                           // [2]
+    uint8_t* sQ = smem;                                                // [NA] atoms
+    uint8_t* sK = sQ + NA * Q_BYTES;                                   // [KV_STAGES][NA]
+    uint8_t* sV = sK + KV_STAGES * KV_STAGE_BYTES;                     // [KV_STAGES][NA]
+    uint8_t* sP = sV + KV_STAGES * KV_STAGE_BYTES;                     // [2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
     uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 4, *v_full = bars + 7, *v_empty = bars + 10,
              *s_full = bars + 13 /* [2] */, *p_full = bars + 15 /* [2] */, *pv_done = bars + 17 /* [2] */;
@@ -89,7 +108,7 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmQ); ptx::prefetch_tmap(&p.tmK); ptx::prefetch_tmap(&p.tmV);
     }
-    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, G::TMEM_COLS); ptx::tmem_relinquish(); }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -99,30 +118,34 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
 
     if (warp == 0) {
         if (lane == 0) {
-            ptx::mbar_expect_tx(q_full, Q_BYTES);
-            ptx::tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
+            ptx::mbar_expect_tx(q_full, NA * Q_BYTES);
+#pragma unroll
+            for (int a = 0; a < NA; ++a) ptx::tma_load_4d(sQ + a * Q_BYTES, &p.tmQ, q_full, a * DP, h, q0, b);
             int st = 0; uint32_t ph = 0;
             for (int t = 0; t < ntiles; ++t) {
                 ptx::mbar_wait(&k_empty[st], ph ^ 1u);
-                ptx::mbar_expect_tx(&k_full[st], KV_BYTES);
-                ptx::tma_load_4d(sK + st * KV_BYTES, &p.tmK, &k_full[st], 0, h, t * BKV, kvb);
+                ptx::mbar_expect_tx(&k_full[st], KV_STAGE_BYTES);
+#pragma unroll
+                for (int a = 0; a < NA; ++a) ptx::tma_load_4d(sK + st * KV_STAGE_BYTES + a * KV_BYTES, &p.tmK, &k_full[st], a * DP, h, t * BKV, kvb);
                 ptx::mbar_wait(&v_empty[st], ph ^ 1u);
-                ptx::mbar_expect_tx(&v_full[st], KV_BYTES);
-                ptx::tma_load_4d(sV + st * KV_BYTES, &p.tmV, &v_full[st], 0, h, t * BKV, kvb);
+                ptx::mbar_expect_tx(&v_full[st], KV_STAGE_BYTES);
+#pragma unroll
+                for (int a = 0; a < NA; ++a) ptx::tma_load_4d(sV + st * KV_STAGE_BYTES + a * KV_BYTES, &p.tmV, &v_full[st], a * DP, h, t * BKV, kvb);
                 if (++st == KV_STAGES) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint64_t dq = ptx::umma_smem_desc_sw128(ptx::smem_u32(sQ));
             int kst = 0; uint32_t kph = 0;                               // K ring position of the next Q K^T
             auto issue_qk = [&](int t) {
                 ptx::mbar_wait(&k_full[kst], kph);
                 ptx::tc_fence_after();
-                const uint64_t dk = ptx::umma_smem_desc_sw128(ptx::smem_u32(sK + kst * KV_BYTES));
 #pragma unroll
-                for (int k = 0; k < KS; ++k)
-                    ptx::umma_bf16(tmem_base + (uint32_t)(t & 1) * 64u, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), IDESC_S, k > 0 ? 1u : 0u);
+                for (int k = 0; k < KS; ++k) {                          // K step k lives in atom k / 4, +32 B per step inside the atom
+                    const uint64_t dq = ptx::umma_smem_desc_sw128(ptx::smem_u32(sQ + (k >> 2) * Q_BYTES));
+                    const uint64_t dk = ptx::umma_smem_desc_sw128(ptx::smem_u32(sK + kst * KV_STAGE_BYTES + (k >> 2) * KV_BYTES));
+                    ptx::umma_bf16(tmem_base + (uint32_t)(t & 1) * 64u, dq + (uint64_t)((k & 3) * 2), dk + (uint64_t)((k & 3) * 2), IDESC_S, k > 0 ? 1u : 0u);
+                }
                 ptx::umma_commit(&k_empty[kst]);
                 ptx::umma_commit(&s_full[t & 1]);
                 if (++kst == KV_STAGES) { kst = 0; kph ^= 1u; }
@@ -137,14 +160,17 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
                 ptx::mbar_wait(&p_full[t & 1], (uint32_t)(t >> 1) & 1u);
                 ptx::tc_fence_after();
                 const uint64_t dp = ptx::umma_smem_desc_sw128(ptx::smem_u32(sP + (t & 1) * P_BYTES));
-                const uint64_t dv = umma_desc_mn_sw128(ptx::smem_u32(sV + vst * KV_BYTES));
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const uint64_t da = dp + (uint64_t)((hh * 2 + k) * 2);                       // +32 B per 16 keys inside the 64-key atom
-                        const uint64_t db = dv + (uint64_t)((hh * 2 + k) * 16 * 128 >> 4);           // +16 key rows of 128 B
-                        ptx::umma_bf16(tmem_base + 128 + hh * 64, da, db, IDESC_O, (t > 0 || k > 0) ? 1u : 0u);
+                    for (int a = 0; a < NA; ++a) {                      // one MMA per 64-wide atom of V (the last one narrower)
+                        const uint64_t dv = umma_desc_mn_sw128(ptx::smem_u32(sV + vst * KV_STAGE_BYTES + a * KV_BYTES));
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const uint64_t da = dp + (uint64_t)((hh * 2 + k) * 2);                       // +32 B per 16 keys inside the 64-key atom
+                            const uint64_t db = dv + (uint64_t)((hh * 2 + k) * 16 * 128 >> 4);           // +16 key rows of 128 B
+                            ptx::umma_bf16(tmem_base + 128 + hh * OW + a * 64, da, db, a == NA - 1 ? IDESC_OL : IDESC_O, (t > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
                 }
                 ptx::umma_commit(&v_empty[vst]);
@@ -163,7 +189,7 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
         const int half = (warp - 2) >> 2;
         const int r = qd * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
-        const uint32_t oaddr = taddr + 128 + half * 64;                  // this stream's accumulator (64 columns, D <= 64 used)
+        const uint32_t oaddr = taddr + 128 + half * OW;                  // this stream's accumulator (OW columns, D of them used)
         const int swz = r & 7;
         constexpr float RAISE = 8.f;                                     // raise the running max only beyond 2^8 of head room
         float m_sc = -INFINITY;                                          // running max * scale*log2(e) (the exponent offset in use)
@@ -194,7 +220,7 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
                 l_run *= corr;
                 uint32_t w[8];
 #pragma unroll 1
-                for (int c = 0; c < DP / 8; ++c) {                   // 8 columns at a time: S stays in registers
+                for (int c = 0; c < (D <= 64 ? DP : D) / 8; ++c) {   // 8 columns at a time: S stays in registers
                     ptx::tmem_ld8(oaddr + c * 8, w);
                     ptx::tmem_ld_wait();
 #pragma unroll
@@ -239,6 +265,7 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
         const float e_me = ex2(m_sc - m_all), e_ot = ex2(other.x - m_all);
         const float inv = 1.f / (l_run * e_me + other.y * e_ot);
         const float w_me = e_me * inv, w_ot = e_ot * inv;
+        if constexpr (D <= 64) {
         constexpr int OD = 32;                                           // output columns per thread (stream 1 stores D - 32 of them)
         const int my_d0 = half * 32;
         const int my_nd = half == 0 ? (D < 32 ? D : 32) : D - 32;
@@ -249,7 +276,7 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < OD; ++j) o[j] = __uint_as_float(u[j]) * w_me;
-            ptx::tmem_ld32(taddr + 128 + (half ^ 1) * 64 + my_d0, u); // the other stream's accumulator
+            ptx::tmem_ld32(taddr + 128 + (half ^ 1) * OW + my_d0, u); // the other stream's accumulator
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < OD; ++j) o[j] = fmaf(__uint_as_float(u[j]), w_ot, o[j]);
@@ -268,10 +295,36 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
                 }
             }
         }
+        } else {
+            // D = 80 / 160: the two threads of a row each write half of the head's columns, 8 at a time
+            constexpr int DH = D / 2;
+            static_assert(DH % 8 == 0, "half a head must be a whole number of 16-byte stores");
+            const int my_d0 = half * DH;
+            const bool row_ok = q0 + r < p.Sq;
+            __nv_bfloat16* op = p.out + (size_t)b * p.o_batch + (size_t)(q0 + r) * p.o_row + (size_t)h * D + my_d0;
+#pragma unroll 1
+            for (int i = 0; i < DH; i += 8) {
+                uint32_t u0[8], u1[8];
+                ptx::tmem_ld8(oaddr + my_d0 + i, u0);
+                ptx::tmem_ld8(taddr + 128 + (half ^ 1) * OW + my_d0 + i, u1);
+                ptx::tmem_ld_wait();
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = fmaf(__uint_as_float(u1[j]), w_ot, __uint_as_float(u0[j]) * w_me);
+                if (row_ok) {
+                    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b2 = __floats2bfloat162_rn(o[2], o[3]);
+                    __nv_bfloat162 c2 = __floats2bfloat162_rn(o[4], o[5]), d2 = __floats2bfloat162_rn(o[6], o[7]);
+                    uint4 w;
+                    w.x = *reinterpret_cast<uint32_t*>(&a); w.y = *reinterpret_cast<uint32_t*>(&b2);
+                    w.z = *reinterpret_cast<uint32_t*>(&c2); w.w = *reinterpret_cast<uint32_t*>(&d2);
+                    *reinterpret_cast<uint4*>(op + i) = w;
+                }
+            }
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 256); }
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, G::TMEM_COLS); }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -306,7 +359,7 @@ struct AttnPlan { AttnParams prm; dim3 grid; int D; };
 
 template <int D>
 int launch(const AttnPlan* a, cudaStream_t s) {
-    constexpr int smem = Q_BYTES + 2 * KV_STAGES * KV_BYTES + 2 * P_BYTES + 1024 + 256 + 2 * 128 * 8;
+    constexpr int smem = AttnGeo<D>::SMEM;
     SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(attention_tc_kernel<D>), (int)smem));
     SDK_CUDA(sdk_launch(attention_tc_kernel<D>, a->grid, dim3(AT_THREADS), (size_t)smem, s, a->prm));
     return SDK_OK;
@@ -319,7 +372,7 @@ extern "C" int sdk_attention_tc_create(const void* q, int64_t q_row, int64_t q_b
                                        const void* v, int64_t v_row, int64_t v_batch, void* out, int64_t o_row, int64_t o_batch,
                                        int B, int heads, int Sq, int Sk, int D, float scale, void** handle) {
     SDK_CHECK_ARG(q && k && v && out && handle, "sdk_attention_tc_create: null pointer");
-    SDK_CHECK_ARG(D == 40 || D == 64, "sdk_attention_tc_create: head_dim %d not in {40, 64}", D);
+    SDK_CHECK_ARG(D == 40 || D == 64 || D == 80 || D == 160, "sdk_attention_tc_create: head_dim %d not in {40, 64, 80, 160}", D);
     SDK_CHECK_ARG(B > 0 && heads > 0 && Sq > 0 && Sk > 0 && B * heads < 65536, "sdk_attention_tc_create: bad sizes");
     SDK_CHECK_ARG((q_row % 8) == 0 && (k_row % 8) == 0 && (v_row % 8) == 0 && (q_batch % 8) == 0 && (k_batch % 8) == 0 && (v_batch % 8) == 0 &&
                   (o_row % 8) == 0 && (o_batch % 8) == 0, "sdk_attention_tc_create: strides must keep rows 16-byte aligned");
@@ -345,7 +398,13 @@ extern "C" int sdk_attention_tc_create(const void* q, int64_t q_row, int64_t q_b
 extern "C" int sdk_attention_tc_launch(void* handle, void* stream) {
     SDK_CHECK_ARG(handle, "sdk_attention_tc_launch: null handle");
     AttnPlan* a = (AttnPlan*)handle;
-    return a->D == 40 ? launch<40>(a, (cudaStream_t)stream) : launch<64>(a, (cudaStream_t)stream);
+    switch (a->D) {
+        case 40: return launch<40>(a, (cudaStream_t)stream);
+        case 64: return launch<64>(a, (cudaStream_t)stream);
+        case 80: return launch<80>(a, (cudaStream_t)stream);
+        case 160: return launch<160>(a, (cudaStream_t)stream);
+    }
+    return sdk_fail(SDK_ERR_ARG, "sdk_attention_tc_launch: head_dim %d", a->D);
 }
 
 extern "C" int sdk_attention_tc_destroy(void* handle) {

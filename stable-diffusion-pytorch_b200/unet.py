@@ -535,7 +535,7 @@ class StepProgram:
 
     def _attention(self, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch, B, heads, Sq, Sk, D, Cc):
         out = self.pool.get(B * Sq, Cc, self.act)
-        if self.act != F32_T and D in (40, 64) and self.net.attn_tc:
+        if self.act != F32_T and D in (40, 64, 80, 160) and self.net.attn_tc:
             # tcgen05 flash attention (S and P.V on the tensor core, thread-per-row softmax)
             h = C.c_void_p()
             _lib.check(self.lib.sdk_attention_tc_create(q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch,
@@ -590,7 +590,7 @@ class StepProgram:
         # bf16 program: the three LayerNorms (unet.py:137,141,147) are FOLDED into the projections that consume them -- the
         # producer's epilogue also writes a bf16 copy of the row and its (sum, sum of squares) partials, the consumer multiplies the
         # raw rows by gamma-scaled weights and normalises in ITS epilogue: no LayerNorm launch, no extra pass over the tensor.
-        fold = self.act != F32_T and self.net.ln_fold
+        fold = self.act != F32_T and self.net.ln_fold and M >= self.net.ln_fold_min_rows
 
         def drop(tn):                                           # release a LayerNorm producer together with its side outputs
             for extra in ("_bf16", "_rowstats"):
@@ -871,8 +871,9 @@ class UNet(nn.Module):
         self.tc_splits = int(os.environ.get("SDB200_TC_SPLITS", "0"))
         self.tc_tune_pairs = int(os.environ.get("SDB200_TC_TUNE_PAIRS", "0"))   # also try cta_group::2 pairs when measuring tilings
         self.tc_autotune = int(os.environ.get("SDB200_TC_AUTOTUNE", "1"))     # 0 model | 1 committed cache | 2 measure misses | 3 and print
-        self.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention for head_dim 40 / 64
+        self.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention (head_dim 40 / 64 / 80 / 160); 0: mma.sync kernel
         self.ln_fold = os.environ.get("SDB200_LN_FOLD", "1") != "0"          # bf16: LayerNorm folded into the consuming GEMM (0: layernorm kernel)
+        self.ln_fold_min_rows = int(os.environ.get("SDB200_LN_FOLD_MIN_ROWS", "0"))   # ... only for token counts >= this (small ones are split-K GEMMs)
         self.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
         # sums: statistics from per-channel sums reduced in the producing GEMM's epilogue (bf16 program; fastest measured) |
         # split (stats + apply kernels) | cluster | coop | auto

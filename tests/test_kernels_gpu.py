@@ -290,12 +290,15 @@ def test_attention(dev, case, mode):
 
 
 ATT_TC_CASES = [(2, 8, 4096, 4096, 40), (1, 8, 1024, 77, 40), (2, 5, 2304, 2304, 64), (2, 8, 200, 333, 40), (1, 10, 576, 77, 64),
-                (3, 8, 128, 128, 40), (2, 8, 256, 40, 40), (1, 5, 300, 9216, 64)]
+                (3, 8, 128, 128, 40), (2, 8, 256, 40, 40), (1, 5, 300, 9216, 64),
+                # head dims spanning several swizzle atoms (SD-1.5 levels 1 / 2 / mid), self- and 77-key cross-attention
+                (2, 8, 1024, 1024, 80), (2, 8, 1024, 77, 80), (2, 8, 256, 256, 160), (2, 8, 256, 77, 160), (2, 8, 64, 64, 160),
+                (2, 8, 64, 77, 160), (16, 8, 1024, 1024, 80), (3, 8, 200, 333, 80), (1, 8, 100, 130, 160)]
 
 
 @pytest.mark.parametrize("case", ATT_TC_CASES)
 def test_attention_tc(dev, case):
-    """tcgen05 flash attention (head_dim 40 / 64) vs fp32 softmax(QK^T/sqrt(D))V on the bf16-rounded inputs."""
+    """tcgen05 flash attention (head_dim 40 / 64 / 80 / 160) vs fp32 softmax(QK^T/sqrt(D))V on the bf16-rounded inputs."""
     B, Hh, Sq, Sk, D = case
     lib = _lib.lib()
     Cc = Hh * D
