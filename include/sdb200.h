@@ -194,6 +194,12 @@ typedef struct SdkTcGemmDesc {
     const float* ln_colsum;
     int ln_parts;
     float ln_eps;
+    /* --- conv gathers folded into the TMA coordinates (no im2col / upsampled tensor in memory); one 3x3 k-block-major segment --- */
+    int a_stride;             /* 2: stride-2 3x3 conv, pad 1 (unet.py:236-240): `a` is the INPUT image [B][a_h][a_w][C], H x W the output size */
+    int a_h, a_w;
+    int up2;                  /* 1: nearest-2x upsample + 3x3 conv (unet.py:248-251): `a` is the LOW-RES input [B][H][W][C], `out` is
+                                 [B][2H][2W][N]; `w` holds FOUR parity sets of 2x2 taps, [py][px][2][2][C/64][N][64] (3x3 taps that
+                                 read the same input pixel pre-summed by the host) */
 } SdkTcGemmDesc;
 int sdk_tc_gemm_create(const SdkTcGemmDesc* desc, void** handle);
 int64_t sdk_tc_gemm_workspace_bytes(void* handle);

@@ -77,6 +77,13 @@ struct alignas(64) TcParams {
     //   out = rstd[m] * (acc[m][n] - mean[m] * ln_colsum[n]) + bias'[n]      (bias' = bias + W beta, packed by the host)
     // mean / rstd come from ln_stats [M][ln_parts] (the producer's row_stats), ln_colsum[n] = sum_k W'[n][k].
     const float2* ln_stats; const float* ln_colsum; int ln_parts; float ln_eps, ln_inv_c;
+    // ---- conv gathers folded into the TMA coordinates (unet.py:236,250)
+    //   a_stride = 2: stride-2 3x3 conv -- the A box walks the INPUT image with element stride 2, starting at (2*w0 + dx, 2*h0 + dy)
+    //   up2 = 1: nearest-2x upsample + 3x3 conv as four 2x2 convolutions on the LOW-RES input, one per output parity (py, px):
+    //            output pixel (2y+py, 2x+px) sees input rows {y-1+py, y+py} and columns {x-1+px, x+px}; the host pre-sums the 3x3 taps
+    //            that fall on the same input pixel.  The parity is the outermost factor of the m-tile index; the output tensor map
+    //            is {N, x, (b,y), px, py} over the [B][2H][2W][N] tensor.
+    int a_stride, up2;
 };
 
 __device__ __forceinline__ void stamp(const TcParams& p, int slot) {
@@ -268,7 +275,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     int t = blockIdx.x;
     const int tw = t % p.tiles_w; t /= p.tiles_w;
     const int th = t % p.tiles_h; t /= p.tiles_h;
-    const int tb = t;
+    const int tb = t % p.tiles_b;
+    const int par = t / p.tiles_b;                     // output parity 2*py + px of a folded upsample (0 otherwise)
     const int w0 = tw * p.TW, h0 = th * p.TH, b0 = tb * p.TB;
     const int n0 = blockIdx.y * BN;
     const int kb_begin = blockIdx.z * p.kb_per_split;
@@ -313,6 +321,9 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
                 int dx = 0, dy = 0;
                 if (p.seg_ksize[seg] == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
+                else if (p.seg_ksize[seg] == 2) { dy = (tap >> 1) + (par >> 1) - 1; dx = (tap & 1) + (par & 1) - 1; }
+                const int wk = tap * p.seg_kb[seg] + kb + par * 4 * p.seg_kb[seg];     // k-block of the weights (parity sets are stacked)
+                const int ax = w0 * p.a_stride + dx, ay = h0 * p.a_stride + dy;
                 ptx::mbar_wait(&empty[s], ph ^ 1u);
                 if (TWO) {
                     const int nb = n0 + (int)rank * B_ROWS;              // this CTA's half of the B tile
@@ -323,8 +334,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                     else ptx::mbar_arrive_remote(&full[s], 0);
                 } else {
                     ptx::mbar_expect_tx(&full[s], stage_bytes);
-                    ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 + dx, h0 + dy, b0);
-                    if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, tap * p.seg_kb[seg] + kb);
+                    ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, ax, ay, b0);
+                    if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, wk);
                     else ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, n0);
                 }
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -578,7 +589,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                     if (et == 0) ptx::bulk_wait_read<1>();
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (et == 0) {
-                        ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
+                        if (p.up2) ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, b0 * p.H + h0, par & 1, par >> 1);
+                        else ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
                         if (p.out2) ptx::tma_store_5d(&p.tmOut2, obuf + p.out2_off, n0 + c * 32, w0, h0, b0, 0);
                         ptx::bulk_commit();
                         if (p.epi_res && i + 2 < n_my) {   // every thread has consumed residual chunk i: refill its buffer
@@ -769,7 +781,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = p.N / BN;
-    const int total = p.tiles_w * p.tiles_h * p.tiles_b * n_tiles;
+    const int total = p.tiles_w * p.tiles_h * p.tiles_b * n_tiles * (p.up2 ? 4 : 1);
     const int n_it = p.total_kb;
 
     if (threadIdx.x == 0) {
@@ -792,11 +804,12 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
     pdl_wait();
 
     // tile id -> (pixel-tile origin, first output column, tile indices inside the image)
-    auto coords = [&](int t, int& w0, int& h0, int& b0, int& n0) {
+    auto coords = [&](int t, int& w0, int& h0, int& b0, int& n0, int& par) {
         const int ni = t % n_tiles; int m = t / n_tiles;
         const int tw = m % p.tiles_w; m /= p.tiles_w;
         const int th = m % p.tiles_h; m /= p.tiles_h;
-        w0 = tw * p.TW; h0 = th * p.TH; b0 = m * p.TB; n0 = ni * BN;
+        par = m / p.tiles_b;                           // output parity of a folded upsample (0 otherwise)
+        w0 = tw * p.TW; h0 = th * p.TH; b0 = (m % p.tiles_b) * p.TB; n0 = ni * BN;
     };
 
     if (warp == 0) {
@@ -806,18 +819,19 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
             const int seg0_its = p.seg_taps[0] * p.seg_kb[0];
             int s = 0; uint32_t ph = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                int w0, h0, b0, n0;
-                coords(t, w0, h0, b0, n0);
+                int w0, h0, b0, n0, par;
+                coords(t, w0, h0, b0, n0, par);
                 for (int i = 0; i < n_it; ++i) {
                     int it = i, seg = 0;
                     if (it >= seg0_its) { it -= seg0_its; seg = 1; }
                     const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
                     int dx = 0, dy = 0;
                     if (p.seg_ksize[seg] == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
+                    else if (p.seg_ksize[seg] == 2) { dy = (tap >> 1) + (par >> 1) - 1; dx = (tap & 1) + (par & 1) - 1; }
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     ptx::mbar_expect_tx(&full[s], stage_bytes);
-                    ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 + dx, h0 + dy, b0);
-                    if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, tap * p.seg_kb[seg] + kb);
+                    ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 * p.a_stride + dx, h0 * p.a_stride + dy, b0);
+                    if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, tap * p.seg_kb[seg] + kb + par * 4 * p.seg_kb[seg]);
                     else ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, n0);
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
@@ -871,8 +885,8 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
         uint32_t gc = 0;                                // output chunks this group has issued so far (ring position)
         int lt = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
-            int w0, h0, b0, n0;
-            coords(t, w0, h0, b0, n0);
+            int w0, h0, b0, n0, par;
+            coords(t, w0, h0, b0, n0, par);
             const int ab = lt & 1;
             const uint32_t taddr = tmem_base + (uint32_t)ab * TMEM_COLS + ((uint32_t)(q * 32) << 16);
             // this group's first residual chunk (the buffer is free: the group passed its last barrier of the previous tile)
@@ -992,7 +1006,8 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                 if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (et == 0) {
                     if (last) ptx::mbar_arrive(&acc_empty[ab]);          // (2 arrivals: both groups) the MMA warp may overwrite this buffer
-                    ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
+                    if (p.up2) ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, b0 * p.H + h0, par & 1, par >> 1);
+                    else ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
                     if (p.out2) ptx::tma_store_5d(&p.tmOut2, obuf + p.out2_off, n0 + c * 32, w0, h0, b0, 0);
                     ptx::bulk_commit();
                     if (p.epi_res && c + 2 < NCH) {
@@ -1212,6 +1227,23 @@ int encode_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int esiz
     return SDK_OK;
 }
 
+// general form: explicit byte strides of dimensions 1..rank-1 and per-dimension traversal (element) strides
+int encode_map_strided(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, const uint32_t* elem_strides, CUtensorMapSwizzle swz, CUtensorMapL2promotion promo) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return sdk_fail(SDK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[5]; cuuint64_t gstride[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = elem_strides ? elem_strides[i] : 1;
+        if (i < rank - 1) gstride[i] = strides_bytes[i];
+    }
+    CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sdk_fail(SDK_ERR_CUDA, "cuTensorMapEncodeTiled (strided) failed with %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
+                                           (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
+    return SDK_OK;
+}
+
 int encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint32_t* box, CUtensorMapL2promotion promo) {
     return encode_map(m, ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rank, dims, box, CU_TENSOR_MAP_SWIZZLE_128B, promo);
 }
@@ -1284,13 +1316,14 @@ const void* tc_kernel_ptr(int bn, bool two) {
     return nullptr;
 }
 
-void pick_tile(int W, int H, int B, int* TW, int* TH, int* TB) {
-    // rectangular pixel tile of <= 128 rows maximising MMA row occupancy
+void pick_tile(int W, int H, int B, int* TW, int* TH, int* TB, bool exact = false) {
+    // rectangular pixel tile of <= 128 rows maximising MMA row occupancy (exact: tiles may not overhang the image)
     double best = -1.0;
     int bw = 1, bh = 1, bb = 1;
     for (int w = 1; w <= 128 && w <= W; ++w) {
-        if (W % w != 0 && w != 128) continue;               // divisors of W, or the full 128-wide strip
+        if (W % w != 0 && (w != 128 || exact)) continue;    // divisors of W, or the full 128-wide strip
         int h = 128 / w; if (h > H) h = H; if (h < 1) h = 1;
+        if (exact) while (H % h != 0) --h;
         int b = 1;
         if (w == W && h == H) { b = 128 / (w * h); if (b > B) b = B; if (b < 1) b = 1; }
         const long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((B + b - 1) / b);
@@ -1313,7 +1346,17 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     if (!g) return sdk_fail(SDK_ERR_CUDA, "out of host memory");
     TcParams& p = g->prm;
     memset(&p, 0, sizeof(p));
-    pick_tile(d->W, d->H, d->B, &p.TW, &p.TH, &p.TB);
+    const bool up2 = d->up2 != 0, s2 = d->a_stride == 2;
+    if (up2 || s2) {
+        // conv gathers folded into the TMA coordinates: one 3x3 segment, k-block-major weights, NHWC output, no split-K / CTA pairs
+        if (!(d->nseg == 1 && d->ksize[0] == 3 && d->w_kmajor && !d->out_nchw && !(up2 && s2) && !(up2 && (d->residual || d->out2 || d->row_stats || d->ln_stats)) &&
+              (!s2 || (d->a_h > 0 && d->a_w > 0 && d->H == (d->a_h - 1) / 2 + 1 && d->W == (d->a_w - 1) / 2 + 1)))) {
+            delete g;
+            return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: folded upsample / stride-2 gather needs one 3x3 k-block-major segment and an NHWC output");
+        }
+    }
+    p.up2 = up2 ? 1 : 0; p.a_stride = s2 ? 2 : 1;
+    pick_tile(d->W, d->H, d->B, &p.TW, &p.TH, &p.TB, up2);
     p.rows = p.TW * p.TH * p.TB;
     p.W = d->W; p.H = d->H; p.B = d->B;
     p.tiles_w = (d->W + p.TW - 1) / p.TW; p.tiles_h = (d->H + p.TH - 1) / p.TH; p.tiles_b = (d->B + p.TB - 1) / p.TB;
@@ -1325,11 +1368,11 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
             delete g;
             return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: segment %d needs C %% 64 == 0 and ksize 1|3 (C=%d k=%d)", s, d->C[s], d->ksize[s]);
         }
-        p.seg_C[s] = d->C[s]; p.seg_ksize[s] = d->ksize[s];
-        p.seg_taps[s] = d->ksize[s] * d->ksize[s]; p.seg_kb[s] = d->C[s] / BK;
+        p.seg_C[s] = d->C[s]; p.seg_ksize[s] = up2 ? 2 : d->ksize[s];        // folded upsample: 2x2 taps per output parity
+        p.seg_taps[s] = p.seg_ksize[s] * p.seg_ksize[s]; p.seg_kb[s] = d->C[s] / BK;
         p.total_kb += p.seg_taps[s] * p.seg_kb[s];
     }
-    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b * (up2 ? 4 : 1);     // the four output parities of a folded upsample are m-tiles
     p.M = (long long)d->B * d->H * d->W;
     if (p.M >= (1ll << 24)) { delete g; return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_create: B*H*W = %lld output rows exceeds 2^24", p.M); }
     p.w_kmajor = d->w_kmajor;
@@ -1341,6 +1384,8 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     const int sms = sdk_num_sms();
     int bn = d->block_n, splits = d->splits;
     bool two = false;
+    const int want_splits = (up2 || s2) ? 1 : d->splits;      // folded gathers: the direct epilogue only
+    const int want_two = (up2 || s2) ? 1 : d->two_cta;
     {
         const int cands[5] = {256, 160, 128, 64, 32};
         double best = 1e30;
@@ -1350,8 +1395,8 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
             // pair == 1: cta_group::2 (256-row CTA pairs): needs an even number of m-tiles
             // Measured on B200 (profiles/r01_gemm_pairs.txt): the pair form is 1-5 % SLOWER than two independent CTAs on every
             // UNet shape (the 1-CTA kernel is not bound by the B-tile fill), so auto (0) never picks it; 2 forces it.
-            if (pair == 1 && (d->two_cta != 2 || (m_tiles & 1) || m_tiles < 2 || d->N < 128)) continue;
-            if (pair == 0 && d->two_cta == 2 && !(m_tiles & 1) && m_tiles >= 2 && d->N >= 128) continue;   // narrow outputs stay single-CTA
+            if (pair == 1 && (want_two != 2 || (m_tiles & 1) || m_tiles < 2 || d->N < 128)) continue;
+            if (pair == 0 && want_two == 2 && !(m_tiles & 1) && m_tiles >= 2 && d->N >= 128) continue;   // narrow outputs stay single-CTA
             for (int i = 0; i < 5; ++i) {
                 const int c = cands[i];
                 if (pair == 1 && c < 128) continue;
@@ -1362,12 +1407,12 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
                 }
                 const int n_t = (d->N + c - 1) / c;
                 const int tiles = m_tiles * n_t;
-                const int max_sp = d->splits ? d->splits : (p.total_kb / 4 > 0 ? (p.total_kb / 4 < 32 ? p.total_kb / 4 : 32) : 1);
-                for (int sp = (d->splits ? d->splits : 1); sp <= max_sp; ++sp) {
+                const int max_sp = want_splits ? want_splits : (p.total_kb / 4 > 0 ? (p.total_kb / 4 < 32 ? p.total_kb / 4 : 32) : 1);
+                for (int sp = (want_splits ? want_splits : 1); sp <= max_sp; ++sp) {
                     const int kb_cta = (p.total_kb + sp - 1) / sp;
                     const int real_sp = (p.total_kb + kb_cta - 1) / kb_cta;
-                    if (real_sp != sp && !d->splits) continue;
-                    if (pair == 1 && kb_cta < 8 && d->two_cta != 2) continue;  // pairing costs two cluster barriers: not for short K
+                    if (real_sp != sp && !want_splits) continue;
+                    if (pair == 1 && kb_cta < 8 && want_two != 2) continue;  // pairing costs two cluster barriers: not for short K
                     const long long ctas = (long long)tiles * real_sp;
                     const long long waves = (ctas + sms - 1) / sms;
                     const double active = (double)(ctas < sms ? ctas : sms);
@@ -1382,7 +1427,7 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
                     if (t < t_hbm) t = t_hbm;
                     if (real_sp > 1) t += 9000.0 + (double)real_sp * p.M * d->N * 8.0 / 2500.0;
                     if (t < best) { best = t; best_bn = c; best_sp = real_sp; best_two = pair == 1; }
-                    if (d->splits) break;
+                    if (want_splits) break;
                 }
             }
         }
@@ -1398,12 +1443,23 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     // ---- tensor maps
     int rc = SDK_OK;
     for (int s = 0; s < d->nseg && rc == SDK_OK; ++s) {
+        if (s2) {
+            // stride-2 gather: the box walks the input image with element stride 2 (2*TW x 2*TH elements -> TW x TH pixels)
+            const uint64_t adims[4] = {(uint64_t)d->C[s], (uint64_t)d->a_w, (uint64_t)d->a_h, (uint64_t)d->B};
+            const uint64_t astr[3] = {(uint64_t)d->C[s] * 2, (uint64_t)d->C[s] * 2 * d->a_w, (uint64_t)d->C[s] * 2 * d->a_w * d->a_h};
+            const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)(2 * p.TW), (uint32_t)(2 * p.TH), (uint32_t)p.TB};
+            const uint32_t aes[4] = {1u, 2u, 2u, 1u};
+            if (2 * p.TW > 256 || 2 * p.TH > 256) { rc = sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: stride-2 box too large"); break; }
+            rc = encode_map_strided(&p.tmA[s], d->a[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, adims, astr, abox, aes, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+        } else {
         const uint64_t adims[4] = {(uint64_t)d->C[s], (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
         const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB};
         rc = encode_bf16(&p.tmA[s], d->a[s], 4, adims, abox, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+        }
         if (rc != SDK_OK) break;
         if (d->w_kmajor) {
-            const uint64_t bdims[3] = {(uint64_t)BK, (uint64_t)d->N, (uint64_t)p.seg_taps[s] * p.seg_kb[s]};
+            const uint64_t bdims[3] = {(uint64_t)BK, (uint64_t)d->N, (uint64_t)p.seg_taps[s] * p.seg_kb[s] * (up2 ? 4 : 1)};
             const uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)(two ? bn / 2 : bn), 1u};
             rc = encode_bf16(&p.tmB[s], d->w[s], 3, bdims, bbox, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         } else {
@@ -1437,6 +1493,10 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         delete g;
         return sdk_fail(SDK_ERR_ARG, "sdk_tc_gemm_create: folded LayerNorm needs ln_colsum, ln_parts > 0 and the folded bias");
     }
+    if ((up2 || s2) && !direct_ok) {
+        delete g;
+        return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: folded upsample / stride-2 gather needs the direct TMA epilogue (N %% block_n == 0)");
+    }
     if (want_extras && !direct_ok) {
         delete g;
         return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: out2 / row_stats / folded LayerNorm need the direct TMA epilogue (N %% block_n == 0, <= %d samples per tile)", ADD_ROWS);
@@ -1449,9 +1509,17 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         p.epi_swz = p.epi_rowbytes == 128 ? 7 : p.epi_rowbytes == 64 ? 3 : 1;
         const uint64_t odims[5] = {(uint64_t)p.Nout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B, 1};
         const uint32_t obox[5] = {(uint32_t)p.epi_cols, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TB, 1};
-        rc = encode_map(&p.tmOut, d->out, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, bf ? 2 : 4, 5, odims, obox,
-                        p.epi_swz == 7 ? CU_TENSOR_MAP_SWIZZLE_128B : p.epi_swz == 3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
-                        CU_TENSOR_MAP_L2_PROMOTION_NONE);
+        const CUtensorMapSwizzle oswz = p.epi_swz == 7 ? CU_TENSOR_MAP_SWIZZLE_128B : p.epi_swz == 3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+        const CUtensorMapDataType odt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+        if (up2) {
+            // [B][2H][2W][N] output seen as {N, x, (b, y), px, py}: pixel (2y + py, 2x + px); (b, y) merge because 2H rows of 2W pixels follow each other
+            const uint64_t es = bf ? 2 : 4, rowb = (uint64_t)p.Nout * es;
+            const uint64_t udims[5] = {(uint64_t)p.Nout, (uint64_t)d->W, (uint64_t)d->B * d->H, 2, 2};
+            const uint64_t ustr[4] = {2 * rowb, 4 * (uint64_t)d->W * rowb, rowb, 2 * (uint64_t)d->W * rowb};
+            const uint32_t ubox[5] = {(uint32_t)p.epi_cols, (uint32_t)p.TW, (uint32_t)(p.TH * p.TB), 1, 1};
+            rc = encode_map_strided(&p.tmOut, d->out, odt, 5, udims, ustr, ubox, nullptr, oswz, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+        } else
+        rc = encode_map(&p.tmOut, d->out, odt, bf ? 2 : 4, 5, odims, obox, oswz, CU_TENSOR_MAP_L2_PROMOTION_NONE);
         if (rc == SDK_OK && d->residual) {
             p.epi_res = 1;
             const uint64_t rdims[4] = {(uint64_t)d->N, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};

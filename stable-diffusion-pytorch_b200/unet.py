@@ -148,6 +148,22 @@ class PackedWeights:
             if st.resample is not None:
                 p = st.resample.prefix
                 t[f"{p}.w"], t[f"{p}.b"] = conv_w(f"{p}.weight"), dev(sd[f"{p}.bias"])
+                if precision != "fp32" and st in a.up:
+                    # nearest-2x upsample + 3x3 conv (unet.py:248-251) == four 2x2 convs on the low-res input, one per output
+                    # parity: the 3x3 taps that land on the same input pixel are summed (fp32) before the bf16 rounding
+                    w = sd[f"{p}.weight"].to(device=device, dtype=torch.float32).permute(0, 2, 3, 1)          # [N][kh][kw][C]
+                    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+                    sets = []
+                    for py in (0, 1):
+                        for px in (0, 1):
+                            wp = torch.zeros((w.shape[0], 2, 2, w.shape[3]), dtype=torch.float32, device=device)
+                            for ia in (0, 1):
+                                for ib in (0, 1):
+                                    for kh in rows[py][ia]:
+                                        for kw in rows[px][ib]:
+                                            wp[:, ia, ib] += w[:, kh, kw]
+                            sets.append(dev(wp.reshape(w.shape[0], -1), torch.bfloat16))                      # k-block-major [4C/64][N][64]
+                    t[f"{p}.w_up2"] = torch.cat(sets, 0).contiguous()
         # cross-attention K/V projections of every transformer, rows concatenated: the context program is one [Bc*77, dctx] x
         # [sum 2C, dctx]^T GEMM (24960 output columns for SD1.5) instead of 16 launches; kv_off[index] = first column of a layer
         self.kv_off, self.kv_total = {}, 0
@@ -255,7 +271,7 @@ class StepProgram:
 
     def _conv(self, srcs, w, bias, B, Hin, Win, N, *, k=1, stride=1, up=False, tbias=0, tb_stride=0,
               residual=None, geglu=False, out_code=F32_T, out=None, out_nchw=False, in_code=None, ctx=False,
-              force_simt=False, seg2=None, want_stats=False, ln_out=False, ln_in=None):
+              force_simt=False, seg2=None, want_stats=False, ln_out=False, ln_in=None, fold_gather=False):
         """srcs: [(tensor[rows, C], C)] (1 or 2).  Returns the output tensor [M, N or N/2].
         want_stats: the output feeds a GroupNorm -> also produce its per-channel (sum, sum of squares) table (out._cstats).
         ln_out: the output feeds a LayerNorm that is folded into its consumer -> also produce a bf16 copy (out._bf16) and the per-row
@@ -296,7 +312,12 @@ class StepProgram:
                 extras = dict(out2=out._bf16, row_stats=out._rowstats)
             if ln_in is not None:
                 extras = dict(extras or {}, ln_stats=ln_in[0], ln_colsum=ln_in[1], ln_parts=srcs[0][1] // 32)
+            if fold_gather:
+                extras = dict(extras or {}, gather="up2" if up else "s2")
             fused = self._emit_tc_conv(p, srcs, w, ctx, seg2, cs, extras)
+            if fused is None:                               # folded gather not available for this shape: nothing was emitted
+                self.pool.put(out)
+                return None, Hout, Wout
         if want_stats:
             if not fused:                                   # producer cannot reduce its own columns: one extra small launch
                 self._emit(self.lib.sdk_channel_stats, out.data_ptr(), B, Hout * Wout, N, cs.data_ptr(), ctx=ctx)
@@ -314,13 +335,18 @@ class StepProgram:
 
     def _emit_tc_conv(self, p, srcs, w, ctx, seg2=None, cs=None, extras=None):
         """tcgen05 implicit GEMM for a stride-1 conv / linear described by ConvParams ``p``."""
-        if len(srcs) != 1 or p.stride != 1 or p.upsample:
-            raise RuntimeError("tensor-core conv takes one pre-concatenated, pre-upsampled bf16 source at stride 1")
+        gather = (extras or {}).get("gather")
+        if len(srcs) != 1 or ((p.stride != 1 or p.upsample) and not gather):
+            raise RuntimeError("tensor-core conv takes one pre-concatenated bf16 source (stride 2 / upsample only as folded gathers)")
         d = TcGemmDesc()
         d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = p.src0, p.weight, p.C0, p.ksize, 1
         if seg2 is not None:                                   # (activation [rows, C2] bf16, C2, 1x1 weights)
             d.a[1], d.C[1], d.w[1], d.ksize[1], d.nseg = seg2[0].data_ptr(), seg2[1], seg2[2].data_ptr(), 1, 2
         d.B, d.H, d.W, d.N = p.B, p.Hin, p.Win, p.N
+        if gather == "s2":                                     # stride-2 conv: tiles walk the OUTPUT image, the A box the input
+            d.H, d.W, d.a_stride, d.a_h, d.a_w = p.Hout, p.Wout, 2, p.Hin, p.Win
+        elif gather == "up2":                                  # folded upsample: tiles walk the low-res input, four parities
+            d.up2 = 1
         d.bias, d.tbias, d.tb_stride, d.residual, d.out = p.bias, p.tbias, p.tb_stride, p.residual, p.out
         d.out_dtype, d.geglu, d.out_nchw = p.out_dtype, p.geglu, p.out_nchw
         d.block_n, d.splits, d.w_kmajor, d.two_cta = self.net.tc_block_n, self.net.tc_splits, 1, self.net.tc_two_cta
@@ -334,6 +360,8 @@ class StepProgram:
             d.block_n, d.splits, d.two_cta = self._autotune(d, srcs[0][0], cs)
         h = C.c_void_p()
         rc = self.lib.sdk_tc_gemm_create(C.byref(d), C.byref(h))
+        if rc == -3 and gather:
+            return None                                         # caller falls back to the materialised gather
         if rc == -3 and extras:
             # the tuned tiling cannot carry the fused LayerNorm work (ragged N tile, or a split-K grid too large to reduce inside the
             # kernel): an exact N tile without split-K always can
@@ -418,6 +446,8 @@ class StepProgram:
                                         d.geglu, d.out_dtype, int(bool(d.residual)), int(bool(d.tbias)), int(cs is not None)))
         if d.out2 or d.ln_stats:                              # fused LayerNorm work changes the epilogue: its own measurements
             key += f"|ln{int(bool(d.out2))}{int(bool(d.ln_stats))}"
+        if d.up2 or d.a_stride == 2:
+            key += f"|g{'u' if d.up2 else 's'}"
         hit = StepProgram._tune_cache.get(key)
         if hit is not None:
             return tuple(hit) if len(hit) == 3 else (hit[0], hit[1], d.two_cta)
@@ -740,12 +770,19 @@ class StepProgram:
                 if self.act == F32_T:
                     y, h, w = self._conv([(x, xc)], wn, bn_, B, h, w, xc, k=3, stride=2, want_stats=True)
                 else:
-                    # stride-2 3x3 (unet.py:236): gather the 9 taps into bf16 rows, then a 1-tap tensor-core GEMM
+                    # stride-2 3x3 (unet.py:236): the A boxes walk the bf16 input with element stride 2 (no im2col matrix) ...
                     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-                    col = self.pool.get(B * ho * wo, 9 * xc, BF16_T)
-                    self._emit(lib.sdk_im2col_s2, x.data_ptr(), col.data_ptr(), B, h, w, xc)
-                    y, _, _ = self._conv([(col, 9 * xc)], wn, bn_, B, ho, wo, xc, k=1, want_stats=True)
-                    self.pool.put(col)
+                    y = None
+                    if self.net.fold_gathers:
+                        op, _ = self._operand(x, B, h, w, xc)
+                        y, _, _ = self._conv([(op, xc)], wn, bn_, B, h, w, xc, k=3, stride=2, want_stats=True, fold_gather=True)
+                        self.pool.put(op)
+                    if y is None:
+                        # ... or, for shapes the fold does not take: gather the 9 taps into bf16 rows, then a 1-tap tensor-core GEMM
+                        col = self.pool.get(B * ho * wo, 9 * xc, BF16_T)
+                        self._emit(lib.sdk_im2col_s2, x.data_ptr(), col.data_ptr(), B, h, w, xc)
+                        y, _, _ = self._conv([(col, 9 * xc)], wn, bn_, B, ho, wo, xc, k=1, want_stats=True)
+                        self.pool.put(col)
                     h, w = ho, wo
                 x = y
                 skips.append((x, xc, h, w))
@@ -778,13 +815,23 @@ class StepProgram:
                     x = y
             if st.resample is not None:
                 up = not (skips and skips[-1][3] == prev_w)          # unet.py:346-349
-                op, tmp = self._operand(x, B, h, w, xc, up=2 if (up and self.act != F32_T) else 1)
-                if up and self.act != F32_T:
-                    y, h, w = self._conv([(op, xc)], t[f"{st.resample.prefix}.w"], t[f"{st.resample.prefix}.b"], B, 2 * h, 2 * w, xc, k=3,
-                                         want_stats=True)
-                else:
-                    y, h, w = self._conv([(op, xc)], t[f"{st.resample.prefix}.w"], t[f"{st.resample.prefix}.b"], B, h, w, xc, k=3, up=up,
-                                         want_stats=True)
+                rp = st.resample.prefix
+                y = None
+                if up and self.act != F32_T and self.net.fold_gathers:
+                    # nearest-2x upsample folded into the conv: four 2x2 convs on the low-res bf16 input, one per output parity
+                    op, tmp = self._operand(x, B, h, w, xc)
+                    y, hn, wn_ = self._conv([(op, xc)], t[f"{rp}.w_up2"], t[f"{rp}.b"], B, h, w, xc, k=3, up=True, want_stats=True, fold_gather=True)
+                    if y is None:
+                        self.pool.put(op)
+                        tmp = False
+                    else:
+                        h, w = hn, wn_
+                if y is None:
+                    op, tmp = self._operand(x, B, h, w, xc, up=2 if (up and self.act != F32_T) else 1)
+                    if up and self.act != F32_T:
+                        y, h, w = self._conv([(op, xc)], t[f"{rp}.w"], t[f"{rp}.b"], B, 2 * h, 2 * w, xc, k=3, want_stats=True)
+                    else:
+                        y, h, w = self._conv([(op, xc)], t[f"{rp}.w"], t[f"{rp}.b"], B, h, w, xc, k=3, up=up, want_stats=True)
                 if tmp:
                     self.pool.put(op)
                 self.pool.put(x)
@@ -873,6 +920,7 @@ class UNet(nn.Module):
         self.tc_autotune = int(os.environ.get("SDB200_TC_AUTOTUNE", "1"))     # 0 model | 1 committed cache | 2 measure misses | 3 and print
         self.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention (head_dim 40 / 64 / 80 / 160); 0: mma.sync kernel
         self.ln_fold = os.environ.get("SDB200_LN_FOLD", "1") != "0"          # bf16: LayerNorm folded into the consuming GEMM (0: layernorm kernel)
+        self.fold_gathers = os.environ.get("SDB200_FOLD_GATHERS", "1") != "0"   # bf16: stride-2 / upsample gathers inside the GEMM's TMA coordinates
         self.ln_fold_min_rows = int(os.environ.get("SDB200_LN_FOLD_MIN_ROWS", "0"))   # ... only for token counts >= this (small ones are split-K GEMMs)
         self.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
         # sums: statistics from per-channel sums reduced in the producing GEMM's epilogue (bf16 program; fastest measured) |

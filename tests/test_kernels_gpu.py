@@ -472,6 +472,94 @@ def test_tc_gemm_channel_stats(dev, case):
     assert rel_l2(cs[0], cs[1]) < 1e-13                    # atomics in double: order-independent to the last bits
 
 
+def upsample_parity_weights(w):
+    """[N][3][3][C] conv weights -> [2][2][N][2][2][C]: the 3x3 taps of a conv over a nearest-2x upsampled image that read the same
+    low-res pixel, pre-summed per output parity (what PackedWeights does for sdk_tc_gemm up2)."""
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}                 # parity -> 3x3 taps folded onto input offsets (p-1, p)
+    n, _, _, c = w.shape
+    out = torch.zeros((2, 2, n, 2, 2, c), dtype=torch.float32, device=w.device)
+    for py in (0, 1):
+        for px in (0, 1):
+            for a in (0, 1):
+                for b in (0, 1):
+                    for kh in rows[py][a]:
+                        for kw in rows[px][b]:
+                            out[py, px, :, a, b] += w[:, kh, kw].float()
+    return out
+
+
+GATHER_CASES = [
+    # name, B, H_in, W_in, C, N, mode, block_n
+    ("up_L2", 2, 8, 8, 1280, 1280, "up2", 0),
+    ("up_L1", 2, 16, 16, 1280, 1280, "up2", 0),
+    ("up_L0", 2, 32, 32, 640, 640, "up2", 0),
+    ("up_batch3_bn64", 3, 16, 16, 320, 320, "up2", 64),
+    ("down_L0", 2, 64, 64, 320, 320, "s2", 0),
+    ("down_L1", 2, 32, 32, 640, 640, "s2", 0),
+    ("down_L2", 2, 16, 16, 1280, 1280, "s2", 0),
+    ("down_odd", 1, 24, 40, 320, 320, "s2", 0),
+]
+
+
+@pytest.mark.parametrize("case", GATHER_CASES, ids=[c[0] for c in GATHER_CASES])
+def test_tc_gemm_gather_folds(dev, case):
+    """Upsample (unet.py:248-251) and stride-2 conv (unet.py:236-240) with the gather folded into the TMA coordinates: no upsampled
+    tensor, no im2col matrix.  Reference: F.interpolate(nearest, 2x) + conv2d / conv2d(stride 2) in fp32 on the bf16-rounded input."""
+    name, B, H, W, Cc, N, mode, bn = case
+    lib = _lib.lib()
+    a = gen((B, H, W, Cc), 61, dev).bfloat16()
+    w = gen((N, 3, 3, Cc), 62, dev, 1.0 / math.sqrt(9 * Cc))
+    bias = gen((N,), 63, dev, 0.1)
+    d = TcGemmDesc()
+    d.w_kmajor = 1
+    if mode == "up2":
+        wp = upsample_parity_weights(w).bfloat16()                           # [2][2][N][2][2][C]
+        wk = torch.cat([kmajor(wp[py, px].reshape(N, 4 * Cc)) for py in (0, 1) for px in (0, 1)], 0).contiguous()
+        Ho, Wo = 2 * H, 2 * W
+        d.B, d.H, d.W, d.up2 = B, H, W, 1
+        # reference on what the kernel multiplies: the pre-summed bf16 weights act on the low-res pixels
+        x = a.float().permute(0, 3, 1, 2)
+        want = torch.zeros((B, N, Ho, Wo), device=dev)
+        xp = Fn.pad(x, (1, 1, 1, 1))
+        for py in (0, 1):
+            for px in (0, 1):
+                k2 = wp[py, px].float().permute(0, 3, 1, 2)                    # [N][C][2][2]
+                y = Fn.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], k2)
+                want[:, :, py::2, px::2] = y
+        want = (want + bias[None, :, None, None]).permute(0, 2, 3, 1)
+        # and the un-folded definition (fp32 weights): differs only by the bf16 rounding of the summed weights
+        ref = Fn.conv2d(Fn.interpolate(x, scale_factor=2, mode="nearest"), w.permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
+    else:
+        wk = kmajor(w.reshape(N, 9 * Cc).bfloat16())
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        d.B, d.H, d.W, d.a_stride, d.a_h, d.a_w = B, Ho, Wo, 2, H, W
+        x = a.float().permute(0, 3, 1, 2)
+        want = Fn.conv2d(x, w.bfloat16().float().permute(0, 3, 1, 2), bias, stride=2, padding=1).permute(0, 2, 3, 1)
+        ref = want
+    out = torch.full((B, Ho, Wo, N), float("nan"), device=dev)
+    cs = torch.zeros((B, N, 2), device=dev, dtype=torch.float64)
+    d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg = a.data_ptr(), wk.data_ptr(), Cc, 3, 1
+    d.N, d.bias, d.out, d.out_dtype, d.block_n = N, bias.data_ptr(), out.data_ptr(), F32_T, bn
+    h = C.c_void_p()
+    _lib.check(lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
+    info = (C.c_int * 11)()
+    _lib.check(lib.sdk_tc_gemm_info(h, info, 11))
+    ws = torch.zeros(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=dev)
+    _lib.check(lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr()))
+    rc = lib.sdk_tc_gemm_set_stats(h, cs.data_ptr())
+    _lib.check(lib.sdk_tc_gemm_launch(h, stream()))
+    torch.cuda.synchronize()
+    lib.sdk_tc_gemm_destroy(h)
+    e, e_ref = rel_l2(out, want), rel_l2(out, ref)
+    print(f"{name}: block_n={info[0]} splits={info[1]} grid=({info[2]},{info[3]}) tile=({info[4]},{info[5]},{info[6]}) persistent={info[10]} "
+          f"rel-L2 {e:.2e} (vs un-folded fp32-weight definition {e_ref:.2e})")
+    assert not torch.isnan(out).any()
+    assert e < 2e-5 and e_ref < 4e-3
+    if rc == 0:
+        flat = out.view(B, Ho * Wo, N).double()
+        assert rel_l2(cs[..., 0], flat.sum(1)) < 2e-6 and rel_l2(cs[..., 1], (flat * flat).sum(1)) < 2e-6
+
+
 LN_FOLD_CASES = [
     # name, M, C, N_consumer, geglu, producer (block_n, splits), consumer (block_n, splits)
     ("L0_qkv", 8192, 320, 960, False, (0, 0), (0, 0)),
