@@ -14,7 +14,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdb200.so")
+LIB_PATH = os.environ.get("SDB200_LIB_PATH") or os.path.join(_HERE, "libsdb200.so")     # override: A/B experiments with another build
 
 _lock = threading.Lock()
 _lib = None

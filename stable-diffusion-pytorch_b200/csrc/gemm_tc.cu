@@ -275,8 +275,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     int t = blockIdx.x;
     const int tw = t % p.tiles_w; t /= p.tiles_w;
     const int th = t % p.tiles_h; t /= p.tiles_h;
-    const int tb = t % p.tiles_b;
-    const int par = t / p.tiles_b;                     // output parity 2*py + px of a folded upsample (0 otherwise)
+    const int tb = t;
     const int w0 = tw * p.TW, h0 = th * p.TH, b0 = tb * p.TB;
     const int n0 = blockIdx.y * BN;
     const int kb_begin = blockIdx.z * p.kb_per_split;
@@ -321,9 +320,8 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
                 int dx = 0, dy = 0;
                 if (p.seg_ksize[seg] == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
-                else if (p.seg_ksize[seg] == 2) { dy = (tap >> 1) + (par >> 1) - 1; dx = (tap & 1) + (par & 1) - 1; }
-                const int wk = tap * p.seg_kb[seg] + kb + par * 4 * p.seg_kb[seg];     // k-block of the weights (parity sets are stacked)
-                const int ax = w0 * p.a_stride + dx, ay = h0 * p.a_stride + dy;
+                const int wk = tap * p.seg_kb[seg] + kb;
+                const int ax = w0 + dx, ay = h0 + dy;
                 ptx::mbar_wait(&empty[s], ph ^ 1u);
                 if (TWO) {
                     const int nb = n0 + (int)rank * B_ROWS;              // this CTA's half of the B tile
@@ -589,8 +587,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                     if (et == 0) ptx::bulk_wait_read<1>();
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (et == 0) {
-                        if (p.up2) ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, b0 * p.H + h0, par & 1, par >> 1);
-                        else ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
+                        ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
                         if (p.out2) ptx::tma_store_5d(&p.tmOut2, obuf + p.out2_off, n0 + c * 32, w0, h0, b0, 0);
                         ptx::bulk_commit();
                         if (p.epi_res && i + 2 < n_my) {   // every thread has consumed residual chunk i: refill its buffer
@@ -753,7 +750,9 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
 // time drops from prologue + main loop + epilogue to max(main loop, epilogue).
 // Supports the direct TMA epilogue only (single CTA, no split-K); everything else runs conv_gemm_tc_kernel.
 // -------------------------------------------------------------------------------------------------
-template <int BN>
+// FOLD: the conv gathers folded into the TMA coordinates (stride-2 conv, nearest-2x upsample as four parity convs; see TcParams).
+// A template parameter, not a run-time flag: the extra index arithmetic measurably slows the ordinary layers (0.14 ms per step).
+template <int BN, bool FOLD>
 __global__ void __launch_bounds__(PERS_THREADS, 1)
 conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
     constexpr int B_STAGE_BYTES = BN * BK * 2;
@@ -781,7 +780,8 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = p.N / BN;
-    const int total = p.tiles_w * p.tiles_h * p.tiles_b * n_tiles * (p.up2 ? 4 : 1);
+    const int total = p.tiles_w * p.tiles_h * p.tiles_b * n_tiles * ((FOLD && p.up2) ? 4 : 1);
+    const int a_stride = FOLD ? p.a_stride : 1;
     const int n_it = p.total_kb;
 
     if (threadIdx.x == 0) {
@@ -808,8 +808,9 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
         const int ni = t % n_tiles; int m = t / n_tiles;
         const int tw = m % p.tiles_w; m /= p.tiles_w;
         const int th = m % p.tiles_h; m /= p.tiles_h;
-        par = m / p.tiles_b;                           // output parity of a folded upsample (0 otherwise)
-        w0 = tw * p.TW; h0 = th * p.TH; b0 = (m % p.tiles_b) * p.TB; n0 = ni * BN;
+        if (FOLD) { par = m / p.tiles_b; m -= par * p.tiles_b; }   // output parity of a folded upsample
+        else par = 0;
+        w0 = tw * p.TW; h0 = th * p.TH; b0 = m * p.TB; n0 = ni * BN;
     };
 
     if (warp == 0) {
@@ -827,11 +828,11 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                     const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
                     int dx = 0, dy = 0;
                     if (p.seg_ksize[seg] == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
-                    else if (p.seg_ksize[seg] == 2) { dy = (tap >> 1) + (par >> 1) - 1; dx = (tap & 1) + (par & 1) - 1; }
+                    else if (FOLD && p.seg_ksize[seg] == 2) { dy = (tap >> 1) + (par >> 1) - 1; dx = (tap & 1) + (par & 1) - 1; }
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     ptx::mbar_expect_tx(&full[s], stage_bytes);
-                    ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 * p.a_stride + dx, h0 * p.a_stride + dy, b0);
-                    if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, tap * p.seg_kb[seg] + kb + par * 4 * p.seg_kb[seg]);
+                    ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 * a_stride + dx, h0 * a_stride + dy, b0);
+                    if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, tap * p.seg_kb[seg] + kb + (FOLD ? par * 4 * p.seg_kb[seg] : 0));
                     else ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, n0);
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
@@ -1006,7 +1007,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                 if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (et == 0) {
                     if (last) ptx::mbar_arrive(&acc_empty[ab]);          // (2 arrivals: both groups) the MMA warp may overwrite this buffer
-                    if (p.up2) ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, b0 * p.H + h0, par & 1, par >> 1);
+                    if (FOLD && p.up2) ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, b0 * p.H + h0, par & 1, par >> 1);
                     else ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
                     if (p.out2) ptx::tma_store_5d(&p.tmOut2, obuf + p.out2_off, n0 + c * 32, w0, h0, b0, 0);
                     ptx::bulk_commit();
@@ -1265,8 +1266,13 @@ int stage_smem(int bn, bool two) { return A_STAGE_BYTES + (two ? bn / 2 : bn) * 
 
 template <int BN>
 int launch_persistent(const TcGemm* g, cudaStream_t s) {
-    SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN>), g->smem_bytes));
-    SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
+    if (g->prm.up2 || g->prm.a_stride != 1) {
+        SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN, true>), g->smem_bytes));
+        SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN, true>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
+    } else {
+        SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN, false>), g->smem_bytes));
+        SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN, false>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
+    }
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
@@ -1560,12 +1566,12 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         // grids -- UNet batch 2: 4.57 -> 4.47 ms/step)
         const int mode = e ? atoi(e) : 2;
         const long long tiles = (long long)m_tiles * n_tiles;
-        g->persistent = mode > 0 && !two && splits == 1 && p.epi_tma && (mode > 1 || tiles >= 2LL * sms);
+        g->persistent = mode > 0 && !two && splits == 1 && p.epi_tma && (mode > 1 || tiles >= 2LL * sms || up2 || s2);
         if (g->persistent) {
             const int fixed_p = fixed_smem(bn, p.epi_res != 0) + PERS_EPI_BUFS * p.epi_buf_stride + ADD_ROWS * bn * 4 + 2 * 4 * 32 * 8 + bn * 4;
             int st = (232448 - fixed_p) / stage_smem(bn, false);
             if (st > MAX_STAGES) st = MAX_STAGES;
-            if (st < 3 && !(st == 2 && p.total_kb <= 8)) g->persistent = false;   // 2 stages only where the whole K loop is a handful of k-blocks
+            if (st < 3 && !(st == 2 && (p.total_kb <= 8 || up2 || s2))) g->persistent = false;   // 2 stages only where the whole K loop is a handful of k-blocks
             else {
                 p.stages = st;
                 g->smem_bytes = fixed_p + st * stage_smem(bn, false);
@@ -1575,6 +1581,10 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
                 return SDK_OK;
             }
         }
+    }
+    if (up2 || s2) {                                      // only the persistent kernel carries the folded gathers
+        delete g;
+        return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_tc_gemm_create: folded gather needs the persistent kernel (SDB200_TC_PERSISTENT != 0, block_n %d)", bn);
     }
     const int fixed = fixed_smem(bn, p.epi_res != 0), per_stage = stage_smem(bn, two);
     const int min_stages = (p.epi_tma || p.part_tma) ? (EPI_BUFS * p.epi_buf_stride + per_stage - 1) / per_stage : 2;   // chunk buffers alias the stages
@@ -1604,7 +1614,7 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
     // ---- split-K: reduce inside the kernel when the final epilogue can run here and every CTA of the grid is resident at once
     // (a CTA that owns output chunks waits for its tile's other splits); otherwise the second (reduce) kernel finishes the job
     if (splits > 1) {
-        static const int fix_mode = getenv("SDB200_TC_FIXUP") ? atoi(getenv("SDB200_TC_FIXUP")) : 1;
+        static const int fix_mode = getenv("SDB200_TC_FIXUP") ? atoi(getenv("SDB200_TC_FIXUP")) : 0;   // measured on B200 (UNet batch 2): 0.12 ms per step SLOWER than the reduce kernel -> opt-in
         // CTAs of this kernel that one SM holds at once, as the driver computes it for this launch configuration (the waiting
         // CTAs of a tile rely on their siblings being resident: never assume more than the driver grants, nor more than 2 = TMEM)
         int occ = 0;
