@@ -773,7 +773,7 @@ class StepProgram:
                     # stride-2 3x3 (unet.py:236): the A boxes walk the bf16 input with element stride 2 (no im2col matrix) ...
                     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
                     y = None
-                    if self.net.fold_gathers:
+                    if self.net.fold_gathers and B * ho * wo >= self.net.fold_min_rows_s2:
                         op, _ = self._operand(x, B, h, w, xc)
                         y, _, _ = self._conv([(op, xc)], wn, bn_, B, h, w, xc, k=3, stride=2, want_stats=True, fold_gather=True)
                         self.pool.put(op)
@@ -817,7 +817,7 @@ class StepProgram:
                 up = not (skips and skips[-1][3] == prev_w)          # unet.py:346-349
                 rp = st.resample.prefix
                 y = None
-                if up and self.act != F32_T and self.net.fold_gathers:
+                if up and self.act != F32_T and self.net.fold_gathers and B * h * w >= self.net.fold_min_rows_up:
                     # nearest-2x upsample folded into the conv: four 2x2 convs on the low-res bf16 input, one per output parity
                     op, tmp = self._operand(x, B, h, w, xc)
                     y, hn, wn_ = self._conv([(op, xc)], t[f"{rp}.w_up2"], t[f"{rp}.b"], B, h, w, xc, k=3, up=True, want_stats=True, fold_gather=True)
@@ -919,8 +919,14 @@ class UNet(nn.Module):
         self.tc_tune_pairs = int(os.environ.get("SDB200_TC_TUNE_PAIRS", "0"))   # also try cta_group::2 pairs when measuring tilings
         self.tc_autotune = int(os.environ.get("SDB200_TC_AUTOTUNE", "1"))     # 0 model | 1 committed cache | 2 measure misses | 3 and print
         self.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention (head_dim 40 / 64 / 80 / 160); 0: mma.sync kernel
-        self.ln_fold = os.environ.get("SDB200_LN_FOLD", "1") != "0"          # bf16: LayerNorm folded into the consuming GEMM (0: layernorm kernel)
+        # bf16: LayerNorm folded into the consuming GEMM (built and parity-tested; measured on B200 it costs the GEMMs 0.23 ms per step and
+        # saves 0.20 ms of layernorm launches at UNet batch 2, and loses 0.9 ms of 20.3 at batch 16 -> opt-in)
+        self.ln_fold = os.environ.get("SDB200_LN_FOLD", "0") != "0"
         self.fold_gathers = os.environ.get("SDB200_FOLD_GATHERS", "1") != "0"   # bf16: stride-2 / upsample gathers inside the GEMM's TMA coordinates
+        # ... where the layer has enough rows to fill the chip WITHOUT split-K (the folded form runs on the persistent kernel only; measured
+        # on B200 at UNet batch 2: the 8x8 / 16x16 layers are weight-streaming bound and 1.6-3x faster as im2col / upsample + split-K GEMM)
+        self.fold_min_rows_up = int(os.environ.get("SDB200_FOLD_MIN_ROWS_UP", "512"))      # low-res rows B*h*w of an upsample conv
+        self.fold_min_rows_s2 = int(os.environ.get("SDB200_FOLD_MIN_ROWS_S2", "2048"))     # output rows of a stride-2 conv
         self.ln_fold_min_rows = int(os.environ.get("SDB200_LN_FOLD_MIN_ROWS", "0"))   # ... only for token counts >= this (small ones are split-K GEMMs)
         self.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
         # sums: statistics from per-channel sums reduced in the producing GEMM's epilogue (bf16 program; fastest measured) |

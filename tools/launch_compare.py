@@ -17,7 +17,10 @@ def load(path):
         v *= {"us": 1e3, "ms": 1e6, "ns": 1, "s": 1e9}.get(r["Metric Unit"], 1)
         n = r["Kernel Name"]
         m = re.search(r"(\w+_kernel)\s*<([^>]*)>", n) or re.search(r"(\w+_kernel)", n)
-        name = m.group(1) + ("<" + m.group(2).replace("(int)", "").replace("(bool)", "") + ">" if m.lastindex and m.lastindex > 1 else "")
+        if m is None:
+            name = n[:40]
+        else:
+            name = m.group(1) + ("<" + m.group(2).replace("(int)", "").replace("(bool)", "") + ">" if m.lastindex and m.lastindex > 1 else "")
         rows.append((name, r["Grid Size"].replace(" ", ""), v / 1e3))
     nt = [i for i, r in enumerate(rows) if "next_timestep" in r[0]]
     return rows[nt[-1]:] if nt else rows
