@@ -102,6 +102,9 @@ int sdk_groupnorm_cluster(const float* src0, int C0, const float* src1, int C1, 
                           void* stream);
 int sdk_layernorm(const float* x, const float* gamma, const float* beta, float eps, void* out,
                   int out_dtype, int64_t rows, int C, void* stream);
+/* out[r][:] = softmax(scale * in[r][:]) over rows of a materialised fp32 score matrix (cols %% 4 == 0, <= 16384): the single-head
+ * head_dim = 512 attention of the VAE decoder (models/vae/vae.py:55-80), whose Q K^T and P V products run as sdk_tc_gemm launches */
+int sdk_softmax_rows(const float* in, void* out, int out_dtype, int64_t rows, int cols, float scale, void* stream);
 /* fp32 NHWC -> out_dtype NHWC, nearest upsample by `up` (1 or 2)  (unet.py:250) */
 int sdk_cast_upsample(const float* src, void* dst, int out_dtype, int B, int H, int W, int C, int up, void* stream);
 /* dst[b][p][c] = src[b % B_src][c][p]: NCHW latent -> NHWC, with latent.repeat(2,...) (diffusion.py:228) folded in */

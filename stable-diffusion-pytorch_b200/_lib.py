@@ -42,6 +42,7 @@ SIGNATURES = {
     "sdk_groupnorm_fused": [P, I32, P, I32, I32, I32, F32, P, P, I32, P, P, I32, P, P],
     "sdk_groupnorm_cluster": [P, I32, P, I32, I32, I32, F32, P, P, I32, P, P, I32, P],
     "sdk_layernorm": [P, P, P, F32, P, I32, I64, I32, P],
+    "sdk_softmax_rows": [P, P, I32, I64, I32, F32, P],
     "sdk_cast_upsample": [P, P, I32, I32, I32, I32, I32, I32, P],
     "sdk_nchw_to_nhwc": [P, P, I32, I32, I32, I32, P],
     # --- time_embed.cu

@@ -206,3 +206,65 @@ def param_spec(a: UNetArch):
     s += [("output.0.weight", (320,)), ("output.0.bias", (320,)),
           ("output.2.weight", (a.out_channels, 320, 3, 3)), ("output.2.bias", (a.out_channels,))]
     return s
+
+
+# ======================================================================================
+# VAE (reference models/vae/vae.py): parameter contract and decoder structure
+# ======================================================================================
+VAE_CH, VAE_CH_MULT = 128, (1, 2, 4, 4)
+
+
+def _vae_res(p, cin, cout):
+    s = [(f"{p}.norm1.weight", (cin,)), (f"{p}.norm1.bias", (cin,)), (f"{p}.conv1.weight", (cout, cin, 3, 3)), (f"{p}.conv1.bias", (cout,)),
+         (f"{p}.norm2.weight", (cout,)), (f"{p}.norm2.bias", (cout,)), (f"{p}.conv2.weight", (cout, cout, 3, 3)), (f"{p}.conv2.bias", (cout,))]
+    if cin != cout:
+        s += [(f"{p}.conv_shortcut.weight", (cout, cin, 1, 1)), (f"{p}.conv_shortcut.bias", (cout,))]
+    return s
+
+
+def _vae_attn(p, c):
+    s = [(f"{p}.group_norm.weight", (c,)), (f"{p}.group_norm.bias", (c,))]
+    for n in ("query", "key", "value", "proj_attn"):
+        s += [(f"{p}.{n}.weight", (c, c)), (f"{p}.{n}.bias", (c,))]
+    return s
+
+
+def vae_decoder_blocks():
+    """(up-block index, cin of its first ResidualBlock, cout, has upsampler) in forward order (vae.py:208-224)."""
+    out, block_in = [], VAE_CH * VAE_CH_MULT[-1]
+    for j, i in enumerate(reversed(range(len(VAE_CH_MULT)))):
+        block_out = VAE_CH * VAE_CH_MULT[i]
+        out.append((j, block_in, block_out, i != 0))
+        block_in = block_out
+    return out
+
+
+def vae_param_spec(in_channels=3, z_channels=4, out_channels=3):
+    """(name, shape) of every parameter of the reference ``VAE`` in its registration order (vae.py:136-262); the encoder is part
+    of the ``load_state_dict(strict=True)`` contract although only the decoder runs here."""
+    ch, mult = VAE_CH, VAE_CH_MULT
+    s = [("encoder.conv_in.weight", (ch, in_channels, 3, 3)), ("encoder.conv_in.bias", (ch,))]
+    cur = ch
+    for i, m in enumerate(mult):
+        out = ch * m
+        for j in range(2):
+            s += _vae_res(f"encoder.down_blocks.{i}.resnets.{j}", cur if j == 0 else out, out)
+        if i != len(mult) - 1:
+            s += [(f"encoder.down_blocks.{i}.downsamplers.0.conv.weight", (out, out, 3, 3)), (f"encoder.down_blocks.{i}.downsamplers.0.conv.bias", (out,))]
+        cur = out
+    s += _vae_res("encoder.mid_block.resnets.0", cur, cur) + _vae_res("encoder.mid_block.resnets.1", cur, cur) + _vae_attn("encoder.mid_block.attentions.0", cur)
+    s += [("encoder.conv_norm_out.weight", (cur,)), ("encoder.conv_norm_out.bias", (cur,)),
+          ("encoder.conv_out.weight", (2 * z_channels, cur, 3, 3)), ("encoder.conv_out.bias", (2 * z_channels,))]
+    top = ch * mult[-1]
+    s += [("decoder.conv_in.weight", (top, z_channels, 3, 3)), ("decoder.conv_in.bias", (top,))]
+    s += _vae_attn("decoder.mid_block.attentions.0", top) + _vae_res("decoder.mid_block.resnets.0", top, top) + _vae_res("decoder.mid_block.resnets.1", top, top)
+    for j, cin, cout, up in vae_decoder_blocks():
+        for k in range(3):
+            s += _vae_res(f"decoder.up_blocks.{j}.resnets.{k}", cin if k == 0 else cout, cout)
+        if up:
+            s += [(f"decoder.up_blocks.{j}.upsamplers.0.conv.weight", (cout, cout, 3, 3)), (f"decoder.up_blocks.{j}.upsamplers.0.conv.bias", (cout,))]
+    s += [("decoder.conv_norm_out.weight", (ch,)), ("decoder.conv_norm_out.bias", (ch,)),
+          ("decoder.conv_out.weight", (out_channels, ch, 3, 3)), ("decoder.conv_out.bias", (out_channels,))]
+    s += [("quant_conv.weight", (2 * z_channels, 2 * z_channels, 1, 1)), ("quant_conv.bias", (2 * z_channels,)),
+          ("post_quant_conv.weight", (z_channels, z_channels, 1, 1)), ("post_quant_conv.bias", (z_channels,))]
+    return s

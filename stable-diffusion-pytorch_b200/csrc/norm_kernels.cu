@@ -837,6 +837,75 @@ extern "C" int sdk_layernorm(const float* x, const float* gamma, const float* be
     return SDK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row softmax of a materialised score matrix: out[r][:] = softmax(scale * in[r][:]) -- the single-head, head_dim = 512
+// attention of the VAE (models/vae/vae.py:55-80), whose scores and P.V products run as tensor-core GEMMs.
+// One CTA per row, the row lives in registers (cols <= 256 * 4 * SM_MAXQ), exact max and sum (fp32), exp2 of the pre-scaled logits.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int SM_MAXQ = 16;                             // float4 per thread -> rows of up to 16384 columns
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ in, TOut* __restrict__ out, int cols, float scale_log2) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float s_red[8];
+    const long long row = blockIdx.x;
+    const float4* src = reinterpret_cast<const float4*>(in + row * cols);
+    const int nq = cols >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 v[SM_MAXQ];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < SM_MAXQ; ++k) {
+        const int q = threadIdx.x + k * 256;
+        if (q < nq) { v[k] = __ldg(src + q); mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w))); }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = s_red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i]);
+    __syncthreads();
+    const float off = mx * scale_log2;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < SM_MAXQ; ++k) {
+        const int q = threadIdx.x + k * 256;
+        if (q < nq) {
+            v[k].x = exp2f(fmaf(v[k].x, scale_log2, -off)); v[k].y = exp2f(fmaf(v[k].y, scale_log2, -off));
+            v[k].z = exp2f(fmaf(v[k].z, scale_log2, -off)); v[k].w = exp2f(fmaf(v[k].w, scale_log2, -off));
+            sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+        }
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += s_red[i];
+    const float inv = 1.f / sum;
+    TOut* dst = out + row * cols;
+#pragma unroll
+    for (int k = 0; k < SM_MAXQ; ++k) {
+        const int q = threadIdx.x + k * 256;
+        if (q < nq) store4<TOut>(dst + (q << 2), v[k].x * inv, v[k].y * inv, v[k].z * inv, v[k].w * inv);
+    }
+}
+}  // namespace
+
+extern "C" int sdk_softmax_rows(const float* in, void* out, int out_dtype, int64_t rows, int cols, float scale, void* stream) {
+    SDK_CHECK_ARG(in && out && rows >= 0 && rows < (1ll << 31), "sdk_softmax_rows: bad args");
+    SDK_CHECK_ARG(cols > 0 && cols % 4 == 0 && cols <= 256 * 4 * SM_MAXQ, "sdk_softmax_rows: cols=%d must be a multiple of 4, at most %d", cols, 256 * 4 * SM_MAXQ);
+    if (rows == 0) return SDK_OK;
+    const float sl2 = scale * 1.4426950408889634f;
+    if (out_dtype == SDK_F32) SDK_CUDA(sdk_launch(softmax_rows_kernel<float>, dim3((unsigned)rows), dim3(256), (size_t)0, (cudaStream_t)stream, in, (float*)out, cols, sl2));
+    else if (out_dtype == SDK_BF16) SDK_CUDA(sdk_launch(softmax_rows_kernel<__nv_bfloat16>, dim3((unsigned)rows), dim3(256), (size_t)0, (cudaStream_t)stream, in, (__nv_bfloat16*)out, cols, sl2));
+    else return sdk_fail(SDK_ERR_ARG, "sdk_softmax_rows: out_dtype %d", out_dtype);
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
 extern "C" int sdk_cast_upsample(const float* src, void* dst, int out_dtype, int B, int H, int W, int C, int up, void* stream) {
     SDK_CHECK_ARG(src && dst && (up == 1 || up == 2) && C % 4 == 0, "sdk_cast_upsample: bad args (C=%d up=%d)", C, up);
     const long long total = (long long)B * H * up * W * up * (C / 4);

@@ -47,6 +47,31 @@ def same_context(cond: torch.Tensor, ref, version) -> bool:
     return cond is ref and v is not None and v == version
 
 
+def read_knobs(m):
+    """Environment knobs of the launch-list programs; defaults are the measured best on B200."""
+    m.precision = os.environ.get("SDB200_PRECISION", "bf16")
+    m.tc_block_n = int(os.environ.get("SDB200_TC_BLOCK_N", "0"))      # 0 = auto; tuning / test overrides
+    m.tc_splits = int(os.environ.get("SDB200_TC_SPLITS", "0"))
+    m.tc_tune_pairs = int(os.environ.get("SDB200_TC_TUNE_PAIRS", "0"))   # also try cta_group::2 pairs when measuring tilings
+    m.tc_autotune = int(os.environ.get("SDB200_TC_AUTOTUNE", "1"))     # 0 model | 1 committed cache | 2 measure misses | 3 and print
+    m.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention (head_dim 40 / 64 / 80 / 160); 0: mma.sync kernel
+    # bf16: LayerNorm folded into the consuming GEMM (built and parity-tested; measured on B200 it costs the GEMMs 0.23 ms per step and
+    # saves 0.20 ms of layernorm launches at UNet batch 2, and loses 0.9 ms of 20.3 at batch 16 -> opt-in)
+    m.ln_fold = os.environ.get("SDB200_LN_FOLD", "0") != "0"
+    m.fold_gathers = os.environ.get("SDB200_FOLD_GATHERS", "1") != "0"   # bf16: stride-2 / upsample gathers inside the GEMM's TMA coordinates
+    # ... where the layer has enough rows to fill the chip WITHOUT split-K (the folded form runs on the persistent kernel only; measured
+    # on B200 at UNet batch 2: the 8x8 / 16x16 layers are weight-streaming bound and 1.6-3x faster as im2col / upsample + split-K GEMM)
+    m.fold_min_rows_up = int(os.environ.get("SDB200_FOLD_MIN_ROWS_UP", "512"))      # low-res rows B*h*w of an upsample conv
+    m.fold_min_rows_s2 = int(os.environ.get("SDB200_FOLD_MIN_ROWS_S2", "2048"))     # output rows of a stride-2 conv
+    m.ln_fold_min_rows = int(os.environ.get("SDB200_LN_FOLD_MIN_ROWS", "0"))   # ... only for token counts >= this (small ones are split-K GEMMs)
+    m.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
+    # sums: statistics from per-channel sums reduced in the producing GEMM's epilogue (bf16 program; fastest measured) |
+    # split (stats + apply kernels) | cluster | coop | auto
+    m.gn_mode = os.environ.get("SDB200_GN_MODE", "sums")
+    m.gn_cluster_max_bytes = int(os.environ.get("SDB200_GN_CLUSTER_MAX_BYTES", str(3 << 20)))
+    m.use_cuda_graph = os.environ.get("SDB200_CUDA_GRAPH", "1") != "0"
+
+
 class _Node(nn.Module):
     """Anonymous container so parameters get the reference's dotted names."""
 
@@ -230,12 +255,9 @@ class StepProgram:
         with torch.inference_mode(False), torch.no_grad(), torch.cuda.device(pw.device):
             self._plan(net, pw, B, H, W, nt, Bc, Sk, b_src)
 
-    def _plan(self, net, pw, B, H, W, nt, Bc, Sk, b_src):
-        self.net, self.pw = net, pw
-        self.b_src = B if b_src is None else b_src     # latent rows actually stored: B == 2*b_src folds latent.repeat(2,...)
-        self.B, self.H, self.W, self.nt, self.Bc, self.Sk = B, H, W, nt, Bc, Sk
-        a: UNetArch = net.arch
-        self.arch = a
+    def _init_common(self, net, pw, B):
+        """State shared by every launch-list program built from these emit helpers (UNet step, VAE decoder, text encoder)."""
+        self.net, self.pw, self.B = net, pw, B
         dev = pw.device
         self.device = dev
         self.precision = pw.precision
@@ -254,6 +276,14 @@ class StepProgram:
         self.stat_arena = torch.zeros(max(4, 2 * B) << 20, dtype=torch.uint8, device=dev) if self.gn_from_sums else None
         self.stat_used = 0
 
+    def _plan(self, net, pw, B, H, W, nt, Bc, Sk, b_src):
+        self._init_common(net, pw, B)
+        self.b_src = B if b_src is None else b_src     # latent rows actually stored: B == 2*b_src folds latent.repeat(2,...)
+        self.H, self.W, self.nt, self.Bc, self.Sk = H, W, nt, Bc, Sk
+        a: UNetArch = net.arch
+        self.arch = a
+        dev = pw.device
+
         f32 = torch.float32
         # static I/O staging (graph-stable addresses)
         self.x_in = torch.empty((self.b_src, a.in_channels, H, W), dtype=f32, device=dev)
@@ -271,8 +301,9 @@ class StepProgram:
 
     def _conv(self, srcs, w, bias, B, Hin, Win, N, *, k=1, stride=1, up=False, tbias=0, tb_stride=0,
               residual=None, geglu=False, out_code=F32_T, out=None, out_nchw=False, in_code=None, ctx=False,
-              force_simt=False, seg2=None, want_stats=False, ln_out=False, ln_in=None, fold_gather=False):
+              force_simt=False, seg2=None, want_stats=False, ln_out=False, ln_in=None, fold_gather=False, w_rowmajor=False):
         """srcs: [(tensor[rows, C], C)] (1 or 2).  Returns the output tensor [M, N or N/2].
+        w_rowmajor: ``w`` is a plain [N][K] matrix (an ACTIVATION used as the B operand: attention scores, P V) instead of packed weights.
         want_stats: the output feeds a GroupNorm -> also produce its per-channel (sum, sum of squares) table (out._cstats).
         ln_out: the output feeds a LayerNorm that is folded into its consumer -> also produce a bf16 copy (out._bf16) and the per-row
         statistics partials (out._rowstats).  ln_in = (row statistics tensor, column sums of the folded weights): this GEMM applies
@@ -314,6 +345,8 @@ class StepProgram:
                 extras = dict(extras or {}, ln_stats=ln_in[0], ln_colsum=ln_in[1], ln_parts=srcs[0][1] // 32)
             if fold_gather:
                 extras = dict(extras or {}, gather="up2" if up else "s2")
+            if w_rowmajor:
+                extras = dict(extras or {}, w_rowmajor=True)
             fused = self._emit_tc_conv(p, srcs, w, ctx, seg2, cs, extras)
             if fused is None:                               # folded gather not available for this shape: nothing was emitted
                 self.pool.put(out)
@@ -350,6 +383,8 @@ class StepProgram:
         d.bias, d.tbias, d.tb_stride, d.residual, d.out = p.bias, p.tbias, p.tb_stride, p.residual, p.out
         d.out_dtype, d.geglu, d.out_nchw = p.out_dtype, p.geglu, p.out_nchw
         d.block_n, d.splits, d.w_kmajor, d.two_cta = self.net.tc_block_n, self.net.tc_splits, 1, self.net.tc_two_cta
+        if extras and extras.get("w_rowmajor"):
+            d.w_kmajor = 0
         if extras:
             if "out2" in extras:
                 d.out2, d.row_stats = extras["out2"].data_ptr(), extras["row_stats"].data_ptr()
@@ -362,7 +397,7 @@ class StepProgram:
         rc = self.lib.sdk_tc_gemm_create(C.byref(d), C.byref(h))
         if rc == -3 and gather:
             return None                                         # caller falls back to the materialised gather
-        if rc == -3 and extras:
+        if rc == -3 and extras and ("out2" in extras or "ln_stats" in extras):
             # the tuned tiling cannot carry the fused LayerNorm work (ragged N tile, or a split-K grid too large to reduce inside the
             # kernel): an exact N tile without split-K always can
             d.splits, d.two_cta = 1, 1
@@ -913,27 +948,7 @@ class UNet(nn.Module):
                                down_block_types, t_embed_dim, num_attention_heads, eps)
         for name, shape in param_spec(self.arch):
             self._register(name, shape)
-        self.precision = os.environ.get("SDB200_PRECISION", "bf16")
-        self.tc_block_n = int(os.environ.get("SDB200_TC_BLOCK_N", "0"))      # 0 = auto; tuning / test overrides
-        self.tc_splits = int(os.environ.get("SDB200_TC_SPLITS", "0"))
-        self.tc_tune_pairs = int(os.environ.get("SDB200_TC_TUNE_PAIRS", "0"))   # also try cta_group::2 pairs when measuring tilings
-        self.tc_autotune = int(os.environ.get("SDB200_TC_AUTOTUNE", "1"))     # 0 model | 1 committed cache | 2 measure misses | 3 and print
-        self.attn_tc = os.environ.get("SDB200_ATTN_TC", "1") != "0"          # tcgen05 attention (head_dim 40 / 64 / 80 / 160); 0: mma.sync kernel
-        # bf16: LayerNorm folded into the consuming GEMM (built and parity-tested; measured on B200 it costs the GEMMs 0.23 ms per step and
-        # saves 0.20 ms of layernorm launches at UNet batch 2, and loses 0.9 ms of 20.3 at batch 16 -> opt-in)
-        self.ln_fold = os.environ.get("SDB200_LN_FOLD", "0") != "0"
-        self.fold_gathers = os.environ.get("SDB200_FOLD_GATHERS", "1") != "0"   # bf16: stride-2 / upsample gathers inside the GEMM's TMA coordinates
-        # ... where the layer has enough rows to fill the chip WITHOUT split-K (the folded form runs on the persistent kernel only; measured
-        # on B200 at UNet batch 2: the 8x8 / 16x16 layers are weight-streaming bound and 1.6-3x faster as im2col / upsample + split-K GEMM)
-        self.fold_min_rows_up = int(os.environ.get("SDB200_FOLD_MIN_ROWS_UP", "512"))      # low-res rows B*h*w of an upsample conv
-        self.fold_min_rows_s2 = int(os.environ.get("SDB200_FOLD_MIN_ROWS_S2", "2048"))     # output rows of a stride-2 conv
-        self.ln_fold_min_rows = int(os.environ.get("SDB200_LN_FOLD_MIN_ROWS", "0"))   # ... only for token counts >= this (small ones are split-K GEMMs)
-        self.tc_two_cta = int(os.environ.get("SDB200_TC_TWO_CTA", "0"))       # 0 auto, 1 never, 2 always (even m-tiles)
-        # sums: statistics from per-channel sums reduced in the producing GEMM's epilogue (bf16 program; fastest measured) |
-        # split (stats + apply kernels) | cluster | coop | auto
-        self.gn_mode = os.environ.get("SDB200_GN_MODE", "sums")
-        self.gn_cluster_max_bytes = int(os.environ.get("SDB200_GN_CLUSTER_MAX_BYTES", str(3 << 20)))
-        self.use_cuda_graph = os.environ.get("SDB200_CUDA_GRAPH", "1") != "0"
+        read_knobs(self)
         self._packed: Dict = {}
         self._plans: Dict = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())

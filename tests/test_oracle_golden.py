@@ -149,3 +149,18 @@ def test_unet_oracle_sd21_matches_reference(golden_dir):
         pn = UO.unet_forward(sd, T(g["onestep_lat"]), torch.tensor([999]), T(g["ctx"])[:1], **UO.SD21)
         assert rel_l2(pn.numpy(), g["onestep_pred"]) < 2e-5
         assert rel_l2(SO.x0_from_eps(g["onestep_lat"], pn.numpy()), g["onestep_x0"]) < 2e-5
+
+
+def test_vae_oracle_matches_reference_golden(golden_dir):
+    """oracle/vae_oracle.decode restates VAE.decode (models/vae/vae.py:270-274): pinned on images produced by the unmodified
+    reference (tests/golden/make_golden_vae.py), and the product's parameter contract equals the oracle's (= the reference's)."""
+    import torch
+    from oracle import vae_oracle as VO
+    from stable_diffusion_pytorch_b200.arch import vae_param_spec
+    assert vae_param_spec() == VO.param_spec() and len(VO.param_spec()) == 248
+    g = np.load(os.path.join(golden_dir, "vae_golden.npz"))
+    sd = VO.make_state_dict(3)
+    with torch.no_grad():
+        for name in ("z8", "z8x16"):
+            y = VO.decode(sd, torch.from_numpy(g[name])).numpy()
+            assert np.linalg.norm(y - g[f"img_{name}"]) / np.linalg.norm(g[f"img_{name}"]) < 2e-5

@@ -1,0 +1,76 @@
+"""GPU parity of the VAE decoder against golden images produced by the UNMODIFIED reference
+(tests/golden/make_golden_vae.py -> vae_golden.npz) and, at full size, against the CPU oracle.  Gates: fp32 1e-4, bf16 1e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vae_oracle as VO
+from stable_diffusion_pytorch_b200 import VAE
+
+pytestmark = pytest.mark.gpu
+FP32_TOL, BF16_TOL = 1e-4, 1e-2
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def vae(dev):
+    net = VAE()
+    sd = VO.make_state_dict(3)
+    assert list(net.state_dict().keys()) == list(sd.keys())              # the reference's 248 names, in its order
+    net.load_state_dict(sd, strict=True)
+    return net.to(dev).eval(), sd
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_decode_matches_reference_golden(vae, golden_dir, dev, precision, tol):
+    net, _ = vae
+    net.set_precision(precision)
+    g = np.load(os.path.join(golden_dir, "vae_golden.npz"))
+    with torch.no_grad():
+        for name in ("z8", "z8x16", "z24"):
+            z = torch.from_numpy(g[name]).to(dev)
+            y = net.decode(z)
+            e = rel_l2(y.cpu().numpy(), g[f"img_{name}"])
+            print(f"VAE.decode {precision} {name} -> {tuple(y.shape)}: rel-L2 {e:.3e}")
+            assert y.shape == g[f"img_{name}"].shape and y.dtype == torch.float32 and e < tol
+            y2 = net.decode(z)                                              # second call: CUDA-graph capture + replay
+            y3 = net.decode(z)
+            assert torch.equal(y2, y) and torch.equal(y3, y)
+    net.set_precision("bf16")
+
+
+def test_decode_full_size_bf16_vs_oracle(vae, dev):
+    """512x512 image from a 64x64 latent (BASELINE configs 2/3/5): tcgen05 convs with the folded upsample, 4096-token attention."""
+    net, sd = vae
+    net.set_precision("bf16")
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn((1, 4, 64, 64), generator=g) * 0.18215 * 4.0
+    with torch.no_grad():
+        y = net.decode(z.to(dev)).cpu()
+        want = VO.decode(sd, z)
+    e = rel_l2(y.numpy(), want.numpy())
+    print(f"VAE.decode bf16 64x64 latent -> 512x512: rel-L2 {e:.3e}")
+    assert y.shape == (1, 3, 512, 512) and e < BF16_TOL
+
+
+def test_decode_rejects_cpu_and_bad_shapes(vae, dev):
+    net, _ = vae
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net.decode(torch.zeros((1, 4, 8, 8)))
+    with pytest.raises(RuntimeError):
+        net.decode(torch.zeros((1, 3, 8, 8), device=dev))
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        net.decode(torch.zeros((1, 4, 12, 8), device=dev))
+    with pytest.raises(NotImplementedError):
+        net.encode(torch.zeros((1, 3, 64, 64), device=dev))
