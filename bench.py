@@ -284,6 +284,44 @@ def run_one_step(args, cfg):
         "clocks": sampler.summary()}))
 
 
+def time_vae_decode(dev, B, hw, reps=10):
+    """VAE.decode (models/vae/vae.py:270-274) of a (B,4,hw,hw) latent on random-init weights: device time per decode (CUDA events,
+    graph replay) and end to end with the latent in pinned host memory and the image copied back to the host."""
+    from oracle import vae_oracle as VO          # synthetic weights recipe only (checker infrastructure, outside the timed region)
+    from stable_diffusion_pytorch_b200 import VAE
+    vae = VAE()
+    vae.load_state_dict(VO.make_state_dict(3), strict=True)
+    vae = vae.to(dev).eval()
+    g = torch.Generator().manual_seed(77)
+    z_h = (torch.randn((B, 4, hw, hw), generator=g) * 0.18215 * 4.0).pin_memory()
+    z = z_h.to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            img = vae.decode(z)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            img = vae.decode(z)
+        e1.record()
+        torch.cuda.synchronize()
+        dev_ms = e0.elapsed_time(e1) / reps
+        out_h = torch.empty(img.shape, dtype=img.dtype).pin_memory()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out_h.copy_(vae.decode(z_h.to(dev, non_blocking=True)), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
+    gflop = 1240.0 * B * (hw / 64.0) ** 2            # conv MACs of the decoder at 512^2 (2*MACs), attention excluded
+    res = {"workload": f"VAE.decode, latent ({B},4,{hw},{hw}) -> image ({B},3,{8 * hw},{8 * hw}), bf16 tensor-core path, random-init weights",
+           "ms_per_decode": dev_ms, "images_per_s": B / (dev_ms * 1e-3), "approx_tflops": gflop / dev_ms,
+           "e2e_ms_per_decode": e2e_ms, "h2d_bytes": z_h.numel() * 4, "d2h_bytes": out_h.numel() * 4,
+           "finite": bool(torch.isfinite(img).all().item())}
+    del vae
+    torch.cuda.empty_cache()
+    return res
+
+
 def make_config(cfg, B, ub):
     """The `config` object of the JSON line: the workload only, IDENTICAL for our arm and for the reference arm."""
     return {"workload": cfg["name"], "images_per_gpu": B, "unet_batch_per_gpu": ub, "latent": [cfg["hw"], cfg["hw"]],
@@ -347,6 +385,7 @@ def main():
     ap.add_argument("--no-torch-eager", action="store_true", help="skip timing the reference op sequence in stock PyTorch eager on this GPU")
     ap.add_argument("--no-config3", action="store_true", help="N > 1: skip the batch-64-sharded (BASELINE config 3) measurement")
     ap.add_argument("--no-fp32", action="store_true", help="N = 1: skip the one-off fp32-mode ms/step figure")
+    ap.add_argument("--no-vae", action="store_true", help="N = 1: skip the VAE-decode (latent -> image) figure")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch_per_gpu:
@@ -509,6 +548,14 @@ def main():
             except Exception as ex:
                 fp32_ms = repr(ex)
 
+        # ---- N = 1: the stage after the loop: VAE.decode, latent -> 512^2 image, device-timed and end to end
+        vae_line = None
+        if world == 1 and args.precision == "bf16" and not args.no_vae and args.config == 2:
+            try:
+                vae_line = time_vae_decode(dev, B, cfg["hw"])
+            except Exception as ex:
+                vae_line = {"error": repr(ex)}
+
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -561,6 +608,8 @@ def main():
         line["config3"] = config3
     if fp32_ms is not None:
         line["fp32_mode_ms_per_step"] = fp32_ms
+    if vae_line is not None:
+        line["vae_decode"] = vae_line
     if breakdown:
         line["breakdown_ms_per_step"] = breakdown
     if not args.no_torch_eager and cfg["cfg"] and world == 1:
