@@ -312,7 +312,7 @@ def time_vae_decode(dev, B, hw, reps=10):
             out_h.copy_(vae.decode(z_h.to(dev, non_blocking=True)), non_blocking=True)
             torch.cuda.current_stream().synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
-    gflop = 1240.0 * B * (hw / 64.0) ** 2            # conv MACs of the decoder at 512^2 (2*MACs), attention excluded
+    gflop = 2514.5 * B * (hw / 64.0) ** 2            # 2*MACs of every conv / linear + 4*S*S*C of the attention, per 512^2 image (un-folded upsample convs)
     res = {"workload": f"VAE.decode, latent ({B},4,{hw},{hw}) -> image ({B},3,{8 * hw},{8 * hw}), bf16 tensor-core path, random-init weights",
            "ms_per_decode": dev_ms, "images_per_s": B / (dev_ms * 1e-3), "approx_tflops": gflop / dev_ms,
            "e2e_ms_per_decode": e2e_ms, "h2d_bytes": z_h.numel() * 4, "d2h_bytes": out_h.numel() * 4,
