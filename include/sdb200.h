@@ -105,6 +105,13 @@ int sdk_layernorm(const float* x, const float* gamma, const float* beta, float e
 /* out[r][:] = softmax(scale * in[r][:]) over rows of a materialised fp32 score matrix (cols %% 4 == 0, <= 16384): the single-head
  * head_dim = 512 attention of the VAE decoder (models/vae/vae.py:55-80), whose Q K^T and P V products run as sdk_tc_gemm launches */
 int sdk_softmax_rows(const float* in, void* out, int out_dtype, int64_t rows, int cols, float scale, void* stream);
+/* ---- text encoder front end (models/clip/openclip.py:53-71, clip.py:37-57) and MLP activation ------- */
+/* out[r][:] = tok_emb[ids[r]][:] + pos_emb[r %% S][:]   (rows = B*S token ids, int64) */
+int sdk_embed_tokens(const int64_t* ids, const float* tok_emb, const float* pos_emb, float* out,
+                     int64_t rows, int S, int C, int vocab, void* stream);
+/* elementwise activation of an fp32 tensor, written as out_dtype: kind 1 = exact-erf GELU (openclip.py:78), 2 = QuickGELU
+ * x*sigmoid(1.702x) (activation_fn.py:4-9) */
+int sdk_activation(const float* in, void* out, int out_dtype, int64_t n, int kind, void* stream);
 /* fp32 NHWC -> out_dtype NHWC, nearest upsample by `up` (1 or 2)  (unet.py:250) */
 int sdk_cast_upsample(const float* src, void* dst, int out_dtype, int B, int H, int W, int C, int up, void* stream);
 /* dst[b][p][c] = src[b % B_src][c][p]: NCHW latent -> NHWC, with latent.repeat(2,...) (diffusion.py:228) folded in */
@@ -153,6 +160,11 @@ int sdk_attention_f32(const float* q, int64_t q_row, int64_t q_batch, const floa
                       const float* v, int64_t v_row, int64_t v_batch, float* out, int64_t o_row, int64_t o_batch,
                       int B, int heads, int Sq, int Sk, int D, float scale, void* stream);
 
+/* same with an optional causal (look-ahead) mask: the text encoders' attention in the exact-fp32 mode */
+int sdk_attention_f32_ex(const float* q, int64_t q_row, int64_t q_batch, const float* k, int64_t k_row, int64_t k_batch,
+                         const float* v, int64_t v_row, int64_t v_batch, float* out, int64_t o_row, int64_t o_batch,
+                         int B, int heads, int Sq, int Sk, int D, float scale, int causal, void* stream);
+
 /* bf16 tensor-core attention (mma.sync m16n8k16, fp32 softmax statistics); same contract as sdk_attention_f32 with bf16 tensors */
 int sdk_attention_bf16(const void* q, int64_t q_row, int64_t q_batch, const void* k, int64_t k_row, int64_t k_batch,
                        const void* v, int64_t v_row, int64_t v_batch, void* out, int64_t o_row, int64_t o_batch,
@@ -163,6 +175,8 @@ int sdk_attention_bf16(const void* q, int64_t q_row, int64_t q_batch, const void
 int sdk_attention_tc_create(const void* q, int64_t q_row, int64_t q_batch, const void* k, int64_t k_row, int64_t k_batch,
                             const void* v, int64_t v_row, int64_t v_batch, void* out, int64_t o_row, int64_t o_batch,
                             int B, int heads, int Sq, int Sk, int D, float scale, void** handle);
+/* causal = 1: query i sees keys <= i (text encoders, models/clip/attention.py:38-45 with lookahead_mask=True) */
+int sdk_attention_tc_set_causal(void* handle, int causal);
 int sdk_attention_tc_launch(void* handle, void* stream);
 int sdk_attention_tc_destroy(void* handle);
 

@@ -6,7 +6,7 @@ library (include/sdb200.h).  See DESIGN.md / INTEGRATION.md.
 """
 from .scheduler import DDIMSampler, DDPMSampler, x0_from_eps  # noqa: F401
 
-__all__ = ["DDIMSampler", "DDPMSampler", "x0_from_eps", "UNet", "VAE", "DenoiseLoop", "denoise", "one_step", "img2img", "inpaint"]
+__all__ = ["DDIMSampler", "DDPMSampler", "x0_from_eps", "UNet", "VAE", "OpenCLIP", "CLIPTextModel", "CLIPTextConfig", "TextEncoder", "DenoiseLoop", "denoise", "one_step", "img2img", "inpaint"]
 
 
 def __getattr__(name):
@@ -14,6 +14,9 @@ def __getattr__(name):
     if name == "UNet":
         from .unet import UNet
         return UNet
+    if name in ("OpenCLIP", "CLIPTextModel", "CLIPTextConfig", "TextEncoder"):
+        from . import clip
+        return getattr(clip, name)
     if name == "VAE":
         from .vae import VAE
         return VAE

@@ -43,6 +43,8 @@ SIGNATURES = {
     "sdk_groupnorm_cluster": [P, I32, P, I32, I32, I32, F32, P, P, I32, P, P, I32, P],
     "sdk_layernorm": [P, P, P, F32, P, I32, I64, I32, P],
     "sdk_softmax_rows": [P, P, I32, I64, I32, F32, P],
+    "sdk_embed_tokens": [P, P, P, P, I64, I32, I32, I32, P],
+    "sdk_activation": [P, P, I32, I64, I32, P],
     "sdk_cast_upsample": [P, P, I32, I32, I32, I32, I32, I32, P],
     "sdk_nchw_to_nhwc": [P, P, I32, I32, I32, I32, P],
     # --- time_embed.cu
@@ -52,10 +54,12 @@ SIGNATURES = {
     "sdk_conv_gemm_f32": [P, P],
     # --- attention_simt.cu
     "sdk_attention_f32": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, P],
+    "sdk_attention_f32_ex": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, I32, P],
     # --- attention_mma.cu
     "sdk_attention_bf16": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, P],
     # --- attention_tc.cu
     "sdk_attention_tc_create": [P, I64, I64, P, I64, I64, P, I64, I64, P, I64, I64, I32, I32, I32, I32, I32, F32, P],
+    "sdk_attention_tc_set_causal": [P, I32],
     "sdk_attention_tc_launch": [P, P],
     "sdk_attention_tc_destroy": [P],
     # --- gemm_tc.cu

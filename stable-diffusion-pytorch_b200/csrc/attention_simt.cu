@@ -16,7 +16,7 @@ attention_f32_kernel(const float* __restrict__ q, long long q_row, long long q_b
                      const float* __restrict__ k, long long k_row, long long k_batch,
                      const float* __restrict__ v, long long v_row, long long v_batch,
                      float* __restrict__ out, long long o_row, long long o_batch,
-                     int heads, int Sq, int Sk, float scale) {
+                     int heads, int Sq, int Sk, float scale, int causal) {
     pdl_trigger();
     pdl_wait();
     constexpr int DQ = D / 4;                    // output columns per thread
@@ -64,7 +64,7 @@ attention_f32_kernel(const float* __restrict__ q, long long q_row, long long q_b
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (k0 + part + 4 * j >= Sk) s[j] = -INFINITY;
+            if (k0 + part + 4 * j >= Sk || (causal && k0 + part + 4 * j > q0 + qi)) s[j] = -INFINITY;   // causal: keys after the query (clip/attention.py:44)
             mx = fmaxf(mx, s[j]);
         }
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -102,31 +102,37 @@ attention_f32_kernel(const float* __restrict__ q, long long q_row, long long q_b
 template <int D>
 int launch(const float* q, long long q_row, long long q_batch, const float* k, long long k_row, long long k_batch,
            const float* v, long long v_row, long long v_batch, float* out, long long o_row, long long o_batch,
-           int B, int heads, int Sq, int Sk, float scale, cudaStream_t s) {
+           int B, int heads, int Sq, int Sk, float scale, int causal, cudaStream_t s) {
     const size_t smem = sizeof(float) * ((size_t)(BQ + BKV) * (D + 1) + (size_t)BKV * D + (size_t)BQ * (BKV + 1));
     SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(attention_f32_kernel<D>), (int)smem));
     dim3 grid((Sq + BQ - 1) / BQ, B * heads);
     SDK_CUDA(sdk_launch(attention_f32_kernel<D>, dim3(grid), dim3(THREADS), (size_t)(smem), s, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch,
-                                                        out, o_row, o_batch, heads, Sq, Sk, scale));
+                                                        out, o_row, o_batch, heads, Sq, Sk, scale, causal));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
 
 }  // namespace
 
-extern "C" int sdk_attention_f32(const float* q, int64_t q_row, int64_t q_batch, const float* k, int64_t k_row, int64_t k_batch,
+extern "C" int sdk_attention_f32_ex(const float* q, int64_t q_row, int64_t q_batch, const float* k, int64_t k_row, int64_t k_batch,
                                  const float* v, int64_t v_row, int64_t v_batch, float* out, int64_t o_row, int64_t o_batch,
-                                 int B, int heads, int Sq, int Sk, int D, float scale, void* stream) {
-    SDK_CHECK_ARG(q && k && v && out, "sdk_attention_f32: null pointer");
-    SDK_CHECK_ARG(B > 0 && heads > 0 && Sq > 0 && Sk > 0 && B * heads < 65536, "sdk_attention_f32: bad sizes");
+                                 int B, int heads, int Sq, int Sk, int D, float scale, int causal, void* stream) {
+    SDK_CHECK_ARG(q && k && v && out, "sdk_attention_f32_ex: null pointer");
+    SDK_CHECK_ARG(B > 0 && heads > 0 && Sq > 0 && Sk > 0 && B * heads < 65536, "sdk_attention_f32_ex: bad sizes");
     cudaStream_t s = (cudaStream_t)stream;
-#define ATT(DD) return launch<DD>(q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch, out, o_row, o_batch, B, heads, Sq, Sk, scale, s)
+#define ATT(DD) return launch<DD>(q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch, out, o_row, o_batch, B, heads, Sq, Sk, scale, causal, s)
     switch (D) {
         case 40: ATT(40);
         case 64: ATT(64);
         case 80: ATT(80);
         case 160: ATT(160);
-        default: return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_attention_f32: head_dim %d not in {40,64,80,160}", D);
+        default: return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_attention_f32_ex: head_dim %d not in {40,64,80,160}", D);
     }
 #undef ATT
+}
+
+extern "C" int sdk_attention_f32(const float* q, int64_t q_row, int64_t q_batch, const float* k, int64_t k_row, int64_t k_batch,
+                                 const float* v, int64_t v_row, int64_t v_batch, float* out, int64_t o_row, int64_t o_batch,
+                                 int B, int heads, int Sq, int Sk, int D, float scale, void* stream) {
+    return sdk_attention_f32_ex(q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch, out, o_row, o_batch, B, heads, Sq, Sk, D, scale, 0, stream);
 }

@@ -53,7 +53,7 @@ template <int D> struct AttnGeo {
 struct alignas(64) AttnParams {
     CUtensorMap tmQ, tmK, tmV;
     __nv_bfloat16* out; long long o_row, o_batch;
-    int heads, Sq, Sk, kv_bcast;
+    int heads, Sq, Sk, kv_bcast, causal;
     float scale_log2;
 };
 
@@ -206,6 +206,10 @@ attention_tc_kernel(const __grid_constant__ AttnParams p) {
             if (ragged) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) if (kbase + j >= p.Sk) u[j] = 0xff800000u;     // -inf
+            }
+            if (p.causal && kbase + 31 > q0 + r) {                   // look-ahead mask (clip/attention.py:44): keys after the query
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (kbase + j > q0 + r) u[j] = 0xff800000u;
             }
             float mx = -INFINITY;
 #pragma unroll
@@ -392,6 +396,13 @@ extern "C" int sdk_attention_tc_create(const void* q, int64_t q_row, int64_t q_b
     a->grid = dim3((Sq + BQ - 1) / BQ, B * heads);
     a->D = D;
     *handle = a;
+    return SDK_OK;
+}
+
+// causal = 1: query i attends to keys <= i only (text encoders: models/clip/attention.py:38-45 with lookahead_mask=True)
+extern "C" int sdk_attention_tc_set_causal(void* handle, int causal) {
+    SDK_CHECK_ARG(handle, "sdk_attention_tc_set_causal: null handle");
+    ((AttnPlan*)handle)->prm.causal = causal ? 1 : 0;
     return SDK_OK;
 }
 

@@ -906,6 +906,65 @@ extern "C" int sdk_softmax_rows(const float* in, void* out, int out_dtype, int64
     return SDK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Text-encoder front end and activation (models/clip/openclip.py:53-71,73-84; clip.py:37-57; activation_fn.py:4-9)
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+embed_tokens_kernel(const long long* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos, float* __restrict__ out,
+                    long long rows, int S, int C, int vocab) {
+    pdl_trigger();
+    pdl_wait();
+    const int nq = C >> 2;
+    const long long total = rows * nq;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / nq;
+        const int q = (int)(i - r * nq);
+        long long id = ids[r];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);                 // nn.Embedding would raise; never read out of bounds
+        const float4 a = __ldg(reinterpret_cast<const float4*>(tok + (size_t)id * C) + q);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(pos + (size_t)(r % S) * C) + q);
+        reinterpret_cast<float4*>(out)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+}
+
+// kind 1: exact-erf GELU (nn.GELU(), openclip.py:78); kind 2: QuickGELU x * sigmoid(1.702 x) (activation_fn.py:8)
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+activation_kernel(const float* __restrict__ in, TOut* __restrict__ out, long long n4, int kind) {
+    pdl_trigger();
+    pdl_wait();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+        float y[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = kind == 1 ? gelu_erf_f(y[j]) : y[j] / (1.0f + expf(-1.702f * y[j]));
+        store4<TOut>(out + (i << 2), y[0], y[1], y[2], y[3]);
+    }
+}
+}  // namespace
+
+extern "C" int sdk_embed_tokens(const int64_t* ids, const float* tok_emb, const float* pos_emb, float* out,
+                                int64_t rows, int S, int C, int vocab, void* stream) {
+    SDK_CHECK_ARG(ids && tok_emb && pos_emb && out && rows >= 0 && S > 0 && C > 0 && C % 4 == 0 && vocab > 0, "sdk_embed_tokens: bad args");
+    if (rows == 0) return SDK_OK;
+    SDK_CUDA(sdk_launch(embed_tokens_kernel, dim3(grid_for(rows * (C / 4), 256)), dim3(256), (size_t)0, (cudaStream_t)stream,
+                        reinterpret_cast<const long long*>(ids), tok_emb, pos_emb, out, (long long)rows, S, C, vocab));
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
+extern "C" int sdk_activation(const float* in, void* out, int out_dtype, int64_t n, int kind, void* stream) {
+    SDK_CHECK_ARG(in && out && n >= 0 && n % 4 == 0 && (kind == 1 || kind == 2), "sdk_activation: bad args (n %% 4 == 0, kind 1 = GELU, 2 = QuickGELU)");
+    if (n == 0) return SDK_OK;
+    const int grid = grid_for(n / 4, 256);
+    if (out_dtype == SDK_F32) SDK_CUDA(sdk_launch(activation_kernel<float>, dim3(grid), dim3(256), (size_t)0, (cudaStream_t)stream, in, (float*)out, (long long)(n / 4), kind));
+    else if (out_dtype == SDK_BF16) SDK_CUDA(sdk_launch(activation_kernel<__nv_bfloat16>, dim3(grid), dim3(256), (size_t)0, (cudaStream_t)stream, in, (__nv_bfloat16*)out, (long long)(n / 4), kind));
+    else return sdk_fail(SDK_ERR_ARG, "sdk_activation: out_dtype %d", out_dtype);
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
 extern "C" int sdk_cast_upsample(const float* src, void* dst, int out_dtype, int B, int H, int W, int C, int up, void* stream) {
     SDK_CHECK_ARG(src && dst && (up == 1 || up == 2) && C % 4 == 0, "sdk_cast_upsample: bad args (C=%d up=%d)", C, up);
     const long long total = (long long)B * H * up * W * up * (C / 4);

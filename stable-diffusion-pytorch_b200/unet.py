@@ -593,23 +593,31 @@ class StepProgram:
                        g.data_ptr(), b.data_ptr(), int(silu), out.data_ptr(), rawp, self.act)
         return out, raw
 
-    def _ln(self, x, g, b, rows, Cc):
-        out = self.pool.get(rows, Cc, self.act)
-        self._emit(self.lib.sdk_layernorm, x.data_ptr(), g.data_ptr(), b.data_ptr(), 1e-5, out.data_ptr(), self.act, rows, Cc)
+    def _ln(self, x, g, b, rows, Cc, eps=1e-5, out_code=None):
+        code = self.act if out_code is None else out_code
+        out = self.pool.get(rows, Cc, code)
+        self._emit(self.lib.sdk_layernorm, x.data_ptr(), g.data_ptr(), b.data_ptr(), float(eps), out.data_ptr(), code, rows, Cc)
         return out
 
-    def _attention(self, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch, B, heads, Sq, Sk, D, Cc):
+    def _attention(self, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch, B, heads, Sq, Sk, D, Cc, causal=False):
         out = self.pool.get(B * Sq, Cc, self.act)
         if self.act != F32_T and D in (40, 64, 80, 160) and self.net.attn_tc:
             # tcgen05 flash attention (S and P.V on the tensor core, thread-per-row softmax)
             h = C.c_void_p()
             _lib.check(self.lib.sdk_attention_tc_create(q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch,
                                                         out.data_ptr(), Cc, Sq * Cc, B, heads, Sq, Sk, D, float(D ** -0.5), C.byref(h)))
+            if causal:
+                _lib.check(self.lib.sdk_attention_tc_set_causal(h, 1))
             self.attn_handles.append(h)
             self._emit(self.lib.sdk_attention_tc_launch, h)
             return out
-        fn = self.lib.sdk_attention_f32 if self.act == F32_T else self.lib.sdk_attention_bf16
-        self._emit(fn, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch,
+        if self.act == F32_T:
+            self._emit(self.lib.sdk_attention_f32_ex, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch,
+                       out.data_ptr(), Cc, Sq * Cc, B, heads, Sq, Sk, D, float(D ** -0.5), int(causal))
+            return out
+        if causal:
+            raise RuntimeError("causal attention in bf16 needs the tcgen05 kernel (head_dim 40/64/80/160, SDB200_ATTN_TC=1)")
+        self._emit(self.lib.sdk_attention_bf16, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch,
                    out.data_ptr(), Cc, Sq * Cc, B, heads, Sq, Sk, D, float(D ** -0.5))
         return out
 

@@ -164,3 +164,18 @@ def test_vae_oracle_matches_reference_golden(golden_dir):
         for name in ("z8", "z8x16"):
             y = VO.decode(sd, torch.from_numpy(g[name])).numpy()
             assert np.linalg.norm(y - g[f"img_{name}"]) / np.linalg.norm(g[f"img_{name}"]) < 2e-5
+
+
+def test_clip_oracle_matches_reference_golden(golden_dir):
+    """oracle/clip_oracle.text_forward restates CLIPTextModel.forward (openclip.py:133-137) and TextEncoder.forward (clip.py:28-34):
+    pinned on outputs of the unmodified reference classes; the product's parameter contract equals the oracle's."""
+    import torch
+    from oracle import clip_oracle as CO
+    from stable_diffusion_pytorch_b200.clip import text_param_spec
+    g = np.load(os.path.join(golden_dir, "clip_golden.npz"))
+    for tag, cfg, seed in (("openclip", CO.SMALL_OPENCLIP, 5), ("clip", CO.SMALL_CLIP, 6)):
+        assert text_param_spec(cfg["kind"], cfg["vocab"], cfg["hidden"], cfg["heads"], cfg["layers"], cfg["inter"], cfg["max_len"]) == CO.param_spec(**cfg)
+        sd = CO.make_state_dict(seed, **cfg)
+        with torch.no_grad():
+            y = CO.text_forward(sd, torch.from_numpy(g[f"{tag}_ids"]), **cfg).numpy()
+        assert np.linalg.norm(y - g[f"{tag}_out"]) / np.linalg.norm(g[f"{tag}_out"]) < 1e-5
