@@ -217,6 +217,8 @@ typedef struct SdkTcGemmDesc {
     int up2;                  /* 1: nearest-2x upsample + 3x3 conv (unet.py:248-251): `a` is the LOW-RES input [B][H][W][C], `out` is
                                  [B][2H][2W][N]; `w` holds FOUR parity sets of 2x2 taps, [py][px][2][2][C/64][N][64] (3x3 taps that
                                  read the same input pixel pre-summed by the host) */
+    int w_const;              /* 1: `w` is never written by a kernel of the same stream (packed weights): with programmatic dependent launch
+                                 the first weight tiles are fetched BEFORE the wait on the preceding kernel.  0 when `w` is an activation. */
 } SdkTcGemmDesc;
 int sdk_tc_gemm_create(const SdkTcGemmDesc* desc, void** handle);
 int64_t sdk_tc_gemm_workspace_bytes(void* handle);

@@ -84,6 +84,9 @@ struct alignas(64) TcParams {
     //            that fall on the same input pixel.  The parity is the outermost factor of the m-tile index; the output tensor map
     //            is {N, x, (b,y), px, py} over the [B][2H][2W][N] tensor.
     int a_stride, up2;
+    // weights are constants of the stream (never written by a kernel): with programmatic dependent launch the producer fetches the
+    // first ring of WEIGHT tiles before griddepcontrol.wait, i.e. while the preceding kernel is still draining
+    int w_const;
 };
 
 __device__ __forceinline__ void stamp(const TcParams& p, int slot) {
@@ -305,7 +308,10 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
-    pdl_wait();          // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+    // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail; the producer thread goes further
+    // when the weights are constants: it fetches its first ring of B tiles before it waits for the preceding kernel
+    const bool early_b = !TWO && p.w_const != 0;
+    if (!(early_b && warp == 0)) pdl_wait();
     if (threadIdx.x == 0) stamp(p, 1);
 
     if (warp == 0) {
@@ -313,6 +319,19 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         if (lane == 0) {
             const uint32_t stage_bytes = (uint32_t)p.rows * (BK * 2) + (uint32_t)B_STAGE_BYTES;
             const int seg0_its = p.seg_taps[0] * p.seg_kb[0];
+            int pre = 0;                                  // stages whose B tile is already travelling
+            if (early_b) {
+                pre = n_it < STAGES ? n_it : STAGES;
+                for (int i = 0; i < pre; ++i) {
+                    int it = kb_begin + i, seg = 0;
+                    if (it >= seg0_its) { it -= seg0_its; seg = 1; }
+                    const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
+                    ptx::mbar_expect_tx(&full[i], stage_bytes);
+                    if (p.w_kmajor) ptx::tma_load_3d(sB + i * B_STAGE_BYTES, &p.tmB[seg], &full[i], 0, n0, tap * p.seg_kb[seg] + kb);
+                    else ptx::tma_load_2d(sB + i * B_STAGE_BYTES, &p.tmB[seg], &full[i], tap * p.seg_C[seg] + kb * BK, n0);
+                }
+                pdl_wait();                               // the activations are the preceding kernel's output
+            }
             int s = 0; uint32_t ph = 0;
             for (int i = 0; i < n_it; ++i) {
                 int it = kb_begin + i, seg = 0;
@@ -322,6 +341,11 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 if (p.seg_ksize[seg] == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
                 const int wk = tap * p.seg_kb[seg] + kb;
                 const int ax = w0 + dx, ay = h0 + dy;
+                if (i < pre) {                            // fresh stage, bytes already expected, B already issued: only A is missing
+                    ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, ax, ay, b0);
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    continue;
+                }
                 ptx::mbar_wait(&empty[s], ph ^ 1u);
                 if (TWO) {
                     const int nb = n0 + (int)rank * B_ROWS;              // this CTA's half of the B tile
@@ -801,7 +825,8 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
-    pdl_wait();
+    const bool early_b = p.w_const != 0;                  // see conv_gemm_tc_kernel: constant weights are fetched before the wait
+    if (!(early_b && warp == 0)) pdl_wait();
 
     // tile id -> (pixel-tile origin, first output column, tile indices inside the image)
     auto coords = [&](int t, int& w0, int& h0, int& b0, int& n0, int& par) {
@@ -818,6 +843,23 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
         if (lane == 0) {
             const uint32_t stage_bytes = (uint32_t)p.rows * (BK * 2) + (uint32_t)B_STAGE_BYTES;
             const int seg0_its = p.seg_taps[0] * p.seg_kb[0];
+            int pre = 0;                                  // stages of the FIRST tile whose B tile is already travelling
+            if (early_b) {
+                if ((int)blockIdx.x < total) {
+                    int w0, h0, b0, n0, par;
+                    coords((int)blockIdx.x, w0, h0, b0, n0, par);
+                    pre = n_it < STAGES ? n_it : STAGES;
+                    for (int i = 0; i < pre; ++i) {
+                        int it = i, seg = 0;
+                        if (it >= seg0_its) { it -= seg0_its; seg = 1; }
+                        const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
+                        ptx::mbar_expect_tx(&full[i], stage_bytes);
+                        if (p.w_kmajor) ptx::tma_load_3d(sB + i * B_STAGE_BYTES, &p.tmB[seg], &full[i], 0, n0, tap * p.seg_kb[seg] + kb + (FOLD ? par * 4 * p.seg_kb[seg] : 0));
+                        else ptx::tma_load_2d(sB + i * B_STAGE_BYTES, &p.tmB[seg], &full[i], tap * p.seg_C[seg] + kb * BK, n0);
+                    }
+                }
+                pdl_wait();
+            }
             int s = 0; uint32_t ph = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 int w0, h0, b0, n0, par;
@@ -829,6 +871,12 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                     int dx = 0, dy = 0;
                     if (p.seg_ksize[seg] == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
                     else if (FOLD && p.seg_ksize[seg] == 2) { dy = (tap >> 1) + (par >> 1) - 1; dx = (tap & 1) + (par & 1) - 1; }
+                    if (pre > 0) {                        // first ring of the first tile: only A is missing
+                        --pre;
+                        ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 * a_stride + dx, h0 * a_stride + dy, b0);
+                        if (++s == STAGES) { s = 0; ph ^= 1u; }
+                        continue;
+                    }
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     ptx::mbar_expect_tx(&full[s], stage_bytes);
                     ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 * a_stride + dx, h0 * a_stride + dy, b0);
@@ -1362,6 +1410,7 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         }
     }
     p.up2 = up2 ? 1 : 0; p.a_stride = s2 ? 2 : 1;
+    p.w_const = d->w_const ? 1 : 0;
     pick_tile(d->W, d->H, d->B, &p.TW, &p.TH, &p.TB, up2);
     p.rows = p.TW * p.TH * p.TB;
     p.W = d->W; p.H = d->H; p.B = d->B;

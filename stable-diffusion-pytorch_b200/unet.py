@@ -383,8 +383,9 @@ class StepProgram:
         d.bias, d.tbias, d.tb_stride, d.residual, d.out = p.bias, p.tbias, p.tb_stride, p.residual, p.out
         d.out_dtype, d.geglu, d.out_nchw = p.out_dtype, p.geglu, p.out_nchw
         d.block_n, d.splits, d.w_kmajor, d.two_cta = self.net.tc_block_n, self.net.tc_splits, 1, self.net.tc_two_cta
+        d.w_const = 1                                          # packed weights: constants of the stream (early fetch under PDL)
         if extras and extras.get("w_rowmajor"):
-            d.w_kmajor = 0
+            d.w_kmajor, d.w_const = 0, 0                       # the B operand is an activation written by the preceding kernels
         if extras:
             if "out2" in extras:
                 d.out2, d.row_stats = extras["out2"].data_ptr(), extras["row_stats"].data_ptr()
