@@ -7,6 +7,7 @@
 // QK^T and PV run on mma.sync m16n8k16 with ldmatrix-fed fragments.  Head dims 40/64/80/160 (the
 // QK^T reduction is zero-padded to a multiple of 16).  At D=40 this kernel is bound by the exp
 // (MUFU) rate, not by the tensor pipe: 4096^2 exps per head against 2*2*4096^2*40 flops.
+#define SDK_PDL_CAT 4
 #include "common.cuh"
 
 namespace {

@@ -4,6 +4,7 @@
 // CTA = 64 queries of one (batch, head); K/V streamed in 32-key tiles through shared memory; four
 // threads cooperate on one query row (each owns 8 of the 32 scores and a quarter of the D outputs)
 // and exchange running max / sum with warp shuffles.  No score matrix is ever written to memory.
+#define SDK_PDL_CAT 2
 #include "common.cuh"
 
 namespace {

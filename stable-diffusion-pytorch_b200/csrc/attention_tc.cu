@@ -26,6 +26,7 @@
 //                is rare after the first tiles.  Nothing waits for P.V inside the loop.
 // Warp roles: warp 0 TMA producer (3-stage K and V rings), warp 1 MMA issuer + TMEM owner, warps 2..9 softmax (two threads
 // per row).  ~98 KiB of smem and 256 TMEM columns per CTA: two CTAs per SM.
+#define SDK_PDL_CAT 3
 #include "common.cuh"
 #include "ptx.cuh"
 #include <new>

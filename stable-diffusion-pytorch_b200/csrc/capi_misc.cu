@@ -1,6 +1,8 @@
 // Library-level C-ABI entry points: error text, version, device info.
+#define SDK_PDL_CAT 8
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = {0};
 char* sdk_err_buf() { return g_err; }
@@ -46,6 +48,13 @@ cudaError_t sdk_ensure_dyn_smem(const void* fn, int bytes) {
 
 static int g_pdl = 0;   // measured on B200 inside CUDA graphs: -3.5 % with early triggers -> off by default
 bool sdk_pdl_enabled() { return g_pdl != 0; }
+bool sdk_pdl_enabled_cat(int cat) {
+    // default: the tensor-core GEMM family (category 0) and the tcgen05 attention (3), whose reads of earlier kernels' output go
+    // through TMA / ld.global.cg.  The elementwise / SIMT kernels read activations through ld.global.nc (__ldg, const __restrict__),
+    // which is not coherent for a grid that started before its producer finished (see gemm_tc.cu) -> no PDL for them.
+    static const unsigned mask = getenv("SDB200_PDL_MASK") ? (unsigned)strtoul(getenv("SDB200_PDL_MASK"), nullptr, 0) : 0x9u;
+    return g_pdl != 0 && ((mask >> cat) & 1u);
+}
 // enable (1) / disable (0, default) programmatic dependent launch for all subsequent launches
 extern "C" int sdk_set_pdl(int enabled) { g_pdl = enabled ? 1 : 0; return SDK_OK; }
 

@@ -88,6 +88,12 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool sdk_pdl_enabled();
+// per-source-file category (SDK_PDL_CAT, defined before including this header) so that PDL can be switched off for one family of
+// kernels while hunting an ordering bug: SDB200_PDL_MASK is a bit mask of the categories that MAY use PDL (default: all)
+#ifndef SDK_PDL_CAT
+#define SDK_PDL_CAT 0
+#endif
+bool sdk_pdl_enabled_cat(int cat);
 // one-time per kernel: ask for the max-shared-memory L1 carve-out so that the SM configuration does not flip between the
 // big-smem tensor-core kernels and the small elementwise kernels that run in between (a carve-out change drains the SM)
 void sdk_prefer_max_smem_once(const void* fn);
@@ -99,7 +105,7 @@ static inline cudaError_t sdk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 b
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = sdk_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = sdk_pdl_enabled_cat(SDK_PDL_CAT) ? 1 : 0;
     sdk_prefer_max_smem_once(reinterpret_cast<const void*>(kernel));
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }

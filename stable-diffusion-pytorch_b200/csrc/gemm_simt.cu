@@ -9,6 +9,7 @@
 //
 // Tiling: 128x128x16 CTA tile, 256 threads, 8x8 register tile per thread, A/B staged transposed in
 // shared memory (conflict-free float4 fragment reads), register double-buffering of the next tile.
+#define SDK_PDL_CAT 1
 #include "common.cuh"
 #include "../../include/sdb200.h"
 

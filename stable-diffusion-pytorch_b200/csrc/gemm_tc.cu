@@ -1,3 +1,10 @@
+// NOTE on loads: these kernels are launched with programmatic dependent launch (their CTAs start while the preceding kernel is still
+// running and block in griddepcontrol.wait before the first access to its output).  Data written by earlier kernels of the stream
+// (activations, residuals, the time-bias row, split-K partials, row statistics) is therefore read through TMA or ld.global.cg
+// (__ldcg), NEVER through the non-coherent path (__ldg / const __restrict__): ld.global.nc is only defined for data that is
+// read-only during the WHOLE lifetime of the grid, and a line cached by an earlier launch is not invalidated for a grid that
+// started early (observed as stale values in the fp32 program).  Only true constants (weights, bias, gamma) use __ldg.
+//
 // tcgen05 / TMEM / TMA implicit-GEMM convolution and linear layers — the tensor-core path of the
 // UNet (84 % of the step's FLOPs).
 //
@@ -23,6 +30,7 @@
 // * Small-M layers (deep UNet levels at small batch) are weight-streaming bound: split-K over
 //   blockIdx.z writes fp32 partials [split][row][N]; a second, fully parallel kernel sums the splits in
 //   fixed order (deterministic) and applies the epilogue.
+#define SDK_PDL_CAT 0
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/sdb200.h"
@@ -97,6 +105,22 @@ __device__ __forceinline__ void stamp(const TcParams& p, int slot) {
     }
 }
 
+// Position of a k-block inside the (segment, tap, 64-channel block) iteration space, advanced incrementally: the producer thread
+// issues two TMA loads per ~300 ns k-block, and a runtime integer division per iteration (it / seg_kb) measurably slows its loop.
+struct KIter {
+    int seg, tap, kb;
+    __device__ __forceinline__ void init(const TcParams& p, int it) {
+        const int seg0 = p.seg_taps[0] * p.seg_kb[0];
+        seg = 0;
+        if (it >= seg0) { it -= seg0; seg = 1; }
+        tap = it / p.seg_kb[seg];
+        kb = it - tap * p.seg_kb[seg];
+    }
+    __device__ __forceinline__ void next(const TcParams& p) {
+        if (++kb == p.seg_kb[seg]) { kb = 0; if (++tap == p.seg_taps[seg]) { tap = 0; ++seg; } }
+    }
+};
+
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* v) {
     __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
     __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
@@ -129,7 +153,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
             const float4* tb = reinterpret_cast<const float4*>(p.tbias + (long long)b * p.tb_stride + n);
             float4 tv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tv[j] = __ldg(tb + j);
+            for (int j = 0; j < 8; ++j) tv[j] = __ldcg(tb + j);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { v[4 * j] += tv[j].x; v[4 * j + 1] += tv[j].y; v[4 * j + 2] += tv[j].z; v[4 * j + 3] += tv[j].w; }
         }
@@ -141,7 +165,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
         if (p.tbias) {
             const float* tb = p.tbias + (long long)b * p.tb_stride + n;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(tb + j);
+            for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldcg(tb + j);
         }
     }
     if (p.geglu) {
@@ -152,7 +176,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
         const long long off = grow * p.Nout + (n >> 1);
         if (p.residual) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] += __ldg(p.residual + off + j);
+            for (int j = 0; j < 16; ++j) o[j] += __ldcg(p.residual + off + j);
         }
         if (p.out_dtype == SDK_BF16) {
             store_bf16x8((__nv_bfloat16*)p.out + off, o);
@@ -169,7 +193,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
             if (n + j < N) {
                 float y = v[j];
                 const long long o = (((long long)b * N + n + j) * p.H + oy) * p.W + ox;
-                if (p.residual) y += __ldg(p.residual + o);
+                if (p.residual) y += __ldcg(p.residual + o);
                 if (p.out_dtype == SDK_BF16) ((__nv_bfloat16*)p.out)[o] = __float2bfloat16_rn(y);
                 else ((float*)p.out)[o] = y;
             }
@@ -184,7 +208,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
         } else if (p.residual) {
             float4 rv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rv[j] = __ldg(reinterpret_cast<const float4*>(p.residual + off) + j);
+            for (int j = 0; j < 8; ++j) rv[j] = __ldcg(reinterpret_cast<const float4*>(p.residual + off) + j);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { v[4 * j] += rv[j].x; v[4 * j + 1] += rv[j].y; v[4 * j + 2] += rv[j].z; v[4 * j + 3] += rv[j].w; }
         }
@@ -200,7 +224,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, float* v, int 
         for (int j = 0; j < 32; ++j) {
             if (n + j < N) {
                 float y = v[j];
-                if (p.residual) y += __ldg(p.residual + off + j);
+                if (p.residual) y += __ldcg(p.residual + off + j);
                 if (p.out_dtype == SDK_BF16) ((__nv_bfloat16*)p.out)[off + j] = __float2bfloat16_rn(y);
                 else ((float*)p.out)[off + j] = y;
             }
@@ -318,25 +342,23 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         // ================= TMA producer =================
         if (lane == 0) {
             const uint32_t stage_bytes = (uint32_t)p.rows * (BK * 2) + (uint32_t)B_STAGE_BYTES;
-            const int seg0_its = p.seg_taps[0] * p.seg_kb[0];
             int pre = 0;                                  // stages whose B tile is already travelling
             if (early_b) {
                 pre = n_it < STAGES ? n_it : STAGES;
-                for (int i = 0; i < pre; ++i) {
-                    int it = kb_begin + i, seg = 0;
-                    if (it >= seg0_its) { it -= seg0_its; seg = 1; }
-                    const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
+                KIter kp;
+                kp.init(p, kb_begin);
+                for (int i = 0; i < pre; ++i, kp.next(p)) {
                     ptx::mbar_expect_tx(&full[i], stage_bytes);
-                    if (p.w_kmajor) ptx::tma_load_3d(sB + i * B_STAGE_BYTES, &p.tmB[seg], &full[i], 0, n0, tap * p.seg_kb[seg] + kb);
-                    else ptx::tma_load_2d(sB + i * B_STAGE_BYTES, &p.tmB[seg], &full[i], tap * p.seg_C[seg] + kb * BK, n0);
+                    if (p.w_kmajor) ptx::tma_load_3d(sB + i * B_STAGE_BYTES, &p.tmB[kp.seg], &full[i], 0, n0, kp.tap * p.seg_kb[kp.seg] + kp.kb);
+                    else ptx::tma_load_2d(sB + i * B_STAGE_BYTES, &p.tmB[kp.seg], &full[i], kp.tap * p.seg_C[kp.seg] + kp.kb * BK, n0);
                 }
                 pdl_wait();                               // the activations are the preceding kernel's output
             }
             int s = 0; uint32_t ph = 0;
-            for (int i = 0; i < n_it; ++i) {
-                int it = kb_begin + i, seg = 0;
-                if (it >= seg0_its) { it -= seg0_its; seg = 1; }
-                const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
+            KIter ki;
+            ki.init(p, kb_begin);
+            for (int i = 0; i < n_it; ++i, ki.next(p)) {
+                const int seg = ki.seg, tap = ki.tap, kb = ki.kb;
                 int dx = 0, dy = 0;
                 if (p.seg_ksize[seg] == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
                 const int wk = tap * p.seg_kb[seg] + kb;
@@ -418,7 +440,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 float x = 0.f;
                 if (n0 + j < p.N) {
                     if (p.bias) x = __ldg(p.bias + n0 + j);
-                    if (p.tbias && b0 + tbi < p.B) x += __ldg(p.tbias + (long long)(b0 + tbi) * p.tb_stride + n0 + j);
+                    if (p.tbias && b0 + tbi < p.B) x += __ldcg(p.tbias + (long long)(b0 + tbi) * p.tb_stride + n0 + j);
                 }
                 s_add[i] = x;
             }
@@ -693,19 +715,19 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                         float4 a = ad;
                         if (staged) a = *reinterpret_cast<const float4*>(s_add + (pk[it] >> 24) * BN + c * 32 + c4);
                         else if (p.tbias) {
-                            const float4 tv = __ldg(reinterpret_cast<const float4*>(p.tbias + (long long)(b0 + (pk[it] >> 24)) * p.tb_stride + ncol));
+                            const float4 tv = __ldcg(reinterpret_cast<const float4*>(p.tbias + (long long)(b0 + (pk[it] >> 24)) * p.tb_stride + ncol));
                             a.x += tv.x; a.y += tv.y; a.z += tv.z; a.w += tv.w;
                         }
                         float4 o = make_float4(x[it].x + a.x, x[it].y + a.y, x[it].z + a.z, x[it].w + a.w);
                         if (p.geglu) {                                    // (value, gate) pairs -> 2 outputs per float4
                             const long long off = row * Nout + (ncol >> 1);
                             float o0 = o.x * gelu_erf_f(o.y), o1 = o.z * gelu_erf_f(o.w);
-                            if (p.residual) { const float2 r2 = __ldg(reinterpret_cast<const float2*>(p.residual + off)); o0 += r2.x; o1 += r2.y; }
+                            if (p.residual) { const float2 r2 = __ldcg(reinterpret_cast<const float2*>(p.residual + off)); o0 += r2.x; o1 += r2.y; }
                             if (p.out_dtype == SDK_BF16) *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)p.out + off) = __floats2bfloat162_rn(o0, o1);
                             else *reinterpret_cast<float2*>((float*)p.out + off) = make_float2(o0, o1);
                         } else {
                             const long long off = row * p.N + ncol;
-                            if (p.residual) { const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + off)); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
+                            if (p.residual) { const float4 r4 = __ldcg(reinterpret_cast<const float4*>(p.residual + off)); o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w; }
                             if (p.out_dtype == SDK_BF16) {
                                 __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
                                 uint2 w2; w2.x = *reinterpret_cast<unsigned*>(&lo); w2.y = *reinterpret_cast<unsigned*>(&hi);
@@ -842,20 +864,18 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
         // ================= TMA producer =================
         if (lane == 0) {
             const uint32_t stage_bytes = (uint32_t)p.rows * (BK * 2) + (uint32_t)B_STAGE_BYTES;
-            const int seg0_its = p.seg_taps[0] * p.seg_kb[0];
             int pre = 0;                                  // stages of the FIRST tile whose B tile is already travelling
             if (early_b) {
                 if ((int)blockIdx.x < total) {
                     int w0, h0, b0, n0, par;
                     coords((int)blockIdx.x, w0, h0, b0, n0, par);
                     pre = n_it < STAGES ? n_it : STAGES;
-                    for (int i = 0; i < pre; ++i) {
-                        int it = i, seg = 0;
-                        if (it >= seg0_its) { it -= seg0_its; seg = 1; }
-                        const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
+                    KIter kp;
+                    kp.init(p, 0);
+                    for (int i = 0; i < pre; ++i, kp.next(p)) {
                         ptx::mbar_expect_tx(&full[i], stage_bytes);
-                        if (p.w_kmajor) ptx::tma_load_3d(sB + i * B_STAGE_BYTES, &p.tmB[seg], &full[i], 0, n0, tap * p.seg_kb[seg] + kb + (FOLD ? par * 4 * p.seg_kb[seg] : 0));
-                        else ptx::tma_load_2d(sB + i * B_STAGE_BYTES, &p.tmB[seg], &full[i], tap * p.seg_C[seg] + kb * BK, n0);
+                        if (p.w_kmajor) ptx::tma_load_3d(sB + i * B_STAGE_BYTES, &p.tmB[kp.seg], &full[i], 0, n0, kp.tap * p.seg_kb[kp.seg] + kp.kb + (FOLD ? par * 4 * p.seg_kb[kp.seg] : 0));
+                        else ptx::tma_load_2d(sB + i * B_STAGE_BYTES, &p.tmB[kp.seg], &full[i], kp.tap * p.seg_C[kp.seg] + kp.kb * BK, n0);
                     }
                 }
                 pdl_wait();
@@ -864,10 +884,10 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 int w0, h0, b0, n0, par;
                 coords(t, w0, h0, b0, n0, par);
-                for (int i = 0; i < n_it; ++i) {
-                    int it = i, seg = 0;
-                    if (it >= seg0_its) { it -= seg0_its; seg = 1; }
-                    const int tap = it / p.seg_kb[seg], kb = it - tap * p.seg_kb[seg];
+                KIter ki;
+                ki.seg = 0; ki.tap = 0; ki.kb = 0;
+                for (int i = 0; i < n_it; ++i, ki.next(p)) {
+                    const int seg = ki.seg, tap = ki.tap, kb = ki.kb;
                     int dx = 0, dy = 0;
                     if (p.seg_ksize[seg] == 3) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
                     else if (FOLD && p.seg_ksize[seg] == 2) { dy = (tap >> 1) + (par >> 1) - 1; dx = (tap & 1) + (par & 1) - 1; }
@@ -951,7 +971,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                 const int tbi = i / BN, j = i - tbi * BN;
                 float x = 0.f;
                 if (p.bias) x = __ldg(p.bias + n0 + j);
-                if (p.tbias && b0 + tbi < p.B) x += __ldg(p.tbias + (long long)(b0 + tbi) * p.tb_stride + n0 + j);
+                if (p.tbias && b0 + tbi < p.B) x += __ldcg(p.tbias + (long long)(b0 + tbi) * p.tb_stride + n0 + j);
                 s_add_t[i] = x;
             }
             if (p.ln_colsum)
@@ -1141,13 +1161,13 @@ splitk_reduce_kernel(const __grid_constant__ TcParams p) {
         for (int j = 0; j < 4; ++j) {
             if (n + j < N) {
                 if (p.bias) v[j] += __ldg(p.bias + n + j);
-                if (p.tbias) v[j] += __ldg(p.tbias + (long long)b * p.tb_stride + n + j);
+                if (p.tbias) v[j] += __ldcg(p.tbias + (long long)b * p.tb_stride + n + j);
             }
         }
         if (p.geglu) {
             const long long off = grow * p.Nout + (n >> 1);
             float o0 = v[0] * gelu_erf_f(v[1]), o1 = v[2] * gelu_erf_f(v[3]);
-            if (p.residual) { o0 += __ldg(p.residual + off); o1 += __ldg(p.residual + off + 1); }
+            if (p.residual) { o0 += __ldcg(p.residual + off); o1 += __ldcg(p.residual + off + 1); }
             if (p.out_dtype == SDK_BF16) *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)p.out + off) = __floats2bfloat162_rn(o0, o1);
             else *reinterpret_cast<float2*>((float*)p.out + off) = make_float2(o0, o1);
         } else if (p.out_nchw || n + 4 > N) {
@@ -1155,14 +1175,14 @@ splitk_reduce_kernel(const __grid_constant__ TcParams p) {
                 if (n + j >= N) break;
                 const long long o = p.out_nchw ? (((long long)b * N + n + j) * p.H + oy) * p.W + ox : grow * N + n + j;
                 float y = v[j];
-                if (p.residual) y += __ldg(p.residual + o);
+                if (p.residual) y += __ldcg(p.residual + o);
                 if (p.out_dtype == SDK_BF16) ((__nv_bfloat16*)p.out)[o] = __float2bfloat16_rn(y);
                 else ((float*)p.out)[o] = y;
             }
         } else {
             const long long off = grow * N + n;
             if (p.residual) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+                const float4 r = __ldcg(reinterpret_cast<const float4*>(p.residual + off));
                 v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
             }
             if (p.out_dtype == SDK_BF16) {
@@ -1192,7 +1212,7 @@ splitk_reduce_stats_kernel(const __grid_constant__ TcParams p) {
     float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) add = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     if (p.tbias) {
-        const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.tbias + (long long)b * p.tb_stride + n));
+        const float4 t4 = __ldcg(reinterpret_cast<const float4*>(p.tbias + (long long)b * p.tb_stride + n));
         add.x += t4.x; add.y += t4.y; add.z += t4.z; add.w += t4.w;
     }
     float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1220,7 +1240,7 @@ splitk_reduce_stats_kernel(const __grid_constant__ TcParams p) {
         }
         v[0] += add.x; v[1] += add.y; v[2] += add.z; v[3] += add.w;
         if (p.residual) {
-            const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+            const float4 r4 = __ldcg(reinterpret_cast<const float4*>(p.residual + off));
             v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
         }
         *reinterpret_cast<float4*>((float*)p.out + off) = make_float4(v[0], v[1], v[2], v[3]);
@@ -1410,7 +1430,8 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         }
     }
     p.up2 = up2 ? 1 : 0; p.a_stride = s2 ? 2 : 1;
-    p.w_const = d->w_const ? 1 : 0;
+    static const int early_mode = getenv("SDB200_TC_EARLY_W") ? atoi(getenv("SDB200_TC_EARLY_W")) : 1;
+    p.w_const = (d->w_const && early_mode) ? 1 : 0;
     pick_tile(d->W, d->H, d->B, &p.TW, &p.TH, &p.TB, up2);
     p.rows = p.TW * p.TH * p.TB;
     p.W = d->W; p.H = d->H; p.B = d->B;
@@ -1797,7 +1818,7 @@ extern "C" int sdk_tc_gemm_destroy(void* handle) {
 // ---- stride-2 3x3 conv support: gather fp32 NHWC -> bf16 [B*Ho*Wo][9*C] (k = tap*C + c), pad 1 ----
 namespace {
 __global__ void __launch_bounds__(256)
-im2col_s2_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C, int Ho, int Wo) {
+im2col_s2_kernel(const float* src, __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C, int Ho, int Wo) {
     pdl_trigger();
     pdl_wait();
     const int nq = C >> 2;
@@ -1811,7 +1832,7 @@ im2col_s2_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
         const int b = (int)(r / Ho);
         const int iy = oy * 2 + tap / 3 - 1, ix = ox * 2 + tap % 3 - 1;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)b * H + iy) * W + ix) * C) + q);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldcg(reinterpret_cast<const float4*>(src + (((size_t)b * H + iy) * W + ix) * C) + q);
         __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
         uint2 u; u.x = *reinterpret_cast<unsigned*>(&lo); u.y = *reinterpret_cast<unsigned*>(&hi);
         *reinterpret_cast<uint2*>(dst + (i << 2)) = u;

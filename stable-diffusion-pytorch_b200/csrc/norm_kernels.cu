@@ -10,6 +10,7 @@
 //   LayerNorm over C                                                             (unet.py:102-108)
 //   cast (+ nearest 2x upsample)                                                 (unet.py:250)
 //   NCHW -> NHWC for the 4-channel latent                                        (unet.py:256 input)
+#define SDK_PDL_CAT 5
 #include "common.cuh"
 #include <stdlib.h>
 #include <cooperative_groups.h>

@@ -15,6 +15,7 @@
 //     v-pred:    x0 = s2*x - s1*e   ; ee = s2*e + s1*x
 //     x' = sqrt_prev*x0 + dir*ee   (+ noise*std when eta > 0)
 //   DDPM  (models/scheduler/ddpm.py:72-81)   x' = inv*(x - ce*e) + std*z
+#define SDK_PDL_CAT 6
 #include "common.cuh"
 
 namespace {

@@ -3,6 +3,7 @@
 // mat-vec over the row-concatenated weight matrix.  n (distinct timesteps) is 1 in sampling and B in
 // training-style calls, so this is a weight-streaming (HBM-bound) op: one warp per output row,
 // 16-byte loads along K, warp-shuffle reduction, fp32 accumulate.
+#define SDK_PDL_CAT 7
 #include "common.cuh"
 
 namespace {
