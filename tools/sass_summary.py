@@ -41,7 +41,8 @@ def main():
     print(f"# {'kernel':<78} {'instr':>6} " + " ".join(f"{m:>8}" for m in MNEMONICS))
     for fn in order:
         c = counts[fn]
-        name = re.sub(r"\(.*", "", demangle(fn).replace("(anonymous namespace)::", "").replace("<unnamed>::", ""))
+        name = demangle(fn).replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+        name = re.sub(r"\([^()]*\)$", "", name).replace("(int)", "").replace("(bool)", "").replace("void ", "")
         print(f"  {name[:78]:<78} {c['_total']:>6} " + " ".join(f"{c[m]:>8}" for m in MNEMONICS))
     tot = collections.Counter()
     for c in counts.values():
