@@ -95,6 +95,7 @@ struct alignas(64) TcParams {
     // weights are constants of the stream (never written by a kernel): with programmatic dependent launch the producer fetches the
     // first ring of WEIGHT tiles before griddepcontrol.wait, i.e. while the preceding kernel is still draining
     int w_const;
+    int b_resident;              // persistent kernel: weight-stationary tile walk (see conv_gemm_tc_persistent_kernel)
 };
 
 __device__ __forceinline__ void stamp(const TcParams& p, int slot) {
@@ -810,16 +811,23 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
     // shared memory: [A stages][B stages][2 x 2 output chunks][2 residual chunks (only with a TMA residual)][barriers][2 x s_add][2 x s_stat]
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // Weight-stationary form (b_res, FOLD = false only): the CTA owns ONE n-tile and walks m-tiles; all total_kb k-blocks of its
+    // weight tile are loaded once into sB (slot = k-block) and stay there, so a k-block costs the SM 16 KiB of L2->smem traffic (the
+    // A tile) instead of 16 KiB + BN*128 B.  Short-K linears (q/k/v, attention out, GEGLU-in at K = 320 / 640) are bound by exactly
+    // that feed (~46 B/clk per SM) once their grid has more than one wave.
+    const bool b_res = !FOLD && p.b_resident != 0;
+    const int b_slots = b_res ? p.total_kb : STAGES;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint8_t* sOut = sB + STAGES * B_STAGE_BYTES;
+    uint8_t* sOut = sB + b_slots * B_STAGE_BYTES;
     uint8_t* sRes = sOut + PERS_EPI_BUFS * p.epi_buf_stride;
     uint64_t* full = reinterpret_cast<uint64_t*>(sRes + (p.epi_res ? 2 * RES_BUF_BYTES : 0));
     uint64_t* empty = full + MAX_STAGES;
     uint64_t* acc_full = empty + MAX_STAGES;          // [2] MMA -> epilogue: accumulator buffer complete
     uint64_t* acc_empty = acc_full + 2;               // [2] epilogue -> MMA: accumulator buffer drained
     uint64_t* res_full = acc_empty + 2;               // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+    uint64_t* bres_full = res_full + 2;               // resident weight tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 1);
     float* s_add = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
     float2* s_stat_all = reinterpret_cast<float2*>(s_add + 2 * ADD_ROWS * BN);  // s_add is double-buffered by tile parity; [2 groups][2][4][32]
     float* s_lns = reinterpret_cast<float*>(s_stat_all + 2 * 2 * 4 * 32);       // [2][BN] column sums of the gamma-scaled weights (folded LayerNorm), by tile parity
@@ -833,6 +841,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 2); ptx::mbar_init(&res_full[i], 1); }
+        ptx::mbar_init(bres_full, 1);
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmA[0]);
         ptx::prefetch_tmap(&p.tmB[0]);
@@ -860,12 +869,31 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
         w0 = tw * p.TW; h0 = th * p.TH; b0 = m * p.TB; n0 = ni * BN;
     };
 
+    // j-th tile of this CTA: round-robin over all tiles, or (weight-stationary) the m-tiles of one fixed n-tile
+    const int ws_groups = b_res ? (int)gridDim.x / n_tiles : 1;
+    const int t_first = b_res ? ((int)blockIdx.x / n_tiles) * n_tiles + (int)blockIdx.x % n_tiles : (int)blockIdx.x;
+    const int t_step = b_res ? ws_groups * n_tiles : (int)gridDim.x;
+
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            const uint32_t stage_bytes = (uint32_t)p.rows * (BK * 2) + (uint32_t)B_STAGE_BYTES;
+            const uint32_t stage_bytes = (uint32_t)p.rows * (BK * 2) + (b_res ? 0u : (uint32_t)B_STAGE_BYTES);
             int pre = 0;                                  // stages of the FIRST tile whose B tile is already travelling
-            if (early_b) {
+            if (b_res) {
+                // the whole weight tile of this CTA's n-tile, once (before the wait on the preceding kernel when the weights are constants)
+                if (!early_b) pdl_wait();
+                if (t_first < total) {
+                    const int n0r = (t_first % n_tiles) * BN;
+                    ptx::mbar_expect_tx(bres_full, (uint32_t)n_it * (uint32_t)B_STAGE_BYTES);
+                    KIter kp;
+                    kp.init(p, 0);
+                    for (int i = 0; i < n_it; ++i, kp.next(p)) {
+                        if (p.w_kmajor) ptx::tma_load_3d(sB + i * B_STAGE_BYTES, &p.tmB[kp.seg], bres_full, 0, n0r, kp.tap * p.seg_kb[kp.seg] + kp.kb);
+                        else ptx::tma_load_2d(sB + i * B_STAGE_BYTES, &p.tmB[kp.seg], bres_full, kp.tap * p.seg_C[kp.seg] + kp.kb * BK, n0r);
+                    }
+                }
+                if (early_b) pdl_wait();
+            } else if (early_b) {
                 if ((int)blockIdx.x < total) {
                     int w0, h0, b0, n0, par;
                     coords((int)blockIdx.x, w0, h0, b0, n0, par);
@@ -881,7 +909,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                 pdl_wait();
             }
             int s = 0; uint32_t ph = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            for (int t = t_first; t < total; t += t_step) {
                 int w0, h0, b0, n0, par;
                 coords(t, w0, h0, b0, n0, par);
                 KIter ki;
@@ -900,6 +928,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     ptx::mbar_expect_tx(&full[s], stage_bytes);
                     ptx::tma_load_4d(sA + s * A_STAGE_BYTES, &p.tmA[seg], &full[s], kb * BK, w0 * a_stride + dx, h0 * a_stride + dy, b0);
+                    if (b_res) { if (++s == STAGES) { s = 0; ph ^= 1u; } continue; }
                     if (p.w_kmajor) ptx::tma_load_3d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], 0, n0, tap * p.seg_kb[seg] + kb + (FOLD ? par * 4 * p.seg_kb[seg] : 0));
                     else ptx::tma_load_2d(sB + s * B_STAGE_BYTES, &p.tmB[seg], &full[s], tap * p.seg_C[seg] + kb * BK, n0);
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -911,7 +940,8 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             int lt = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            if (b_res && t_first < total) { ptx::mbar_wait(bres_full, 0); ptx::tc_fence_after(); }
+            for (int t = t_first; t < total; t += t_step, ++lt) {
                 const int ab = lt & 1;
                 ptx::mbar_wait(&acc_empty[ab], ((uint32_t)(lt >> 1) & 1u) ^ 1u);     // epilogue of tile lt-2 has drained this buffer
                 ptx::tc_fence_after();
@@ -920,7 +950,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                     ptx::mbar_wait(&full[s], ph);
                     ptx::tc_fence_after();
                     const uint64_t da = ptx::umma_smem_desc_sw128(ptx::smem_u32(sA + s * A_STAGE_BYTES));
-                    const uint64_t db = ptx::umma_smem_desc_sw128(ptx::smem_u32(sB + s * B_STAGE_BYTES));
+                    const uint64_t db = ptx::umma_smem_desc_sw128(ptx::smem_u32(sB + (b_res ? i : s) * B_STAGE_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
                         ptx::umma_bf16(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (i > 0 || k > 0) ? 1u : 0u);
@@ -953,7 +983,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
         uint32_t res_use = 0;                           // completed uses of this group's residual buffer (mbarrier parity)
         uint32_t gc = 0;                                // output chunks this group has issued so far (ring position)
         int lt = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+        for (int t = t_first; t < total; t += t_step, ++lt) {
             int w0, h0, b0, n0, par;
             coords(t, w0, h0, b0, n0, par);
             const int ab = lt & 1;
@@ -1639,6 +1669,22 @@ extern "C" int sdk_tc_gemm_create(const SdkTcGemmDesc* d, void** handle) {
         g->persistent = mode > 0 && !two && splits == 1 && p.epi_tma && (mode > 1 || tiles >= 2LL * sms || up2 || s2);
         if (g->persistent) {
             const int fixed_p = fixed_smem(bn, p.epi_res != 0) + PERS_EPI_BUFS * p.epi_buf_stride + ADD_ROWS * bn * 4 + 2 * 4 * 32 * 8 + bn * 4;
+            // weight-stationary walk (see the kernel): every k-block of the CTA's weight tile resident in shared memory beside >= 3 A
+            // stages; pays when a CTA computes several tiles (>= 2 waves).  SDB200_TC_WS=0 turns it off, =2 takes it whenever it fits.
+            static const int ws_mode = getenv("SDB200_TC_WS") ? atoi(getenv("SDB200_TC_WS")) : 1;
+            const int bres_bytes = p.total_kb * bn * BK * 2;
+            int ws_a = (232448 - fixed_p - bres_bytes) / A_STAGE_BYTES;
+            if (ws_a > 6) ws_a = 6;
+            if (ws_mode > 0 && !up2 && !s2 && n_tiles <= sms && ws_a >= 3 && (ws_mode > 1 || tiles >= 2LL * sms)) {
+                p.b_resident = 1;
+                p.stages = ws_a;
+                g->smem_bytes = fixed_p + ws_a * A_STAGE_BYTES + bres_bytes;
+                g->co_resident = false;
+                g->grid = dim3((unsigned)((sms / n_tiles) * n_tiles), 1, 1);
+                if ((long long)g->grid.x > tiles) g->grid = dim3((unsigned)((tiles / n_tiles) * n_tiles), 1, 1);
+                *handle = g;
+                return SDK_OK;
+            }
             int st = (232448 - fixed_p) / stage_smem(bn, false);
             if (st > MAX_STAGES) st = MAX_STAGES;
             if (st < 3 && !(st == 2 && (p.total_kb <= 8 || up2 || s2))) g->persistent = false;   // 2 stages only where the whole K loop is a handful of k-blocks
@@ -1765,7 +1811,7 @@ extern "C" int sdk_tc_gemm_info(void* handle, int* out, int n) {
     out[4] = g->prm.TW; out[5] = g->prm.TH; out[6] = g->prm.TB; out[7] = g->prm.total_kb;
     if (n >= 9) out[8] = g->two_cta ? 2 : 1;
     if (n >= 10) out[9] = g->prm.fixup;
-    if (n >= 11) out[10] = g->persistent ? 1 : 0;
+    if (n >= 11) out[10] = g->persistent ? (g->prm.b_resident ? 2 : 1) : 0;
     return SDK_OK;
 }
 

@@ -122,6 +122,11 @@ TC_CASES = [
     ("conv_res_bn256", 2, 32, 32, 640, 1280, 3, "per", True, False, F32_T, 0, 256, 1),
     ("conv_res_bn32", 4, 8, 8, 320, 320, 3, "per", True, False, F32_T, 0, 32, 1),
     ("splitk_geglu", 1, 1, 256, 1280, 10240, 1, None, False, True, BF16_T, 0, 256, 4),
+    # weight-stationary persistent walk (short K, several waves of tiles): GEGLU-in and q|k|v at level 0, a 1x1 conv at UNet batch 16
+    ("ws_geglu_L0", 1, 1, 8192, 320, 2560, 1, None, False, True, BF16_T, 0, 0, 0),
+    ("ws_qkv_L0", 1, 1, 8192, 320, 960, 1, None, False, False, BF16_T, 0, 0, 0),
+    ("ws_1x1_res_b16", 16, 64, 64, 320, 320, 1, "per", True, False, F32_T, 0, 0, 0),
+    ("ws_lin_L1_bn64", 1, 1, 16384, 640, 1920, 1, None, False, False, BF16_T, 0, 64, 1),
 ]
 
 
@@ -154,8 +159,8 @@ def test_tc_gemm(dev, case, wk):
     d.out_dtype, d.geglu, d.out_nchw, d.block_n, d.splits = odt, int(geglu), nchw, bn, splits
     h = C.c_void_p()
     _lib.check(lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
-    info = (C.c_int * 8)()
-    _lib.check(lib.sdk_tc_gemm_info(h, info, 8))
+    info = (C.c_int * 11)()
+    _lib.check(lib.sdk_tc_gemm_info(h, info, 11))
     ws = torch.zeros(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=dev)
     _lib.check(lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr()))
     for _ in range(2):                                    # twice: split-K tickets must self-reset
@@ -167,9 +172,12 @@ def test_tc_gemm(dev, case, wk):
     if nchw:
         want = want.permute(0, 3, 1, 2)
     e = rel_l2(out.float(), want)
-    print(f"{name}: block_n={info[0]} splits={info[1]} grid=({info[2]},{info[3]}) tile=({info[4]},{info[5]},{info[6]}) kb={info[7]} rel-L2={e:.2e}")
+    print(f"{name}: block_n={info[0]} splits={info[1]} grid=({info[2]},{info[3]}) tile=({info[4]},{info[5]},{info[6]}) kb={info[7]} "
+          f"kernel={('plain', 'persistent', 'persistent weight-stationary')[info[10]]} rel-L2={e:.2e}")
     assert not torch.isnan(out.float()).any()
     assert e < (4e-3 if odt == BF16_T else 2e-5)
+    if name.startswith("ws_"):
+        assert info[10] == 2, "expected the weight-stationary persistent form"
 
 
 TWO_CTA_CASES = [
