@@ -799,9 +799,12 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
 // -------------------------------------------------------------------------------------------------
 // FOLD: the conv gathers folded into the TMA coordinates (stride-2 conv, nearest-2x upsample as four parity convs; see TcParams).
 // A template parameter, not a run-time flag: the extra index arithmetic measurably slows the ordinary layers (0.14 ms per step).
-template <int BN, bool FOLD>
+// MODE 0: plain; 1: FOLD (conv gathers); 2: WS (weight-stationary walk, see below).  Compile-time for the same reason as FOLD.
+template <int BN, int MODE>
 __global__ void __launch_bounds__(PERS_THREADS, 1)
 conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
+    constexpr bool FOLD = MODE == 1;
+    constexpr bool b_res = MODE == 2;
     constexpr int B_STAGE_BYTES = BN * BK * 2;
     constexpr int NCH = BN / 32;
     constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
@@ -815,7 +818,6 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
     // weight tile are loaded once into sB (slot = k-block) and stay there, so a k-block costs the SM 16 KiB of L2->smem traffic (the
     // A tile) instead of 16 KiB + BN*128 B.  Short-K linears (q/k/v, attention out, GEGLU-in at K = 320 / 640) are bound by exactly
     // that feed (~46 B/clk per SM) once their grid has more than one wave.
-    const bool b_res = !FOLD && p.b_resident != 0;
     const int b_slots = b_res ? p.total_kb : STAGES;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
@@ -1365,11 +1367,14 @@ int stage_smem(int bn, bool two) { return A_STAGE_BYTES + (two ? bn / 2 : bn) * 
 template <int BN>
 int launch_persistent(const TcGemm* g, cudaStream_t s) {
     if (g->prm.up2 || g->prm.a_stride != 1) {
-        SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN, true>), g->smem_bytes));
-        SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN, true>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
+        SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN, 1>), g->smem_bytes));
+        SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN, 1>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
+    } else if (g->prm.b_resident) {
+        SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN, 2>), g->smem_bytes));
+        SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN, 2>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
     } else {
-        SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN, false>), g->smem_bytes));
-        SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN, false>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
+        SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN, 0>), g->smem_bytes));
+        SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN, 0>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
     }
     SDK_LAUNCH_CHECK();
     return SDK_OK;
