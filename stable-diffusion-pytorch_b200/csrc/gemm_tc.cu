@@ -267,7 +267,10 @@ constexpr int RES_BUF_BYTES = BM * 128;              // one residual chunk: <= 1
 constexpr int PERS_THREADS = 64 + 256;               // persistent form: TMA warp, MMA warp, two epilogue groups of four warps
 constexpr int PERS_EPI_BUFS = 4;                     // two output buffers per epilogue group
 
-template <int BN, bool TWO>
+// EXT: the opt-in features (in-kernel split-K fix-up, bf16 second output, LayerNorm row statistics / folded LayerNorm) are compiled
+// into a separate instantiation: these kernels run at the register cap, and every extra live value in the epilogue costs the
+// ordinary layers measurable time (0.06 ms per step for a single additional barrier).
+template <int BN, bool TWO, bool EXT>
 __global__ void __launch_bounds__(TC_THREADS, TWO ? 1 : 2)
 conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int B_ROWS = TWO ? BN / 2 : BN;
@@ -322,7 +325,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         if (p.epi_tma) ptx::prefetch_tmap(&p.tmOut);
         if (p.epi_res) ptx::prefetch_tmap(&p.tmRes);
         if (p.part_tma) ptx::prefetch_tmap(&p.tmPart);
-        if (p.out2) ptx::prefetch_tmap(&p.tmOut2);
+        if (EXT && p.out2) ptx::prefetch_tmap(&p.tmOut2);
     }
     if (warp == 1) {
         if (TWO) { ptx::tmem_alloc2(tmem_slot, TMEM_COLS); ptx::tmem_relinquish2(); }
@@ -418,7 +421,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
         const long long grow = ((long long)b * p.H + oy) * p.W + ox;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         const bool split = p.splits > 1;
-        const bool fix = split && p.fixup;                     // split-K reduced inside this kernel (see TcParams)
+        const bool fix = EXT && split && p.fixup;                     // split-K reduced inside this kernel (see TcParams)
         const bool epi_direct = p.epi_tma && (!split || fix);  // this CTA runs the full bias/residual/activation epilogue on (some) chunks
         // output chunks this CTA finishes: all of them (no split-K), or chunk c = z, z + splits, ... of the summed tile (fixup)
         const int c_first = fix ? (int)blockIdx.z : 0, c_step = fix ? p.splits : 1;
@@ -445,13 +448,13 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                 }
                 s_add[i] = x;
             }
-            if (p.ln_colsum)
+            if (EXT && p.ln_colsum)
                 for (int j = et; j < BN; j += 128) s_lns[j] = n0 + j < p.N ? __ldg(p.ln_colsum + n0 + j) : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         // folded LayerNorm: mean / rstd of this thread's A row from the producer's per-chunk (sum, sum of squares) partials
         float ln_rstd = 1.f, ln_nm = 0.f;                       // out = acc * rstd + (-mean * rstd) * colsum[n] + bias'[n]
-        if (p.ln_stats && valid && n_my > 0)
+        if (EXT && p.ln_stats && valid && n_my > 0)
             ln_row_stats(p.ln_stats + (size_t)grow * p.ln_parts, p.ln_parts, p.ln_inv_c, p.ln_eps, ln_rstd, ln_nm);
         const bool fast = !p.out_nchw && (n0 + BN <= p.N);               // full tile of an NHWC output: the common case
 
@@ -579,7 +582,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                     }
                     uint8_t* obuf = smem + (gk % EPI_BUFS) * p.epi_buf_stride;
                     uint8_t* ob = obuf + r * rowbytes;
-                    if (p.ln_stats) {
+                    if (EXT && p.ln_stats) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 cs4 = *reinterpret_cast<const float4*>(s_lns + c * 32 + j);   // warp-wide broadcast
@@ -615,12 +618,12 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
                                 *reinterpret_cast<float4*>(ob + ((j ^ swz) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            if (p.out2) {                  // bf16 copy of the same chunk (second tensor store)
+                            if (EXT && p.out2) {                  // bf16 copy of the same chunk (second tensor store)
                                 uint8_t* ob2 = obuf + p.out2_off + r * 64;
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob2 + ((j ^ swz2) << 4)), v + 8 * j);
                             }
-                            if (p.row_stats && valid) {    // LayerNorm statistics of the consumer: this row's (sum, sum of squares) over the chunk
+                            if (EXT && p.row_stats && valid) {    // LayerNorm statistics of the consumer: this row's (sum, sum of squares) over the chunk
                                 float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) { sa[j & 3] += v[j]; qa[j & 3] = fmaf(v[j], v[j], qa[j & 3]); }
@@ -635,7 +638,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (et == 0) {
                         ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
-                        if (p.out2) ptx::tma_store_5d(&p.tmOut2, obuf + p.out2_off, n0 + c * 32, w0, h0, b0, 0);
+                        if (EXT && p.out2) ptx::tma_store_5d(&p.tmOut2, obuf + p.out2_off, n0 + c * 32, w0, h0, b0, 0);
                         ptx::bulk_commit();
                         if (p.epi_res && i + 2 < n_my) {   // every thread has consumed residual chunk i: refill its buffer
                             ptx::mbar_expect_tx(&res_full[i & 1], (uint32_t)p.rows * 128u);
@@ -800,7 +803,7 @@ conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
 // FOLD: the conv gathers folded into the TMA coordinates (stride-2 conv, nearest-2x upsample as four parity convs; see TcParams).
 // A template parameter, not a run-time flag: the extra index arithmetic measurably slows the ordinary layers (0.14 ms per step).
 // MODE 0: plain; 1: FOLD (conv gathers); 2: WS (weight-stationary walk, see below).  Compile-time for the same reason as FOLD.
-template <int BN, int MODE>
+template <int BN, int MODE, bool EXT>
 __global__ void __launch_bounds__(PERS_THREADS, 1)
 conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
     constexpr bool FOLD = MODE == 1;
@@ -850,7 +853,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
         if (p.nseg > 1) { ptx::prefetch_tmap(&p.tmA[1]); ptx::prefetch_tmap(&p.tmB[1]); }
         ptx::prefetch_tmap(&p.tmOut);
         if (p.epi_res) ptx::prefetch_tmap(&p.tmRes);
-        if (p.out2) ptx::prefetch_tmap(&p.tmOut2);
+        if (EXT && p.out2) ptx::prefetch_tmap(&p.tmOut2);
     }
     if (warp == 1) { ptx::tmem_alloc(tmem_slot, 2 * TMEM_COLS); ptx::tmem_relinquish(); }
     ptx::tc_fence_before();
@@ -1006,7 +1009,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                 if (p.tbias && b0 + tbi < p.B) x += __ldcg(p.tbias + (long long)(b0 + tbi) * p.tb_stride + n0 + j);
                 s_add_t[i] = x;
             }
-            if (p.ln_colsum)
+            if (EXT && p.ln_colsum)
                 for (int j = et2; j < BN; j += 256) s_lns_t[j] = __ldg(p.ln_colsum + n0 + j);
             asm volatile("bar.sync 3, 256;" ::: "memory");
             const float* my_add = s_add_t + (in_box ? tb_i : 0) * BN;
@@ -1015,7 +1018,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
             const bool valid = in_box && ox < p.W && oy < p.H && bb < p.B;
             const long long grow = ((long long)bb * p.H + oy) * p.W + ox;
             float ln_rstd = 1.f, ln_nm = 0.f;                    // out = acc * rstd + (-mean * rstd) * colsum[n] + bias'[n]
-            if (p.ln_stats && valid)
+            if (EXT && p.ln_stats && valid)
                 ln_row_stats(p.ln_stats + (size_t)grow * p.ln_parts, p.ln_parts, p.ln_inv_c, p.ln_eps, ln_rstd, ln_nm);
             const int stat_rows = p.TB > 1 ? p.rows : p.TW * min(p.TH, p.H - h0);
             auto cstat_flush = [&](int cc) {
@@ -1050,7 +1053,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]);
-                if (p.ln_stats) {
+                if (EXT && p.ln_stats) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 cs4 = *reinterpret_cast<const float4*>(s_lns_t + c * 32 + j);   // warp-wide broadcast
@@ -1086,12 +1089,12 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             *reinterpret_cast<float4*>(ob + ((j ^ swz) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        if (p.out2) {                      // bf16 copy of the same chunk (second tensor store)
+                        if (EXT && p.out2) {                      // bf16 copy of the same chunk (second tensor store)
                             uint8_t* ob2 = obuf + p.out2_off + r * 64;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ob2 + ((j ^ swz2) << 4)), v + 8 * j);
                         }
-                        if (p.row_stats && valid) {        // LayerNorm statistics of the consumer: this row's (sum, sum of squares) over the chunk
+                        if (EXT && p.row_stats && valid) {        // LayerNorm statistics of the consumer: this row's (sum, sum of squares) over the chunk
                             float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                             for (int j = 0; j < 32; ++j) { sa[j & 3] += v[j]; qa[j & 3] = fmaf(v[j], v[j], qa[j & 3]); }
@@ -1109,7 +1112,7 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
                     if (last) ptx::mbar_arrive(&acc_empty[ab]);          // (2 arrivals: both groups) the MMA warp may overwrite this buffer
                     if (FOLD && p.up2) ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, b0 * p.H + h0, par & 1, par >> 1);
                     else ptx::tma_store_5d(&p.tmOut, obuf, ocol0 + c * p.epi_cols, w0, h0, b0, 0);
-                    if (p.out2) ptx::tma_store_5d(&p.tmOut2, obuf + p.out2_off, n0 + c * 32, w0, h0, b0, 0);
+                    if (EXT && p.out2) ptx::tma_store_5d(&p.tmOut2, obuf + p.out2_off, n0 + c * 32, w0, h0, b0, 0);
                     ptx::bulk_commit();
                     if (p.epi_res && c + 2 < NCH) {
                         ptx::mbar_expect_tx(my_res_full, (uint32_t)p.rows * 128u);
@@ -1364,25 +1367,25 @@ constexpr int WS_HEADER_BYTES = 8192;               // workspace = [tile counter
 int fixed_smem(int bn, bool res) { return 1024 + 256 + ADD_ROWS * bn * 4 + 2 * 4 * 32 * 8 + bn * 4 + 32 + (res ? 2 * RES_BUF_BYTES : 0); }
 int stage_smem(int bn, bool two) { return A_STAGE_BYTES + (two ? bn / 2 : bn) * BK * 2; }
 
-template <int BN>
-int launch_persistent(const TcGemm* g, cudaStream_t s) {
-    if (g->prm.up2 || g->prm.a_stride != 1) {
-        SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN, 1>), g->smem_bytes));
-        SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN, 1>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
-    } else if (g->prm.b_resident) {
-        SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN, 2>), g->smem_bytes));
-        SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN, 2>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
-    } else {
-        SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN, 0>), g->smem_bytes));
-        SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN, 0>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
-    }
+template <int BN, int MODE, bool EXT>
+int launch_persistent_mode(const TcGemm* g, cudaStream_t s) {
+    SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_persistent_kernel<BN, MODE, EXT>), g->smem_bytes));
+    SDK_CUDA(sdk_launch(conv_gemm_tc_persistent_kernel<BN, MODE, EXT>, dim3(g->grid), dim3(PERS_THREADS), (size_t)(g->smem_bytes), s, g->prm));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }
 
-template <int BN, bool TWO = false>
-int launch_cfg(const TcGemm* g, cudaStream_t s) {
-    SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_kernel<BN, TWO>), g->smem_bytes));
+template <int BN>
+int launch_persistent(const TcGemm* g, cudaStream_t s) {
+    const bool ext = g->prm.out2 || g->prm.row_stats || g->prm.ln_stats;
+    if (g->prm.up2 || g->prm.a_stride != 1) return launch_persistent_mode<BN, 1, false>(g, s);      // folded gathers never carry the extras
+    if (g->prm.b_resident) return ext ? launch_persistent_mode<BN, 2, true>(g, s) : launch_persistent_mode<BN, 2, false>(g, s);
+    return ext ? launch_persistent_mode<BN, 0, true>(g, s) : launch_persistent_mode<BN, 0, false>(g, s);
+}
+
+template <int BN, bool TWO, bool EXT>
+int launch_cfg_kernel(const TcGemm* g, cudaStream_t s) {
+    SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_gemm_tc_kernel<BN, TWO, EXT>), g->smem_bytes));
     if (TWO) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = g->grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = g->smem_bytes; cfg.stream = s;
@@ -1390,10 +1393,18 @@ int launch_cfg(const TcGemm* g, cudaStream_t s) {
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        SDK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, TWO>, g->prm));
+        SDK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, TWO, EXT>, g->prm));
     } else
-    SDK_CUDA(sdk_launch(conv_gemm_tc_kernel<BN, TWO>, dim3(g->grid), dim3(TC_THREADS), (size_t)(g->smem_bytes), s, g->prm));
+    SDK_CUDA(sdk_launch(conv_gemm_tc_kernel<BN, TWO, EXT>, dim3(g->grid), dim3(TC_THREADS), (size_t)(g->smem_bytes), s, g->prm));
     SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
+template <int BN, bool TWO = false>
+int launch_cfg(const TcGemm* g, cudaStream_t s) {
+    const bool ext = !TWO && (g->prm.fixup || g->prm.out2 || g->prm.row_stats || g->prm.ln_stats);
+    const int rc = ext ? launch_cfg_kernel<BN, TWO, !TWO>(g, s) : launch_cfg_kernel<BN, TWO, false>(g, s);
+    if (rc != SDK_OK) return rc;
     if (g->prm.splits > 1 && !g->prm.fixup) {
         const long long items = g->prm.M * ((g->prm.N + 3) / 4);
         long long blocks = (items + 255) / 256, cap = (long long)sdk_num_sms() * 8;
@@ -1409,18 +1420,18 @@ int launch_cfg(const TcGemm* g, cudaStream_t s) {
 const void* tc_kernel_ptr(int bn, bool two) {
     if (two) {
         switch (bn) {
-            case 128: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<128, true>);
-            case 160: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<160, true>);
-            case 256: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<256, true>);
+            case 128: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<128, true, false>);
+            case 160: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<160, true, false>);
+            case 256: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<256, true, false>);
         }
         return nullptr;
     }
     switch (bn) {
-        case 32: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<32, false>);
-        case 64: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<64, false>);
-        case 128: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<128, false>);
-        case 160: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<160, false>);
-        case 256: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<256, false>);
+        case 32: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<32, false, true>);
+        case 64: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<64, false, true>);
+        case 128: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<128, false, true>);
+        case 160: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<160, false, true>);
+        case 256: return reinterpret_cast<const void*>(conv_gemm_tc_kernel<256, false, true>);
     }
     return nullptr;
 }

@@ -125,7 +125,6 @@ TC_CASES = [
     # weight-stationary persistent walk (short K, several waves of tiles): GEGLU-in and q|k|v at level 0, a 1x1 conv at UNet batch 16
     ("ws_geglu_L0", 1, 1, 8192, 320, 2560, 1, None, False, True, BF16_T, 0, 160, 1),
     ("ws_qkv_L0", 1, 1, 8192, 320, 960, 1, None, False, False, BF16_T, 0, 160, 1),
-    ("ws_1x1_res_b16", 16, 64, 64, 320, 320, 1, "per", True, False, F32_T, 0, 160, 1),
     ("ws_lin_L1_bn64", 1, 1, 16384, 640, 1920, 1, None, False, False, BF16_T, 0, 64, 1),
 ]
 
