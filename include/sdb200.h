@@ -219,6 +219,9 @@ typedef struct SdkTcGemmDesc {
                                  read the same input pixel pre-summed by the host) */
     int w_const;              /* 1: `w` is never written by a kernel of the same stream (packed weights): with programmatic dependent launch
                                  the first weight tiles are fetched BEFORE the wait on the preceding kernel.  0 when `w` is an activation. */
+    int weight_stationary;    /* persistent kernel, short K: each CTA keeps the weight tile of ONE n-tile resident in shared memory and walks
+                                 m-tiles (a k-block then costs 16 KiB of L2->smem traffic instead of 16 KiB + block_n*128 B).
+                                 0 = library default (SDB200_TC_WS, off), 1 = never, 2 = whenever it fits */
 } SdkTcGemmDesc;
 int sdk_tc_gemm_create(const SdkTcGemmDesc* desc, void** handle);
 int64_t sdk_tc_gemm_workspace_bytes(void* handle);

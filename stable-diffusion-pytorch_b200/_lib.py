@@ -96,7 +96,7 @@ class TcGemmDesc(C.Structure):
                 ("bias", P), ("tbias", P), ("tb_stride", I64), ("residual", P), ("out", P),
                 ("out_dtype", I32), ("geglu", I32), ("out_nchw", I32), ("block_n", I32), ("splits", I32), ("w_kmajor", I32), ("two_cta", I32),
                 ("out2", P), ("row_stats", P), ("ln_stats", P), ("ln_colsum", P), ("ln_parts", I32), ("ln_eps", F32),
-                ("a_stride", I32), ("a_h", I32), ("a_w", I32), ("up2", I32), ("w_const", I32)]
+                ("a_stride", I32), ("a_h", I32), ("a_w", I32), ("up2", I32), ("w_const", I32), ("weight_stationary", I32)]
 
 
 F32_T, BF16_T = 0, 1

@@ -156,6 +156,7 @@ def test_tc_gemm(dev, case, wk):
     d.tbias, d.tb_stride = (tb.data_ptr() if tb is not None else 0), (N if tbm == "per" else 0)
     d.residual, d.out = (resid.data_ptr() if res else 0), out.data_ptr()
     d.out_dtype, d.geglu, d.out_nchw, d.block_n, d.splits = odt, int(geglu), nchw, bn, splits
+    d.weight_stationary = 2 if name.startswith("ws_") else 0
     h = C.c_void_p()
     _lib.check(lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
     info = (C.c_int * 11)()
