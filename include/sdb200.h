@@ -238,6 +238,30 @@ int sdk_tc_gemm_set_debug(void* handle, void* stamps);
 /* stride-2 3x3 conv (unet.py:236): gather fp32 NHWC -> bf16 [B*Ho*Wo][9*C] rows, then a 1-tap sdk_tc_gemm */
 int sdk_im2col_s2(const float* src, void* dst, int B, int H, int W, int C, void* stream);
 
+/* ---- Linear (+ bias + residual) fused with the LayerNorm of its output rows (unet.py:86,137-149; attention.py:25,50) --------
+ * out[m][:] = a[m][:] W^T + bias + residual[m][:]   (fp32, the transformer block's residual stream)
+ * ln_out[m][:] = LayerNorm(out[m][:]) * gamma + beta (bf16, the A operand of the next projection)
+ * in ONE launch: the N/160 (or N/128) n-tiles of a 128-row block form a thread-block cluster (<= 8 CTAs) that exchanges the
+ * per-row statistics (exact two-pass mean / variance) through distributed shared memory; the finished fp32 values stay in TMEM
+ * between the passes.  a: bf16 [M][K], K % 64 == 0; w: bf16 k-block-major [K/64][N][64] (as SdkTcGemmDesc.w_kmajor).
+ * SDK_ERR_UNSUPPORTED when N is not 160*k or 128*k with k <= 8: use sdk_tc_gemm + sdk_layernorm. */
+typedef struct SdkLinearLnDesc {
+    const void* a;
+    const void* w;
+    const float* bias;        /* [N] or NULL */
+    const float* residual;    /* fp32 [M][N] or NULL */
+    float* out;               /* fp32 [M][N] */
+    void* ln_out;             /* bf16 [M][N] */
+    const float* gamma; const float* beta;   /* [N] */
+    float eps;
+    int64_t M;
+    int K, N;
+} SdkLinearLnDesc;
+int sdk_linear_ln_create(const SdkLinearLnDesc* desc, void** handle);
+int sdk_linear_ln_info(void* handle, int* out, int n);          /* block_n, cluster size, grid, dynamic shared memory bytes */
+int sdk_linear_ln_launch(void* handle, void* stream);
+int sdk_linear_ln_destroy(void* handle);
+
 #ifdef __cplusplus
 }
 #endif

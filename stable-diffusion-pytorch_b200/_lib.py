@@ -73,6 +73,11 @@ SIGNATURES = {
     "sdk_tc_gemm_set_stats": [P, P],
     "sdk_zero": [P, I64, P],
     "sdk_im2col_s2": [P, P, I32, I32, I32, I32, P],
+    # --- linear_ln.cu
+    "sdk_linear_ln_create": [P, P],
+    "sdk_linear_ln_info": [P, P, I32],
+    "sdk_linear_ln_launch": [P, P],
+    "sdk_linear_ln_destroy": [P],
     # --- misc
     "sdk_device_info": [P, I32],
     "sdk_set_pdl": [I32],
@@ -97,6 +102,12 @@ class TcGemmDesc(C.Structure):
                 ("out_dtype", I32), ("geglu", I32), ("out_nchw", I32), ("block_n", I32), ("splits", I32), ("w_kmajor", I32), ("two_cta", I32),
                 ("out2", P), ("row_stats", P), ("ln_stats", P), ("ln_colsum", P), ("ln_parts", I32), ("ln_eps", F32),
                 ("a_stride", I32), ("a_h", I32), ("a_w", I32), ("up2", I32), ("w_const", I32), ("weight_stationary", I32)]
+
+
+class LinearLnDesc(C.Structure):
+    """Mirror of SdkLinearLnDesc (include/sdb200.h)."""
+    _fields_ = [("a", P), ("w", P), ("bias", P), ("residual", P), ("out", P), ("ln_out", P), ("gamma", P), ("beta", P),
+                ("eps", F32), ("M", I64), ("K", I32), ("N", I32)]
 
 
 F32_T, BF16_T = 0, 1

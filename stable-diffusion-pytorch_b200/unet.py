@@ -25,7 +25,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._lib import BF16_T, F32_T, ConvParams, TcGemmDesc
+from ._lib import BF16_T, F32_T, ConvParams, LinearLnDesc, TcGemmDesc
 from .arch import BLOCK_OUT, Conv, ResBlock, Transformer, UNetArch, build_arch, param_spec
 
 _DT = {F32_T: torch.float32, BF16_T: torch.bfloat16}
@@ -58,6 +58,10 @@ def read_knobs(m):
     # bf16: LayerNorm folded into the consuming GEMM (built and parity-tested; measured on B200 it costs the GEMMs 0.23 ms per step and
     # saves 0.20 ms of layernorm launches at UNet batch 2, and loses 0.9 ms of 20.3 at batch 16 -> opt-in)
     m.ln_fold = os.environ.get("SDB200_LN_FOLD", "0") != "0"
+    # bf16: projection (+ bias + residual) and the LayerNorm of its output rows in ONE cluster launch (linear_ln.cu) for layers
+    # whose grid fits one wave of the chip -- the latency-bound case (every transformer layer at UNet batch 2)
+    m.ln_fuse = os.environ.get("SDB200_LN_FUSE", "1") != "0"
+    m.ln_fuse_max_ctas = int(os.environ.get("SDB200_LN_FUSE_MAX_CTAS", "148"))
     m.fold_gathers = os.environ.get("SDB200_FOLD_GATHERS", "1") != "0"   # bf16: stride-2 / upsample gathers inside the GEMM's TMA coordinates
     # ... where the layer has enough rows to fill the chip WITHOUT split-K (the folded form runs on the persistent kernel only; measured
     # on B200 at UNet batch 2: the 8x8 / 16x16 layers are weight-streaming bound and 1.6-3x faster as im2col / upsample + split-K GEMM)
@@ -270,6 +274,7 @@ class StepProgram:
         self.n_launch = 0
         self.tc_handles = []
         self.attn_handles = []
+        self.lln_handles = []
         # GroupNorm statistics from per-channel sums accumulated by the producing GEMM (bf16 program) instead of a statistics
         # kernel.  All tables live in one arena that the program zeroes with its first op.
         self.gn_from_sums = pw.precision != "fp32" and net.gn_mode == "sums"
@@ -600,6 +605,34 @@ class StepProgram:
         self._emit(self.lib.sdk_layernorm, x.data_ptr(), g.data_ptr(), b.data_ptr(), float(eps), out.data_ptr(), code, rows, Cc)
         return out
 
+    def _linear_ln(self, a, w, bias, residual, g, b, rows, K, N, eps=1e-5):
+        """out = a W^T + bias + residual (fp32) and LayerNorm(out) (bf16) in one launch (sdk_linear_ln), or None when the shape is
+        not taken (row width not 160k / 128k with k <= 8, or a grid of more than one wave: the persistent GEMM + LayerNorm pair
+        overlaps epilogues across tiles there)."""
+        if self.act == F32_T or not getattr(self.net, "ln_fuse", False):
+            return None
+        bn = 160 if (N % 160 == 0 and N // 160 <= 8) else (128 if (N % 128 == 0 and N // 128 <= 8) else 0)
+        if not bn or K % 64 != 0 or ((rows + 127) // 128) * (N // bn) > self.net.ln_fuse_max_ctas:
+            return None
+        out = self.pool.get(rows, N, F32_T)
+        ln = self.pool.get(rows, N, BF16_T)
+        d = LinearLnDesc()
+        d.a, d.w, d.bias = a.data_ptr(), w.data_ptr(), (bias.data_ptr() if bias is not None else 0)
+        d.residual = residual.data_ptr() if residual is not None else 0
+        d.out, d.ln_out, d.gamma, d.beta, d.eps = out.data_ptr(), ln.data_ptr(), g.data_ptr(), b.data_ptr(), float(eps)
+        d.M, d.K, d.N = rows, K, N
+        h = C.c_void_p()
+        rc = self.lib.sdk_linear_ln_create(C.byref(d), C.byref(h))
+        if rc == -3:
+            self.pool.put(out)
+            self.pool.put(ln)
+            return None
+        _lib.check(rc)
+        self.lln_handles.append(h)
+        self.keep.append(d)
+        self._emit(self.lib.sdk_linear_ln_launch, h)
+        return out, ln
+
     def _attention(self, q, q_row, q_batch, k, k_row, k_batch, v, v_row, v_batch, B, heads, Sq, Sk, D, Cc, causal=False):
         out = self.pool.get(B * Sq, Cc, self.act)
         if self.act != F32_T and D in (40, 64, 80, 160) and self.net.attn_tc:
@@ -672,10 +705,17 @@ class StepProgram:
                     self.pool.put(getattr(tn, extra))
             self.pool.put(tn)
 
-        h, _, _ = self._conv([(a, Cc)], t[f"{p}.in.w"], t[f"{p}.in.b"], 1, 1, M, Cc, ln_out=fold)
+        fused = None if fold else self._linear_ln(a, t[f"{p}.in.w"], t[f"{p}.in.b"], None, t[f"{p}.ln1.g"], t[f"{p}.ln1.b"], M, Cc, Cc)
+        if fused is not None:
+            h, n1 = fused
+        else:
+            h, _, _ = self._conv([(a, Cc)], t[f"{p}.in.w"], t[f"{p}.in.b"], 1, 1, M, Cc, ln_out=fold)
         self.pool.put(a)
         # self-attention
-        if fold:
+        if fused is not None:
+            qkv, _, _ = self._conv([(n1, Cc)], t[f"{p}.qkv.w"], None, 1, 1, M, 3 * Cc, out_code=self.act)
+            self.pool.put(n1)
+        elif fold:
             qkv, _, _ = self._conv([(h._bf16, Cc)], t[f"{p}.qkv.lnw"], t[f"{p}.qkv.lnb"], 1, 1, M, 3 * Cc, out_code=self.act,
                                    ln_in=(h._rowstats, t[f"{p}.qkv.lncs"]))
         else:
@@ -686,11 +726,18 @@ class StepProgram:
         ao = self._attention(base, 3 * Cc, S * 3 * Cc, base + Cc * es, 3 * Cc, S * 3 * Cc, base + 2 * Cc * es, 3 * Cc, S * 3 * Cc,
                              B, tr.heads, S, S, D, Cc)
         self.pool.put(qkv)
-        h2, _, _ = self._conv([(ao, Cc)], t[f"{p}.o1.w"], t[f"{p}.o1.b"], 1, 1, M, Cc, residual=h, ln_out=fold)
+        fused = None if fold else self._linear_ln(ao, t[f"{p}.o1.w"], t[f"{p}.o1.b"], h, t[f"{p}.ln2.g"], t[f"{p}.ln2.b"], M, Cc, Cc)
+        if fused is not None:
+            h2, n2 = fused
+        else:
+            h2, _, _ = self._conv([(ao, Cc)], t[f"{p}.o1.w"], t[f"{p}.o1.b"], 1, 1, M, Cc, residual=h, ln_out=fold)
         self.pool.put(ao)
         drop(h)
         # cross-attention: K/V of the context are loop-invariant -> context program
-        if fold:
+        if fused is not None:
+            q2, _, _ = self._conv([(n2, Cc)], t[f"{p}.q2.w"], None, 1, 1, M, Cc, out_code=self.act)
+            self.pool.put(n2)
+        elif fold:
             q2, _, _ = self._conv([(h2._bf16, Cc)], t[f"{p}.q2.lnw"], t[f"{p}.q2.lnb"], 1, 1, M, Cc, out_code=self.act,
                                   ln_in=(h2._rowstats, t[f"{p}.q2.lncs"]))
         else:
@@ -711,11 +758,18 @@ class StepProgram:
         ao2 = self._attention(q2.data_ptr(), Cc, S * Cc, kvb, kv_row, kv_batch, kvb + Cc * es, kv_row, kv_batch,
                               B, tr.heads, S, self.Sk, D, Cc)
         self.pool.put(q2)
-        h3, _, _ = self._conv([(ao2, Cc)], t[f"{p}.o2.w"], t[f"{p}.o2.b"], 1, 1, M, Cc, residual=h2, ln_out=fold)
+        fused = None if fold else self._linear_ln(ao2, t[f"{p}.o2.w"], t[f"{p}.o2.b"], h2, t[f"{p}.ln3.g"], t[f"{p}.ln3.b"], M, Cc, Cc)
+        if fused is not None:
+            h3, n3 = fused
+        else:
+            h3, _, _ = self._conv([(ao2, Cc)], t[f"{p}.o2.w"], t[f"{p}.o2.b"], 1, 1, M, Cc, residual=h2, ln_out=fold)
         self.pool.put(ao2)
         drop(h2)
         # GEGLU feed-forward (activation_fn.py:17-20), GEGLU fused into the first GEMM's epilogue
-        if fold:
+        if fused is not None:
+            g, _, _ = self._conv([(n3, Cc)], t[f"{p}.ff0.w"], t[f"{p}.ff0.b"], 1, 1, M, 8 * Cc, geglu=True, out_code=self.act)
+            self.pool.put(n3)
+        elif fold:
             g, _, _ = self._conv([(h3._bf16, Cc)], t[f"{p}.ff0.lnw"], t[f"{p}.ff0.lnb"], 1, 1, M, 8 * Cc, geglu=True, out_code=self.act,
                                  ln_in=(h3._rowstats, t[f"{p}.ff0.lncs"]))
         else:
@@ -916,6 +970,8 @@ class StepProgram:
                 self.lib.sdk_tc_gemm_destroy(h)
             for h in getattr(self, "attn_handles", []):
                 self.lib.sdk_attention_tc_destroy(h)
+            for h in getattr(self, "lln_handles", []):
+                self.lib.sdk_linear_ln_destroy(h)
         except Exception:
             pass
 

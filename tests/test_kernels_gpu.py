@@ -652,6 +652,76 @@ def test_tc_gemm_layernorm_fold(dev, case):
     assert e < 8e-3                                        # two different bf16 roundings (before / after the normalisation)
 
 
+# (name, M, K, N, residual, bias): the three projection -> LayerNorm pairs of a transformer block (unet.py:86,137-149) at the token
+# counts of UNet batch 2 (64x64 ... 8x8), a ragged row count, and the 128-wide tile (OpenCLIP width 1024)
+LINEAR_LN_CASES = [
+    ("L0_o1", 8192, 320, 320, True, True),
+    ("L0_in", 8192, 320, 320, False, True),
+    ("L1_o2", 2048, 640, 640, True, True),
+    ("L2_o1", 512, 1280, 1280, True, True),
+    ("mid", 128, 1280, 1280, True, False),
+    ("ragged", 200, 640, 640, True, True),
+    ("bn128", 308, 1024, 1024, True, True),
+]
+
+
+@pytest.mark.parametrize("case", LINEAR_LN_CASES, ids=[c[0] for c in LINEAR_LN_CASES])
+def test_linear_layernorm_fused(dev, case):
+    """sdk_linear_ln (projection + bias + residual + LayerNorm in one cluster launch) against fp32 torch on the same bf16 operands:
+    the fp32 output to accumulation-order accuracy, the normalised bf16 output to bf16 rounding."""
+    name, M, K, N, has_res, has_bias = case
+    lib = _lib.lib()
+    a = gen((M, K), 71, dev).to(torch.bfloat16)
+    w = (gen((N, K), 72, dev) / math.sqrt(K)).to(torch.bfloat16)
+    bias = gen((N,), 73, dev) * 0.1 if has_bias else None
+    res = (gen((M, N), 74, dev) * 2 + 0.5) if has_res else None
+    gamma, beta = gen((N,), 75, dev) * 0.1 + 1, gen((N,), 76, dev) * 0.1
+    out = torch.full((M, N), float("nan"), device=dev)
+    ln = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+    wk = kmajor(w)
+    d = _lib.LinearLnDesc()
+    d.a, d.w, d.bias, d.residual = a.data_ptr(), wk.data_ptr(), (bias.data_ptr() if has_bias else 0), (res.data_ptr() if has_res else 0)
+    d.out, d.ln_out, d.gamma, d.beta, d.eps, d.M, d.K, d.N = out.data_ptr(), ln.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-5, M, K, N
+    h = C.c_void_p()
+    _lib.check(lib.sdk_linear_ln_create(C.byref(d), C.byref(h)))
+    info = (C.c_int * 4)()
+    _lib.check(lib.sdk_linear_ln_info(h, info, 4))
+    assert info[0] * info[1] == N and info[2] == (M + 127) // 128 * info[1]
+    for _ in range(2):                                            # relaunchable: no state is left behind
+        _lib.check(lib.sdk_linear_ln_launch(h, stream()))
+    torch.cuda.synchronize()
+    _lib.check(lib.sdk_linear_ln_destroy(h))
+    ref = a.float() @ w.float().t()
+    if has_bias:
+        ref = ref + bias
+    if has_res:
+        ref = ref + res
+    e_out = rel_l2(out, ref)
+    ref_ln = Fn.layer_norm(out, (N,), gamma, beta, 1e-5)          # statistics of the kernel's OWN fp32 rows
+    e_ln = rel_l2(ln.float(), ref_ln)
+    print(f"{name}: out rel-L2 {e_out:.2e}, LayerNorm rel-L2 {e_ln:.2e} (cluster of {info[1]}, {info[2]} CTAs)")
+    assert not torch.isnan(out).any() and not torch.isnan(ln.float()).any()
+    assert e_out < 2e-6
+    assert e_ln < 3e-3                                            # bf16 rounding of the normalised row
+    # the bf16 result must equal the stand-alone LayerNorm kernel's on the same rows up to rare rounding flips
+    ln2 = torch.empty_like(ln)
+    _lib.check(lib.sdk_layernorm(out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-5, ln2.data_ptr(), BF16_T, M, N, stream()))
+    torch.cuda.synchronize()
+    flips = (ln.float() != ln2.float()).float().mean().item()
+    assert flips < 2e-3, flips
+
+
+def test_linear_layernorm_unsupported_width(dev):
+    """Row widths that do not split into <= 8 tiles of 160 / 128 columns are refused (the caller keeps GEMM + LayerNorm)."""
+    lib = _lib.lib()
+    x = torch.zeros((128, 768), device=dev, dtype=torch.bfloat16)
+    o = torch.zeros((128, 768), device=dev)
+    d = _lib.LinearLnDesc()
+    d.a, d.w, d.out, d.ln_out, d.gamma, d.beta, d.eps, d.M, d.K, d.N = x.data_ptr(), x.data_ptr(), o.data_ptr(), x.data_ptr(), o.data_ptr(), o.data_ptr(), 1e-5, 128, 768, 1600
+    h = C.c_void_p()
+    assert lib.sdk_linear_ln_create(C.byref(d), C.byref(h)) == -3
+
+
 @pytest.mark.parametrize("C_", [320, 640, 1280, 768])
 def test_layernorm(dev, C_):
     lib = _lib.lib()
