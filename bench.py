@@ -167,9 +167,7 @@ def run_reference_arm(args, cfg):
 def time_gemm_family(loop, iters=5, fns=None):
     """Average device time of ALL tcgen05 implicit-GEMM launches of one step, replayed back to back as a graph."""
     lib = loop.prog.lib
-    # the GEMM family = every launch that carries conv / linear FLOPs: the implicit-GEMM kernels and the projection + LayerNorm
-    # cluster kernel (sdk_linear_ln), whose matmuls are part of the same 1354 GFLOP
-    names = fns or ["sdk_tc_gemm_launch", "sdk_linear_ln_launch"]
+    names = fns or ["sdk_tc_gemm_launch"]
     targets = [getattr(lib, n) for n in names]
     ops = [(fn, a) for fn, a in loop.prog.ops if any(fn is t for t in targets)]
     if not ops:
@@ -474,9 +472,15 @@ def main():
 
         # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM), rank 0
         gemm_ms, gemm_launches = (None, 0)
+        lln_ms, lln_launches, lln_gflop = (None, 0, 0.0)
         breakdown = None
         if rank == 0 and args.precision == "bf16":
             gemm_ms, gemm_launches = time_gemm_family(loop)
+            # projection + LayerNorm cluster launches (sdk_linear_ln): their matmuls are part of the step's conv / linear FLOPs but
+            # the kernel also does the LayerNorm, so it is timed and reported on its own
+            lln_ms, lln_launches = time_gemm_family(loop, fns=["sdk_linear_ln_launch"])
+            from stable_diffusion_pytorch_b200._lib import LinearLnDesc
+            lln_gflop = sum(2.0 * d.M * d.K * d.N for d in loop.prog.keep if isinstance(d, LinearLnDesc)) / 1e9
             if args.breakdown:
                 breakdown = {}
                 for label, fns in (("tc_gemm", ["sdk_tc_gemm_launch"]), ("linear_ln", ["sdk_linear_ln_launch"]), ("attention", ["sdk_attention_bf16", "sdk_attention_tc_launch"]),
@@ -574,7 +578,9 @@ def main():
     if gemm_ms:
         gemm_gflop = GEMM_GFLOP_B2_SD15_64 * (ub / 2.0) if (cfg["arch"], cfg["hw"]) == ("sd15", 64) else None
         if gemm_gflop:
-            ach = gemm_gflop / gemm_ms            # GFLOP / ms == TFLOP/s
+            # dominant kernel = conv_gemm_tc_kernel: the FLOPs of ITS launches (all conv / linear FLOPs of the step minus the
+            # matmuls that run inside the projection + LayerNorm kernel) over the device time of ITS launches
+            ach = (gemm_gflop - lln_gflop) / gemm_ms            # GFLOP / ms == TFLOP/s
             traffic, traffic_src = None, None
             for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
                 try:
@@ -587,9 +593,16 @@ def main():
                     continue
             roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": traffic,
                     "traffic_note": f"DRAM bytes of all launches of the kernel in one step (ncu, cold L2 per launch): profiles/{traffic_src}",
-                    "kernel": "conv_gemm_tc_kernel + linear_ln_kernel (tcgen05 implicit GEMM family), all launches of one step",
+                    "kernel": "conv_gemm_tc_kernel (tcgen05 implicit GEMM), all launches of one step",
+                    "gflop_per_step_in_kernel": gemm_gflop - lln_gflop,
                     "launches_per_step": gemm_launches, "ms_per_step_in_kernel": gemm_ms, "share_of_step": gemm_ms / ms_step,
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"}
+            if lln_ms:
+                roof["linear_ln"] = {"kernel": "linear_ln_kernel (tcgen05 projection + bias + residual + LayerNorm, one cluster launch)",
+                                     "launches_per_step": lln_launches, "ms_per_step_in_kernel": lln_ms, "gflop_per_step_in_kernel": lln_gflop,
+                                     "achieved": lln_gflop / lln_ms, "share_of_step": lln_ms / ms_step,
+                                     "note": "latency-bound: 48 launches of 1.3-25 GFLOP matmul + the LayerNorm of their rows"}
+                roof["family_frac"] = gemm_gflop / (gemm_ms + lln_ms) / tf_sus
     line = {
         "metric": "images_per_sec", "value": imgs_per_s, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_step, "ms_per_step_min": regions[0], "ms_per_step_max": regions[-1], "repeats": len(regions),

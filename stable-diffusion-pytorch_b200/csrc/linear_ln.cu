@@ -7,14 +7,15 @@
 // A LayerNorm row spans N = C = 320 / 640 / 1280 fp32 columns, more than one CTA's accumulator tile (and, above 512, more than a
 // CTA's TMEM).  So the N/BN n-tiles of one 128-row block form a THREAD-BLOCK CLUSTER (2, 4 or 8 CTAs):
 //   * every CTA runs an ordinary tcgen05 main loop (TMA -> SW128 smem -> tcgen05.mma, fp32 accumulator in TMEM) on its 128 x BN tile;
-//   * epilogue pass 1: TMEM -> registers -> + bias + residual (residual chunks by TMA) -> fp32 `out` (TMA store) -- the finished
-//     values are also written BACK to TMEM (tcgen05.st) and the row's partial sum goes to every peer's shared memory
-//     (st.shared::cluster), one float per row and CTA;
-//   * cluster barrier; mean = (sum of the partials in rank order) / N;
-//   * pass 1b: sum of (v - mean)^2 over the CTA's columns from TMEM, exchanged the same way (exact two-pass statistics, like the
-//     stand-alone layernorm_kernel);
-//   * pass 2: TMEM -> (v - mean) * rstd * gamma + beta -> bf16 -> TMA store to `ln_out`, the A operand of the next GEMM.
-// The thread-per-row TMEM layout makes the row reductions thread-local; nothing but 2 x 128 floats per CTA crosses the cluster.
+//   * statistics pass (two groups of four epilogue warps, alternate 32-column chunks): TMEM -> registers -> + bias + residual (the
+//     residual tile arrives by TMA under the main loop) -> the finished values go BACK to TMEM (tcgen05.st); each thread keeps the
+//     pivot-shifted (sum, sum of squares) of its row, i.e. a (mean, M2) partial over its group's columns, and stores it into every
+//     peer's shared memory (st.shared::cluster);
+//   * ONE cluster barrier; every CTA combines the 2 x cluster-size partials of a row in the same order (Chan's parallel-variance
+//     formula: no cancellation, the statistics equal the two-pass ones to fp32 rounding);
+//   * output pass: TMEM -> fp32 chunk -> `out` and (v - mean) * rstd * gamma + beta -> bf16 chunk -> `ln_out` (the A operand of the
+//     next GEMM), both by TMA tensor stores from a swizzled staging ring.
+// The thread-per-row TMEM layout makes the row reductions thread-local; nothing but 2 x 128 float2 per CTA crosses the cluster.
 // Loads of earlier kernels' output go through TMA only (programmatic dependent launch, see gemm_tc.cu); bias / gamma / beta are
 // constants of the stream.
 #define SDK_PDL_CAT 0
@@ -26,10 +27,12 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, THREADS = 192, STAGES = 4, MAX_CLUSTER = 8;
+constexpr int BM = 128, BK = 64, STAGES = 3, MAX_CLUSTER = 8;
+constexpr int THREADS = 64 + 256;                    // TMA warp, MMA warp, two epilogue groups of four warps
 constexpr int A_STAGE = BM * BK * 2;                 // 16 KiB
 constexpr int CHUNK_BYTES = BM * 128;                // one 32-column fp32 chunk of the tile
-constexpr int EPI_BUFS = 3;
+constexpr int OUT_BUF_BYTES = CHUNK_BYTES + BM * 64; // staging of one chunk: fp32 rows (SWIZZLE_128B) + bf16 rows (SWIZZLE_64B)
+constexpr int MAX_NCH = 5;
 
 struct alignas(64) LlnParams {
     CUtensorMap tmA, tmB, tmOut, tmRes, tmLn;
@@ -42,15 +45,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
-// one float into the same shared-memory offset of CTA `rank` of the cluster
-__device__ __forceinline__ void st_cluster_f32(float* local, uint32_t rank, float v) {
+// two floats into the same shared-memory offset of CTA `rank` of the cluster
+__device__ __forceinline__ void st_cluster_f32x2(float2* local, uint32_t rank, float a, float b) {
     asm volatile(
         "{\n\t"
         ".reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "st.shared::cluster.f32 [ra], %2;\n\t"
+        "st.shared::cluster.v2.f32 [ra], {%2, %3};\n\t"
         "}\n"
-        ::"r"(ptx::smem_u32(local)), "r"(rank), "f"(v) : "memory");
+        ::"r"(ptx::smem_u32(local)), "r"(rank), "f"(a), "f"(b) : "memory");
 }
 
 template <int BN>
@@ -60,21 +63,22 @@ linear_ln_kernel(const __grid_constant__ LlnParams p) {
     constexpr int NCH = BN / 32;
     constexpr uint32_t TMEM_COLS = BN <= 128 ? 128 : 256;
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM, BN);
+    static_assert(NCH <= MAX_NCH, "tile too wide");
+    static_assert(4 * OUT_BUF_BYTES <= STAGES * (A_STAGE + B_STAGE), "output staging must fit behind the pipeline stages");
 
-    // shared memory: [A stages][B stages][2 residual chunks][2 x exchange][barriers][bias | gamma | beta]; the output staging ring
-    // aliases the pipeline stages (idle once the accumulator is complete)
+    // shared memory: [A stages][B stages][NCH residual chunks][exchange][barriers][bias | gamma | beta]; the output staging
+    // (2 groups x 2 buffers) aliases the pipeline stages (idle once the accumulator is complete)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = sA + STAGES * A_STAGE;
     uint8_t* sRes = sB + STAGES * B_STAGE;
-    float* xch_sum = reinterpret_cast<float*>(sRes + 2 * CHUNK_BYTES);        // [MAX_CLUSTER][BM]
-    float* xch_sq = xch_sum + MAX_CLUSTER * BM;                               // [MAX_CLUSTER][BM]
-    uint64_t* full = reinterpret_cast<uint64_t*>(xch_sq + MAX_CLUSTER * BM);
+    float2* xch = reinterpret_cast<float2*>(sRes + MAX_NCH * CHUNK_BYTES);    // [2 * MAX_CLUSTER][BM] (mean, M2) partials
+    uint64_t* full = reinterpret_cast<uint64_t*>(xch + 2 * MAX_CLUSTER * BM);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
-    uint64_t* res_full = tmem_full + 1;                                       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+    uint64_t* res_full = tmem_full + 1;                                       // [MAX_NCH]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + MAX_NCH);
     float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
     float* s_gamma = s_bias + BN;
     float* s_beta = s_gamma + BN;
@@ -89,7 +93,7 @@ linear_ln_kernel(const __grid_constant__ LlnParams p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(tmem_full, 1);
-        ptx::mbar_init(&res_full[0], 1); ptx::mbar_init(&res_full[1], 1);
+        for (int i = 0; i < MAX_NCH; ++i) ptx::mbar_init(&res_full[i], 1);
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&p.tmA); ptx::prefetch_tmap(&p.tmB); ptx::prefetch_tmap(&p.tmOut); ptx::prefetch_tmap(&p.tmLn);
         if (p.has_res) ptx::prefetch_tmap(&p.tmRes);
@@ -121,6 +125,13 @@ linear_ln_kernel(const __grid_constant__ LlnParams p) {
                 }
                 ptx::tma_load_2d(sA + s * A_STAGE, &p.tmA, &full[s], i * BK, m0);
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
+                if (i == 0 && p.has_res) {                  // the whole residual tile travels under the main loop
+#pragma unroll 1
+                    for (int c = 0; c < NCH; ++c) {
+                        ptx::mbar_expect_tx(&res_full[c], (uint32_t)CHUNK_BYTES);
+                        ptx::tma_load_2d(sRes + c * CHUNK_BYTES, &p.tmRes, &res_full[c], n0 + c * 32, m0);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -142,39 +153,32 @@ linear_ln_kernel(const __grid_constant__ LlnParams p) {
         }
     }
 
-    // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
+    // ================= epilogue: two groups of four warps (warps 2..5, 6..9), group g owns the chunks g, g+2, ... =================
+    const int grp = (warp - 2) >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;                        // tile row == TMEM lane
-    const int et = threadIdx.x - 64;                    // 0..127 within the epilogue warps
+    const int et = (threadIdx.x - 64) & 127;            // 0..127 within the group
+    const int et2 = threadIdx.x - 64;                   // 0..255 over both groups
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t swz = (uint32_t)r & 7u;              // fp32 chunk rows: 128 B, SWIZZLE_128B
     const uint32_t swz2 = ((uint32_t)r >> 1) & 3u;      // bf16 chunk rows: 64 B, SWIZZLE_64B
-    uint32_t gk = 0;                                    // chunks staged so far (ring position over both store passes)
-    float row_sum = 0.f;
     if (warp >= 2) {
-        if (p.has_res && et == 0) {
-#pragma unroll 1
-            for (int i = 0; i < (NCH < 2 ? NCH : 2); ++i) {
-                ptx::mbar_expect_tx(&res_full[i], (uint32_t)CHUNK_BYTES);
-                ptx::tma_load_2d(sRes + i * CHUNK_BYTES, &p.tmRes, &res_full[i], n0 + i * 32, m0);
-            }
-        }
-        for (int j = et; j < BN; j += 128) {
+        for (int j = et2; j < BN; j += 256) {
             s_bias[j] = p.bias ? __ldg(p.bias + n0 + j) : 0.f;
             s_gamma[j] = __ldg(p.gamma + n0 + j);
             s_beta[j] = __ldg(p.beta + n0 + j);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 3, 256;" ::: "memory");
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
-        // ---- pass 1: finished fp32 values -> `out` (TMA store), back into TMEM, row sum
-        float sa[4] = {0.f, 0.f, 0.f, 0.f};
+        // ---- statistics pass: finished fp32 values (acc + bias + residual) back into TMEM; shifted sums about a pivot (the row's
+        // first value in this group) so that the single-pass variance does not cancel
+        float pivot = 0.f, sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
+        int n_mine = 0;
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c, ++gk) {
+        for (int c = grp; c < NCH; c += 2, ++n_mine) {
             uint32_t u[32];
             ptx::tmem_ld32(taddr + c * 32, u);
-            uint8_t* obuf = smem + (gk % EPI_BUFS) * CHUNK_BYTES;
-            uint8_t* ob = obuf + r * 128;
             ptx::tmem_ld_wait();
             float v[32];
 #pragma unroll
@@ -184,70 +188,69 @@ linear_ln_kernel(const __grid_constant__ LlnParams p) {
                 v[j + 2] = __uint_as_float(u[j + 2]) + a.z; v[j + 3] = __uint_as_float(u[j + 3]) + a.w;
             }
             if (p.has_res) {
-                ptx::mbar_wait(&res_full[c & 1], (uint32_t)(c >> 1) & 1u);
-                const uint8_t* rb = sRes + (c & 1) * CHUNK_BYTES + r * 128;
+                ptx::mbar_wait(&res_full[c], 0);
+                const uint8_t* rb = sRes + c * CHUNK_BYTES + r * 128;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 a = *reinterpret_cast<const float4*>(rb + ((j ^ swz) << 4));
                     v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
                 }
             }
+            if (n_mine == 0) pivot = v[0];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { sa[j & 3] += v[j]; u[j] = __float_as_uint(v[j]); }
-            ptx::tmem_st32(taddr + c * 32, u);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(ob + ((j ^ swz) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            ptx::fence_proxy_async();                  // this thread's smem writes -> visible to the TMA engine
-            if (et == 0) ptx::bulk_wait_read<1>();     // the buffer the NEXT chunk writes was read by the store issued two chunks ago
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et == 0) {
-                tma_store_2d(&p.tmOut, obuf, n0 + c * 32, m0);
-                ptx::bulk_commit();
-                if (p.has_res && c + 2 < NCH) {        // every thread has consumed residual chunk c: refill its buffer
-                    ptx::mbar_expect_tx(&res_full[c & 1], (uint32_t)CHUNK_BYTES);
-                    ptx::tma_load_2d(sRes + (c & 1) * CHUNK_BYTES, &p.tmRes, &res_full[c & 1], n0 + (c + 2) * 32, m0);
-                }
+            for (int j = 0; j < 32; ++j) {
+                const float d = v[j] - pivot;
+                sa[j & 3] += d; qa[j & 3] = fmaf(d, d, qa[j & 3]);
+                u[j] = __float_as_uint(v[j]);
             }
+            ptx::tmem_st32(taddr + c * 32, u);
         }
         ptx::tmem_st_wait();
-        row_sum = (sa[0] + sa[1]) + (sa[2] + sa[3]);
-        for (int k = 0; k < nc; ++k) st_cluster_f32(xch_sum + (int)rank * BM + r, (uint32_t)k, row_sum);
+        if (n_mine > 0) {
+            const float cnt = 32.f * (float)n_mine;
+            const float s1 = (sa[0] + sa[1]) + (sa[2] + sa[3]), s2 = (qa[0] + qa[1]) + (qa[2] + qa[3]);
+            const float part_mean = pivot + s1 / cnt, part_m2 = fmaxf(s2 - s1 * s1 / cnt, 0.f);
+            for (int k = 0; k < nc; ++k) st_cluster_f32x2(xch + ((int)rank * 2 + grp) * BM + r, (uint32_t)k, part_mean, part_m2);
+        }
     }
     __syncwarp();
-    ptx::cluster_sync_all();                 // (release / acquire) every CTA's row sums have landed in every peer
-    float mean = 0.f;
+    ptx::cluster_sync_all();                 // (release / acquire) every CTA's row partials have landed in every peer
     if (warp >= 2) {
-        float s = 0.f;
-        for (int k = 0; k < nc; ++k) s += xch_sum[k * BM + r];          // rank order: identical in every CTA of the cluster
-        mean = s * p.inv_n;
-        // ---- pass 1b: centred sum of squares of this CTA's columns
-        float qa[4] = {0.f, 0.f, 0.f, 0.f};
+        // ---- combine the 2 * nc partials (counts: group 0 has ceil(NCH/2) chunks, group 1 floor(NCH/2)) in slot order: every CTA of
+        // the cluster computes the same mean / rstd
+        constexpr float CNT0 = 32.f * (float)((NCH + 1) / 2), CNT1 = 32.f * (float)(NCH / 2);
+        float msum = 0.f;
+        for (int k = 0; k < nc; ++k) {
+            msum = fmaf(CNT0, xch[(2 * k) * BM + r].x, msum);
+            if (NCH > 1) msum = fmaf(CNT1, xch[(2 * k + 1) * BM + r].x, msum);
+        }
+        const float mean = msum * p.inv_n;
+        float m2 = 0.f;
+        for (int k = 0; k < nc; ++k) {
+            const float2 a = xch[(2 * k) * BM + r];
+            const float da = a.x - mean;
+            m2 += a.y + CNT0 * da * da;
+            if (NCH > 1) {
+                const float2 b = xch[(2 * k + 1) * BM + r];
+                const float db = b.x - mean;
+                m2 += b.y + CNT1 * db * db;
+            }
+        }
+        const float rstd = rsqrtf(m2 * p.inv_n + p.eps);
+        // ---- output pass: fp32 rows -> `out`, normalised bf16 rows -> `ln_out` (one bulk group per chunk, 2-buffer ring per group)
+        uint8_t* my_out = smem + grp * 2 * OUT_BUF_BYTES;
+        uint32_t gc = 0;
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = grp; c < NCH; c += 2, ++gc) {
             uint32_t u[32];
             ptx::tmem_ld32(taddr + c * 32, u);
+            uint8_t* obuf = my_out + (gc & 1u) * OUT_BUF_BYTES;
+            uint8_t* ob = obuf + r * 128;
+            uint8_t* ob2 = obuf + CHUNK_BYTES + r * 64;
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(u[j]) - mean; qa[j & 3] = fmaf(d, d, qa[j & 3]); }
-        }
-        const float row_sq = (qa[0] + qa[1]) + (qa[2] + qa[3]);
-        for (int k = 0; k < nc; ++k) st_cluster_f32(xch_sq + (int)rank * BM + r, (uint32_t)k, row_sq);
-    }
-    __syncwarp();
-    ptx::cluster_sync_all();
-    if (warp >= 2) {
-        float s = 0.f;
-        for (int k = 0; k < nc; ++k) s += xch_sq[k * BM + r];
-        const float rstd = rsqrtf(s * p.inv_n + p.eps);
-        // ---- pass 2: normalised bf16 rows -> `ln_out`
-#pragma unroll 1
-        for (int c = 0; c < NCH; ++c, ++gk) {
-            uint32_t u[32];
-            ptx::tmem_ld32(taddr + c * 32, u);
-            uint8_t* obuf = smem + (gk % EPI_BUFS) * CHUNK_BYTES;
-            uint8_t* ob = obuf + r * 64;
-            ptx::tmem_ld_wait();
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(ob + ((j ^ swz) << 4)) = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float y[8];
@@ -262,13 +265,14 @@ linear_ln_kernel(const __grid_constant__ LlnParams p) {
                 uint4 w;
                 w.x = *reinterpret_cast<unsigned*>(&h0); w.y = *reinterpret_cast<unsigned*>(&h1);
                 w.z = *reinterpret_cast<unsigned*>(&h2); w.w = *reinterpret_cast<unsigned*>(&h3);
-                *reinterpret_cast<uint4*>(ob + (((uint32_t)j ^ swz2) << 4)) = w;
+                *reinterpret_cast<uint4*>(ob2 + (((uint32_t)j ^ swz2) << 4)) = w;
             }
-            ptx::fence_proxy_async();
-            if (et == 0) ptx::bulk_wait_read<1>();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            ptx::fence_proxy_async();                  // this thread's smem writes -> visible to the TMA engine
+            if (et == 0) ptx::bulk_wait_read<0>();     // 2-buffer ring: the previous store (other buffer) has been read before anyone moves on
+            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
             if (et == 0) {
-                tma_store_2d(&p.tmLn, obuf, n0 + c * 32, m0);
+                tma_store_2d(&p.tmOut, obuf, n0 + c * 32, m0);
+                tma_store_2d(&p.tmLn, obuf + CHUNK_BYTES, n0 + c * 32, m0);
                 ptx::bulk_commit();
             }
         }
@@ -319,7 +323,7 @@ struct LinearLn {
 };
 
 int smem_need(int bn) {
-    return 1024 + STAGES * (A_STAGE + bn * BK * 2) + 2 * CHUNK_BYTES + 2 * MAX_CLUSTER * BM * 4 + 256 + 3 * bn * 4 + 32;
+    return 1024 + STAGES * (A_STAGE + bn * BK * 2) + MAX_NCH * CHUNK_BYTES + 2 * MAX_CLUSTER * BM * 8 + 256 + 3 * bn * 4 + 32;
 }
 
 template <int BN>
