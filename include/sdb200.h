@@ -262,6 +262,45 @@ int sdk_linear_ln_info(void* handle, int* out, int n);          /* block_n, clus
 int sdk_linear_ln_launch(void* handle, void* stream);
 int sdk_linear_ln_destroy(void* handle);
 
+/* ---- plan-level entry: a program's LAUNCH LIST behind the C ABI, replayable, serialisable (engine file) -------------------------
+ * The planning host records every launch of a program (one UNet forward = models/unet/unet.py:431-443, the context program, one
+ * whole sampler step = the loop body of models/diffusion.py:223-236, a VAE decode, ...) with sdk_plan_add_launch; the plan ADOPTS the
+ * tensor-core handles together with the descriptors they were created from (tuned tilings included), replays a program with ONE
+ * call, and sdk_plan_save / sdk_plan_load move the whole thing -- launch lists, descriptors, packed weights, tables -- to a host
+ * that has neither Python nor PyTorch (tools/c_host/denoise.c).  Up to 16 programs per plan; the package uses
+ * 0 = UNet forward, 1 = context program, 2 = time-embedding chain, 3 = forward without that chain, 4 = one sampler step. */
+typedef struct SdkAttentionTcDesc {      /* the arguments of sdk_attention_tc_create, as a struct (what a plan stores for the handle) */
+    const void* q; const void* k; const void* v; void* out;
+    int64_t q_row, q_batch, k_row, k_batch, v_row, v_batch, o_row, o_batch;
+    int B, heads, Sq, Sk, D;
+    float scale;
+} SdkAttentionTcDesc;
+int sdk_plan_create(void** plan);
+int sdk_plan_destroy(void* plan);       /* also destroys the adopted handles and, for a loaded plan, frees its device memory */
+/* Declare a device buffer the program touches: kind 0 = constant (weights / tables: contents are saved), 1 = scratch (zero-filled on
+ * load), 2 = scratch with a NAME the loading host can look up (inputs / outputs / loop state). */
+int sdk_plan_add_region(void* plan, const void* base, int64_t bytes, int kind, const char* name);
+/* handle_kind 1 = sdk_tc_gemm (desc = SdkTcGemmDesc, aux = {chan_stats pointer or 0, workspace pointer or 0}), 2 = sdk_attention_tc
+ * (desc = SdkAttentionTcDesc, aux = {causal}), 3 = sdk_linear_ln (desc = SdkLinearLnDesc).  The plan owns the handle from here on. */
+int sdk_plan_adopt(void* plan, int handle_kind, void* handle, const void* desc, int desc_bytes, const uint64_t* aux, int n_aux);
+/* Append one launch to `program`: fn_name = a launch-type entry point of this header ("sdk_layernorm", "sdk_tc_gemm_launch", ...),
+ * args = its arguments WITHOUT the trailing stream, each widened to 64 bits (pointers and integers as they are, floats as their
+ * IEEE-754 bit pattern, parameter structs by host address -- they are copied). */
+int sdk_plan_add_launch(void* plan, int program, const char* fn_name, const uint64_t* args, int nargs);
+int sdk_plan_num_launches(void* plan, int program);   /* -1 on a bad argument */
+int sdk_plan_launch(void* plan, int program, void* stream);
+/* capture `program` into a CUDA graph owned by the plan (after one eager launch); sdk_plan_launch then replays the graph */
+int sdk_plan_capture(void* plan, int program, void* stream);
+int sdk_plan_save(void* plan, const char* path);      /* synchronous (reads the constant regions back); fails if a pointer is in no region */
+int sdk_plan_load(const char* path, void** plan);     /* allocates ONE device slab for all regions on the current device */
+int sdk_plan_region(void* plan, const char* name, void** ptr, int64_t* bytes);
+/* conveniences for hosts without the CUDA runtime headers: async copies into / out of a named region, stream handling */
+int sdk_plan_upload(void* plan, const char* name, const void* host, int64_t bytes, void* stream);
+int sdk_plan_download(void* plan, const char* name, void* host, int64_t bytes, void* stream);
+int sdk_stream_create(void** stream);
+int sdk_stream_sync(void* stream);
+int sdk_stream_destroy(void* stream);
+
 #ifdef __cplusplus
 }
 #endif

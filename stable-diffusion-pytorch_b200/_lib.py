@@ -78,6 +78,23 @@ SIGNATURES = {
     "sdk_linear_ln_info": [P, P, I32],
     "sdk_linear_ln_launch": [P, P],
     "sdk_linear_ln_destroy": [P],
+    # --- plan.cu
+    "sdk_plan_create": [P],
+    "sdk_plan_destroy": [P],
+    "sdk_plan_add_region": [P, P, I64, I32, C.c_char_p],
+    "sdk_plan_adopt": [P, I32, P, P, I32, P, I32],
+    "sdk_plan_add_launch": [P, I32, C.c_char_p, P, I32],
+    "sdk_plan_num_launches": [P, I32],
+    "sdk_plan_launch": [P, I32, P],
+    "sdk_plan_capture": [P, I32, P],
+    "sdk_plan_save": [P, C.c_char_p],
+    "sdk_plan_load": [C.c_char_p, P],
+    "sdk_plan_region": [P, C.c_char_p, P, P],
+    "sdk_plan_upload": [P, C.c_char_p, P, I64, P],
+    "sdk_plan_download": [P, C.c_char_p, P, I64, P],
+    "sdk_stream_create": [P],
+    "sdk_stream_sync": [P],
+    "sdk_stream_destroy": [P],
     # --- misc
     "sdk_device_info": [P, I32],
     "sdk_set_pdl": [I32],
@@ -108,6 +125,13 @@ class LinearLnDesc(C.Structure):
     """Mirror of SdkLinearLnDesc (include/sdb200.h)."""
     _fields_ = [("a", P), ("w", P), ("bias", P), ("residual", P), ("out", P), ("ln_out", P), ("gamma", P), ("beta", P),
                 ("eps", F32), ("M", I64), ("K", I32), ("N", I32)]
+
+
+class AttentionTcDesc(C.Structure):
+    """Mirror of SdkAttentionTcDesc (include/sdb200.h)."""
+    _fields_ = [("q", P), ("k", P), ("v", P), ("out", P),
+                ("q_row", I64), ("q_batch", I64), ("k_row", I64), ("k_batch", I64), ("v_row", I64), ("v_batch", I64),
+                ("o_row", I64), ("o_batch", I64), ("B", I32), ("heads", I32), ("Sq", I32), ("Sk", I32), ("D", I32), ("scale", F32)]
 
 
 F32_T, BF16_T = 0, 1

@@ -110,6 +110,44 @@ class DenoiseLoop:
             _lib.check(lib.sdk_ddim_step(self.latent.data_ptr(), eps_u, eps_c, self.cfg_scale, 0, self.latent.data_ptr(), n,
                                          self.coef.data_ptr(), s.noise_step, p.t_in.data_ptr(), 0, pred, stream))
 
+    def export_engine(self, path: str):
+        """Engine file of the WHOLE sampling loop for a host without Python (sdk_plan_load; tools/c_host/denoise.c): programs 0-3 of
+        the UNet plan plus program 4 = one sampler step (next timestep -> time-embedding row -> UNet -> CFG + DDIM/DDPM update in
+        place).  Call after ``reset`` (the timestep grid, coefficient and time-embedding tables are baked in as constants).
+        Named regions: "x" (the latent state, NCHW fp32), "context", "counter" (int32 grid position: zero it to restart), "out",
+        and "noise" for DDPM."""
+        s, p = self.sampler, self.prog
+        if self.ts_table is None:
+            raise RuntimeError("export_engine: call reset(latent, context) first (the timestep grid is part of the engine)")
+        if self.inpaint_orig is not None:
+            raise RuntimeError("export_engine: the inpainting loop is not exportable (its image / mask are per-call inputs)")
+        pid = StepProgram.PROGRAM_LOOP_STEP
+        if self.lib.sdk_plan_num_launches(p._ensure_plan(), pid) == 0:
+            p.plan_add(pid, "sdk_next_timestep", (self.ts_table.data_ptr(), self.ts_table.numel(), self.counter.data_ptr(), p.t_in.data_ptr()))
+            body = p.ops
+            if self.tb_table is not None:
+                p.plan_add(pid, "sdk_gather_row", (self.tb_table.data_ptr(), p.tb.shape[1], self.tb_table.shape[0], self.counter.data_ptr(),
+                                                   -1, p.tb.data_ptr()))
+                body = p.body_ops
+            for fn, args in body:
+                p.plan_add(pid, fn.__name__, args)
+            n = self.latent.numel()
+            eps_u = p.out.data_ptr()
+            eps_c = p.out.data_ptr() + 4 * n if self.do_cfg else 0
+            if isinstance(s, DDPMSampler):
+                p.plan_add(pid, "sdk_ddpm_step", (self.latent.data_ptr(), eps_u, eps_c, self.cfg_scale, self.noise.data_ptr(),
+                                                  self.latent.data_ptr(), n, self.coef.data_ptr(), s.noise_step, p.t_in.data_ptr(), 0))
+            else:
+                pred = PRED_V if s.prediction_type == "v_prediction" else PRED_EPS
+                p.plan_add(pid, "sdk_ddim_step", (self.latent.data_ptr(), eps_u, eps_c, self.cfg_scale, 0, self.latent.data_ptr(), n,
+                                                  self.coef.data_ptr(), s.noise_step, p.t_in.data_ptr(), 0, pred))
+        extra = [(self.ts_table, 0, ""), (self.coef, 0, ""), (self.counter, 2, "counter")]
+        if self.tb_table is not None:
+            extra.append((self.tb_table, 0, ""))
+        if self.noise is not None:
+            extra.append((self.noise, 2, "noise"))
+        p.export_engine(path, extra_regions=extra)
+
     def _prepare(self, context: torch.Tensor):
         s, p = self.sampler, self.prog
         key = (tuple(s.timesteps.tolist()), s._stride())

@@ -19,13 +19,14 @@ import ctypes as C
 import json
 import math
 import os
+import struct
 from typing import Dict, List, Optional, Union
 
 import torch
 from torch import nn
 
 from . import _lib
-from ._lib import BF16_T, F32_T, ConvParams, LinearLnDesc, TcGemmDesc
+from ._lib import BF16_T, F32_T, AttentionTcDesc, ConvParams, LinearLnDesc, TcGemmDesc
 from .arch import BLOCK_OUT, Conv, ResBlock, Transformer, UNetArch, build_arch, param_spec
 
 _DT = {F32_T: torch.float32, BF16_T: torch.bfloat16}
@@ -275,6 +276,10 @@ class StepProgram:
         self.tc_handles = []
         self.attn_handles = []
         self.lln_handles = []
+        self._handle_meta = []   # (kind, handle, descriptor, aux) of every tensor-core handle: what the plan-level C entry adopts
+        self.consts = []         # constant device tensors created by the planner itself (beside the packed weights)
+        self.plan = None         # sdk_plan (built on first launch): the launch lists behind the C ABI
+        self._plan_ids = {}
         # GroupNorm statistics from per-channel sums accumulated by the producing GEMM (bf16 program) instead of a statistics
         # kernel.  All tables live in one arena that the program zeroes with its first op.
         self.gn_from_sums = pw.precision != "fp32" and net.gn_mode == "sums"
@@ -413,12 +418,14 @@ class StepProgram:
         _lib.check(rc)
         self.tc_handles.append(h)
         self.keep.append(d)
+        self._handle_meta.append([1, h, d, cs.data_ptr() if cs is not None else 0])
         self._emit(self.lib.sdk_tc_gemm_launch, h, ctx=ctx)
         if cs is None:
             return False
         # statistics of the output accumulated by the GEMM's own epilogue into the (zeroed once per step) table
         rc = self.lib.sdk_tc_gemm_set_stats(h, cs.data_ptr())
         if rc == -3:                                        # SDK_ERR_UNSUPPORTED: tiling cannot attribute rows to samples
+            self._handle_meta[-1][3] = 0
             return False
         _lib.check(rc)
         return True
@@ -630,6 +637,7 @@ class StepProgram:
         _lib.check(rc)
         self.lln_handles.append(h)
         self.keep.append(d)
+        self._handle_meta.append([3, h, d, 0])
         self._emit(self.lib.sdk_linear_ln_launch, h)
         return out, ln
 
@@ -642,6 +650,12 @@ class StepProgram:
                                                         out.data_ptr(), Cc, Sq * Cc, B, heads, Sq, Sk, D, float(D ** -0.5), C.byref(h)))
             if causal:
                 _lib.check(self.lib.sdk_attention_tc_set_causal(h, 1))
+            ad = AttentionTcDesc()
+            ad.q, ad.k, ad.v, ad.out = q, k, v, out.data_ptr()
+            ad.q_row, ad.q_batch, ad.k_row, ad.k_batch, ad.v_row, ad.v_batch = q_row, q_batch, k_row, k_batch, v_row, v_batch
+            ad.o_row, ad.o_batch, ad.B, ad.heads, ad.Sq, ad.Sk, ad.D, ad.scale = Cc, Sq * Cc, B, heads, Sq, Sk, D, float(D ** -0.5)
+            self.keep.append(ad)
+            self._handle_meta.append([2, h, ad, int(bool(causal))])
             self.attn_handles.append(h)
             self._emit(self.lib.sdk_attention_tc_launch, h)
             return out
@@ -835,6 +849,7 @@ class StepProgram:
             cs = self._stat_table(B, BLOCK_OUT[0]) if self.gn_from_sums else None
             w_t = t["conv_in.w"].float().reshape(BLOCK_OUT[0], 36).t().contiguous()        # [kh][kw][cin][N]
             self.keep.append(w_t)
+            self.consts.append(w_t)
             self._emit(lib.sdk_conv_in, xin.data_ptr(), w_t.data_ptr(), t["conv_in.b"].data_ptr(), x.data_ptr(),
                        cs.data_ptr() if cs is not None else 0, B, H, W, BLOCK_OUT[0])
             if cs is not None:
@@ -966,6 +981,9 @@ class StepProgram:
 
     def __del__(self):
         try:
+            if getattr(self, "plan", None) is not None:           # the plan owns the adopted handles
+                self.lib.sdk_plan_destroy(self.plan)
+                return
             for h in getattr(self, "tc_handles", []):
                 self.lib.sdk_tc_gemm_destroy(h)
             for h in getattr(self, "attn_handles", []):
@@ -975,10 +993,112 @@ class StepProgram:
         except Exception:
             pass
 
+    # ---- plan-level C entry (include/sdb200.h: sdk_plan_*) -------------------------------------------------
+    # The launch lists live in an sdk_plan: one C call replays a program, sdk_plan_save writes an engine file that a host
+    # without Python / PyTorch loads and runs (tools/c_host/denoise.c).  Program ids of the package:
+    PROGRAM_IDS = {"ops": 0, "ctx_ops": 1, "time_ops": 2, "body_ops": 3}
+    PROGRAM_LOOP_STEP = 4
+
+    @staticmethod
+    def _slots(fn_name, args):
+        """Arguments of one recorded launch as the 64-bit slots sdk_plan_add_launch takes (floats as IEEE-754 bits)."""
+        types = _lib.SIGNATURES[fn_name][:-1]                # without the trailing stream
+        if len(types) != len(args):
+            raise RuntimeError(f"{fn_name}: {len(args)} recorded arguments, the binding table has {len(types)}")
+        out = (C.c_uint64 * max(len(args), 1))()
+        for i, (a, ty) in enumerate(zip(args, types)):
+            if ty is _lib.F32:
+                v = struct.unpack("<I", struct.pack("<f", float(a)))[0]
+            elif hasattr(a, "_obj"):                         # ctypes.byref(struct): the struct's host address (the plan copies it)
+                v = C.addressof(a._obj)
+            elif isinstance(a, C.c_void_p):
+                v = a.value or 0
+            elif a is None:
+                v = 0
+            else:
+                v = int(a) & 0xFFFFFFFFFFFFFFFF
+            out[i] = v
+        return out
+
+    def _ensure_plan(self):
+        if self.plan is not None:
+            return self.plan
+        lib = self.lib
+        h = C.c_void_p()
+        _lib.check(lib.sdk_plan_create(C.byref(h)))
+        ws = self.tc_ws.data_ptr() if getattr(self, "tc_ws", None) is not None else 0
+        for kind, hd, desc, aux in self._handle_meta:
+            a = (C.c_uint64 * 2)(aux, ws if kind == 1 else 0)
+            _lib.check(lib.sdk_plan_adopt(h, kind, hd, C.byref(desc), C.sizeof(desc), a, 2))
+        self.plan = h
+        return h
+
+    def plan_add(self, program, fn_name, args):
+        """Append one launch (entry-point name + arguments without the stream) to ``program`` of this plan."""
+        sl = self._slots(fn_name, args)
+        _lib.check(self.lib.sdk_plan_add_launch(self._ensure_plan(), program, fn_name.encode(), sl, len(args)))
+
+    def _program_of(self, ops):
+        """Program id of one of this object's launch lists (transcribed into the plan on first use), None for ad-hoc lists."""
+        pid = self._plan_ids.get(id(ops))
+        if pid is not None:
+            return pid
+        for name, pid in self.PROGRAM_IDS.items():
+            if getattr(self, name, None) is ops:
+                for fn, args in ops:
+                    self.plan_add(pid, fn.__name__, args)
+                self._plan_ids[id(ops)] = pid
+                return pid
+        return None
+
+    def plan_regions(self):
+        """(tensor, kind, name) of every device buffer the programs touch: kind 0 constant, 1 scratch, 2 named I/O."""
+        reg = [(t, 0, "") for t in self.pw.t.values()] + [(t, 0, "") for t in self.consts]
+        reg += [(raw, 1, "") for raw in self.pool.all]
+        for name in ("stat_arena", "gn_ws", "gn_stats", "tc_ws", "tb", "cond_act", "kv_all"):
+            t = getattr(self, name, None)
+            if t is not None:
+                reg.append((t, 1, ""))
+        reg += [(t, 1, "") for t in getattr(self, "kv", {}).values()]
+        reg += [(t, 1, "") for t in self.keep if isinstance(t, torch.Tensor) and all(t is not c for c in self.consts)]
+        for name, attr in (("x", "x_in"), ("timestep", "t_in"), ("context", "cond_in"), ("out", "out")):
+            t = getattr(self, attr, None)
+            if t is not None:
+                reg.append((t, 2, name))
+        return reg
+
+    def export_engine(self, path, extra_regions=()):
+        """Write the engine file of this program set (sdk_plan_save): launch lists, descriptors with their tuned tilings, packed
+        weights.  A host without Python loads it with sdk_plan_load and runs program 1 (context) then 0 (forward)."""
+        plan = self._ensure_plan()
+        for name in self.PROGRAM_IDS:
+            ops = getattr(self, name, None)
+            if ops:
+                self._program_of(ops)
+        seen = set()
+        for t, kind, name in list(self.plan_regions()) + list(extra_regions):
+            nbytes = t.numel() * t.element_size()
+            key = (t.data_ptr(), nbytes)
+            if nbytes == 0 or key in seen:
+                continue
+            if kind != 2 and any(k[0] == key[0] for k in seen):           # a view of a buffer that is already registered
+                continue
+            seen.add(key)
+            _lib.check(self.lib.sdk_plan_add_region(plan, t.data_ptr(), nbytes, kind, name.encode()))
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sdk_plan_save(plan, os.fsencode(path)))
+
     # ---- execution ----------------------------------------------------------------------
     def launch(self, ops):
         with torch.cuda.device(self.device):                    # the library keys its per-device state on the CURRENT device
             stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            pid = self._program_of(ops)
+            if pid is not None:                                 # the program's launch list lives in the C plan: one call
+                rc = self.lib.sdk_plan_launch(self.plan, pid, stream)
+                if rc != 0:
+                    _lib.check(rc)
+                return
             for fn, args in ops:
                 rc = fn(*args, stream)
                 if rc != 0:

@@ -47,7 +47,7 @@ def test_struct_layouts_match_header():
     """ctypes mirrors of the two parameter structs have the field order of the header."""
     from stable_diffusion_pytorch_b200 import _lib
     src = open(HEADER).read()
-    for cname, mirror in (("SdkConvParams", _lib.ConvParams), ("SdkTcGemmDesc", _lib.TcGemmDesc), ("SdkLinearLnDesc", _lib.LinearLnDesc)):
+    for cname, mirror in (("SdkConvParams", _lib.ConvParams), ("SdkTcGemmDesc", _lib.TcGemmDesc), ("SdkLinearLnDesc", _lib.LinearLnDesc), ("SdkAttentionTcDesc", _lib.AttentionTcDesc)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = []
