@@ -582,7 +582,7 @@ def main():
             # matmuls that run inside the projection + LayerNorm kernel) over the device time of ITS launches
             ach = (gemm_gflop - lln_gflop) / gemm_ms            # GFLOP / ms == TFLOP/s
             traffic, traffic_src = None, None
-            for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+            for name in ("r02b_gemm_traffic.json", "r02_gemm_traffic.json", "r01_gemm_traffic.json"):
                 try:
                     with open(os.path.join(ROOT, "profiles", name)) as f:
                         tj = json.load(f)

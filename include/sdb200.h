@@ -59,6 +59,12 @@ int sdk_ddim_inpaint_step(const float* x, const float* eps_c, const float* eps_u
                           const float* orig, int64_t orig_batch, const uint8_t* mask, float* out,
                           int64_t batch, int64_t channels, int64_t hw, const float* coef_table, int T,
                           const int64_t* t_dev, int64_t t_host, int prediction_type, void* stream);
+/* the same loop body with the DDPM update (the reference's inpaint also takes sampler='ddpm', models/diffusion.py:314-316;
+ * ddpm.py:62-82); noise = the randn draw of ddpm.py:80, [batch][channels][hw] */
+int sdk_ddpm_inpaint_step(const float* x, const float* eps_c, const float* eps_u, float cfg_scale,
+                          const float* orig, int64_t orig_batch, const uint8_t* mask, const float* noise, float* out,
+                          int64_t batch, int64_t channels, int64_t hw, const float* coef_table, int T,
+                          const int64_t* t_dev, int64_t t_host, void* stream);
 /* models/scheduler/ddim.py:46-55 — per-sample timesteps t_dev[batch] */
 int sdk_forward_process(const float* x0, const float* noise, float* out, int64_t batch, int64_t per_sample,
                         const float* coef_table, int T, const int64_t* t_dev, void* stream);

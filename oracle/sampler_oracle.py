@@ -136,11 +136,13 @@ def x0_from_eps(x, eps, alpha_T=0.0047 ** 0.5, sigma_T=(1 - 0.0047) ** 0.5):
     return (((x.astype(F) - (F(sigma_T) * eps.astype(F)).astype(F)).astype(F)) / F(alpha_T)).astype(F)
 
 
-def inpaint_step(x_t, t, pred_2b, orig, mask, cfg_scale, alphas, a_hat, noise_step, inference_steps, prediction_type="epsilon"):
+def inpaint_step(x_t, t, pred_2b, orig, mask, cfg_scale, alphas, a_hat, noise_step, inference_steps, prediction_type="epsilon",
+                 ddpm_noise=None):
     """Loop body of the inpainting path after the UNet call (models/diffusion.py:387-398), fp32, op by op:
     cond, uncond = chunk(2); e = s*(cond - uncond) + cond; noised = forward_process(orig, t, e);
     x = where(~mask, noised, x_t); reverse_process(x, t, e).  ``pred_2b`` may also be the plain (B, ...) prediction with
-    cfg_scale None.  mask: bool [h, w], True = repaint."""
+    cfg_scale None.  mask: bool [h, w], True = repaint.  ``ddpm_noise`` given: the ancestral DDPM update (ddpm.py:62-82) with that
+    randn draw instead of DDIM (the reference's inpaint takes sampler='ddpm' too, diffusion.py:314-316)."""
     f = np.float32
     if cfg_scale is None:
         e = pred_2b.astype(f)
@@ -149,4 +151,6 @@ def inpaint_step(x_t, t, pred_2b, orig, mask, cfg_scale, alphas, a_hat, noise_st
         e = (f(cfg_scale) * (c - u)).astype(f) + c
     noised = forward_process(np.broadcast_to(orig, e.shape).astype(f), np.array([t]), e, a_hat)
     x = np.where(mask[None, None].astype(bool), x_t.astype(f), noised)
+    if ddpm_noise is not None:
+        return ddpm_reverse(x, t, e, a_hat, noise_step, inference_steps, ddpm_noise)
     return ddim_reverse(x, t, e, alphas, a_hat, noise_step, inference_steps, prediction_type=prediction_type)

@@ -109,12 +109,12 @@ step_kernel(const float* x, const float* __restrict__ eu, const float* __restric
 //   e      = s*(c - u) + c                      CFG in the inpaint loop's own form, model output ordered [cond ; uncond]
 //   noised = sqrt(a_hat_t)*orig + sqrt(1 - a_hat_t)*e        forward_process(encoded_img, t, e)   (ddim.py:46-55)
 //   xin    = mask ? x : noised                  torch.where(~mask, noised, latent); mask is per pixel, shared by batch and channels
-//   x'     = DDIM(xin, e)                       reverse_process
-template <int PRED>
+//   x'     = DDIM(xin, e)  |  DDPM(xin, e, z)   reverse_process (MODE 0 / 1: DDIM eps / v; MODE 2: DDPM with the randn draw z of ddpm.py:80)
+template <int MODE>
 __global__ void __launch_bounds__(256)
 inpaint_step_kernel(const float* x, const float* __restrict__ ec, const float* __restrict__ eu, float scale,
                     const float* __restrict__ orig, long long orig_batch_stride, const unsigned char* __restrict__ mask,
-                    float* out, long long n, long long chw, long long hw,
+                    const float* __restrict__ noise, float* out, long long n, long long chw, long long hw,
                     const float* __restrict__ table, int T, const long long* __restrict__ t_dev, long long t_host) {
     pdl_trigger();
     pdl_wait();
@@ -127,7 +127,7 @@ inpaint_step_kernel(const float* x, const float* __restrict__ ec, const float* _
         if (eu) e = __fadd_rn(__fmul_rn(scale, __fsub_rn(e, eu[i])), e);
         const float noised = __fadd_rn(__fmul_rn(k.c[5], __ldg(orig + b * orig_batch_stride + r)), __fmul_rn(k.c[6], e));
         const float xin = mask[r % hw] ? x[i] : noised;
-        const float y = ddim_one<PRED>(xin, e, k, false, 0.f);
+        const float y = MODE == 2 ? ddpm_one(xin, e, k, noise[i]) : ddim_one<(MODE == 2 ? 0 : MODE)>(xin, e, k, false, 0.f);
         out[i] = ok ? y : qnan;
     }
 }
@@ -202,11 +202,29 @@ extern "C" int sdk_ddim_inpaint_step(const float* x, const float* eps_c, const f
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = grid_for(n, 256);
     if (prediction_type == 0)
-        SDK_CUDA(sdk_launch(inpaint_step_kernel<0>, dim3(grid), dim3(256), (size_t)0, s, x, eps_c, eps_u, cfg_scale, orig, ostride, mask, out, n, chw,
+        SDK_CUDA(sdk_launch(inpaint_step_kernel<0>, dim3(grid), dim3(256), (size_t)0, s, x, eps_c, eps_u, cfg_scale, orig, ostride, mask, (const float*)nullptr, out, n, chw,
                             (long long)hw, coef_table, T, (const long long*)t_dev, (long long)t_host));
     else
-        SDK_CUDA(sdk_launch(inpaint_step_kernel<1>, dim3(grid), dim3(256), (size_t)0, s, x, eps_c, eps_u, cfg_scale, orig, ostride, mask, out, n, chw,
+        SDK_CUDA(sdk_launch(inpaint_step_kernel<1>, dim3(grid), dim3(256), (size_t)0, s, x, eps_c, eps_u, cfg_scale, orig, ostride, mask, (const float*)nullptr, out, n, chw,
                             (long long)hw, coef_table, T, (const long long*)t_dev, (long long)t_host));
+    SDK_LAUNCH_CHECK();
+    return SDK_OK;
+}
+
+// the same loop body with the ancestral DDPM update (the reference's inpaint accepts sampler='ddpm', models/diffusion.py:314-316);
+// noise = the randn draw of ddpm.py:80, caller-supplied
+extern "C" int sdk_ddpm_inpaint_step(const float* x, const float* eps_c, const float* eps_u, float cfg_scale,
+                                     const float* orig, int64_t orig_batch, const uint8_t* mask, const float* noise, float* out,
+                                     int64_t batch, int64_t channels, int64_t hw, const float* coef_table, int T,
+                                     const int64_t* t_dev, int64_t t_host, void* stream) {
+    SDK_CHECK_ARG(x && eps_c && orig && mask && noise && out && coef_table, "sdk_ddpm_inpaint_step: null pointer");
+    SDK_CHECK_ARG(batch >= 0 && channels > 0 && hw > 0 && T > 0, "sdk_ddpm_inpaint_step: bad sizes");
+    SDK_CHECK_ARG(orig_batch == 1 || orig_batch == batch, "sdk_ddpm_inpaint_step: orig batch %lld must be 1 or %lld", (long long)orig_batch, (long long)batch);
+    const long long chw = channels * hw, n = batch * chw;
+    if (n == 0) return SDK_OK;
+    const long long ostride = orig_batch == 1 ? 0 : chw;
+    SDK_CUDA(sdk_launch(inpaint_step_kernel<2>, dim3(grid_for(n, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, x, eps_c, eps_u, cfg_scale, orig, ostride, mask,
+                        noise, out, n, chw, (long long)hw, coef_table, T, (const long long*)t_dev, (long long)t_host));
     SDK_LAUNCH_CHECK();
     return SDK_OK;
 }

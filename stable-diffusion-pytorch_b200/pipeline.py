@@ -66,8 +66,6 @@ class DenoiseLoop:
         if encoded_img is None:
             self.inpaint_orig, self.inpaint_mask = None, None
         else:
-            if not isinstance(self.sampler, DDIMSampler):
-                raise RuntimeError("the inpainting loop is defined for the DDIM sampler")
             o = encoded_img.to(self.device, torch.float32).contiguous()
             if o.shape[0] not in (1, self.B) or tuple(o.shape[1:]) != tuple(self.latent.shape[1:]):
                 raise RuntimeError(f"encoded_img {tuple(o.shape)} does not broadcast against the latent {tuple(self.latent.shape)}")
@@ -95,7 +93,13 @@ class DenoiseLoop:
         out = p.out
         eps_u = out.data_ptr()
         eps_c = out.data_ptr() + 4 * n if self.do_cfg else 0
-        if isinstance(s, DDPMSampler):
+        if isinstance(s, DDPMSampler) and self.inpaint_orig is not None:
+            ch = self.latent.shape[1]                  # rows are [cond ; uncond] in the inpaint loop: eps_u / eps_c name the halves
+            _lib.check(lib.sdk_ddpm_inpaint_step(self.latent.data_ptr(), eps_u, eps_c, self.cfg_scale, self.inpaint_orig.data_ptr(),
+                                                 self.inpaint_orig.shape[0], self.inpaint_mask.data_ptr(), self.noise.data_ptr(),
+                                                 self.latent.data_ptr(), self.B, ch, self.H * self.W, self.coef.data_ptr(), s.noise_step,
+                                                 p.t_in.data_ptr(), 0, stream))
+        elif isinstance(s, DDPMSampler):
             _lib.check(lib.sdk_ddpm_step(self.latent.data_ptr(), eps_u, eps_c, self.cfg_scale, self.noise.data_ptr(),
                                          self.latent.data_ptr(), n, self.coef.data_ptr(), s.noise_step, p.t_in.data_ptr(), 0, stream))
         elif self.inpaint_orig is not None:

@@ -170,6 +170,60 @@ class _SamplerBase:
         return tab
 
 
+    def inpaint_step(self, x_t: torch.Tensor, timestep, model_output: torch.Tensor, encoded_img: torch.Tensor, mask: torch.Tensor,
+                     *, cfg_scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
+                     noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Everything the inpainting loop does after the UNet call (models/diffusion.py:387-398), fused:
+
+            cond, uncond = model_output.chunk(2); pred = cfg_scale * (cond - uncond) + cond      (only with cfg_scale)
+            noised, _ = forward_process(encoded_img, timestep, pred)
+            x = torch.where(~mask, noised, x_t)                   # mask: (1, 1, h, w) or (h, w) bool, True = repaint
+            return reverse_process(x, timestep, pred)
+
+        Note the inpaint loop's own CFG convention: rows ordered [cond ; uncond] and pred = s*(c-u) + c.
+        Both samplers (the reference's inpaint takes sampler='ddim' or 'ddpm', diffusion.py:314-320); with DDPM the update draws
+        fresh N(0,1) noise from torch's global generator like ddpm.py:80 unless ``noise`` is given."""
+        self._check_cuda(x_t, "inpaint_step")
+        x = x_t.contiguous().float()
+        b, ch, h, w = x.shape
+        mo = model_output.to(x.device, torch.float32).contiguous()
+        n = x.numel()
+        if cfg_scale is None:
+            if mo.shape != x.shape:
+                raise RuntimeError(f"model_output {tuple(mo.shape)} vs x_t {tuple(x.shape)}")
+            eps_c, eps_u, scale = mo.data_ptr(), 0, 0.0
+        else:
+            if mo.shape[0] != 2 * b or mo.shape[1:] != x.shape[1:]:
+                raise RuntimeError(f"CFG model_output must be (2B, ...) = {(2 * b,) + tuple(x.shape[1:])}, got {tuple(mo.shape)}")
+            eps_c, eps_u, scale = mo.data_ptr(), mo.data_ptr() + n * 4, float(cfg_scale)
+        orig = encoded_img.to(x.device, torch.float32).contiguous()
+        if orig.shape[0] not in (1, b) or tuple(orig.shape[1:]) != (ch, h, w):
+            raise RuntimeError(f"encoded_img {tuple(orig.shape)} does not broadcast against x_t {tuple(x.shape)}")
+        if mask.numel() != h * w:
+            raise RuntimeError(f"mask must hold one value per latent pixel ({h}x{w}), got {tuple(mask.shape)}")
+        m8 = mask.to(x.device).reshape(h * w).ne(0).to(torch.uint8).contiguous()
+        tab = self._coef_table(x.device, 0.0)
+        t_ptr, t_host, keep = self._timestep_args(timestep, x.device)
+        res = torch.empty_like(x) if out is None else out
+        if n == 0:
+            return res
+        if isinstance(self, DDPMSampler):
+            if noise is None:
+                noise = torch.randn(x_t.shape, dtype=x_t.dtype, device=x_t.device)
+            nz = noise.to(x.device, torch.float32).contiguous()
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.lib().sdk_ddpm_inpaint_step(
+                    x.data_ptr(), eps_c, eps_u, scale, orig.data_ptr(), orig.shape[0], m8.data_ptr(), nz.data_ptr(), res.data_ptr(), b, ch,
+                    h * w, tab.data_ptr(), self.noise_step, t_ptr, t_host, _lib.current_stream(x.device)))
+            return res
+        with torch.cuda.device(x.device):              # launches go to the tensor's device, not the caller's current one
+            _lib.check(_lib.lib().sdk_ddim_inpaint_step(
+                x.data_ptr(), eps_c, eps_u, scale, orig.data_ptr(), orig.shape[0], m8.data_ptr(), res.data_ptr(), b, ch, h * w,
+                tab.data_ptr(), self.noise_step, t_ptr, t_host, PRED_V if self.prediction_type == "v_prediction" else PRED_EPS,
+                _lib.current_stream(x.device)))
+        return res
+
+
 class DDIMSampler(_SamplerBase):
     """reference: models/scheduler/ddim.py:7-96."""
     _timestep_offset = 1
@@ -246,47 +300,6 @@ class DDIMSampler(_SamplerBase):
         return out
 
     step = reverse_process
-
-    def inpaint_step(self, x_t: torch.Tensor, timestep, model_output: torch.Tensor, encoded_img: torch.Tensor, mask: torch.Tensor,
-                     *, cfg_scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Everything the inpainting loop does after the UNet call (models/diffusion.py:387-398), fused:
-
-            cond, uncond = model_output.chunk(2); pred = cfg_scale * (cond - uncond) + cond      (only with cfg_scale)
-            noised, _ = forward_process(encoded_img, timestep, pred)
-            x = torch.where(~mask, noised, x_t)                   # mask: (1, 1, h, w) or (h, w) bool, True = repaint
-            return reverse_process(x, timestep, pred)
-
-        Note the inpaint loop's own CFG convention: rows ordered [cond ; uncond] and pred = s*(c-u) + c."""
-        self._check_cuda(x_t, "inpaint_step")
-        x = x_t.contiguous().float()
-        b, ch, h, w = x.shape
-        mo = model_output.to(x.device, torch.float32).contiguous()
-        n = x.numel()
-        if cfg_scale is None:
-            if mo.shape != x.shape:
-                raise RuntimeError(f"model_output {tuple(mo.shape)} vs x_t {tuple(x.shape)}")
-            eps_c, eps_u, scale = mo.data_ptr(), 0, 0.0
-        else:
-            if mo.shape[0] != 2 * b or mo.shape[1:] != x.shape[1:]:
-                raise RuntimeError(f"CFG model_output must be (2B, ...) = {(2 * b,) + tuple(x.shape[1:])}, got {tuple(mo.shape)}")
-            eps_c, eps_u, scale = mo.data_ptr(), mo.data_ptr() + n * 4, float(cfg_scale)
-        orig = encoded_img.to(x.device, torch.float32).contiguous()
-        if orig.shape[0] not in (1, b) or tuple(orig.shape[1:]) != (ch, h, w):
-            raise RuntimeError(f"encoded_img {tuple(orig.shape)} does not broadcast against x_t {tuple(x.shape)}")
-        if mask.numel() != h * w:
-            raise RuntimeError(f"mask must hold one value per latent pixel ({h}x{w}), got {tuple(mask.shape)}")
-        m8 = mask.to(x.device).reshape(h * w).ne(0).to(torch.uint8).contiguous()
-        tab = self._coef_table(x.device, 0.0)
-        t_ptr, t_host, keep = self._timestep_args(timestep, x.device)
-        res = torch.empty_like(x) if out is None else out
-        if n == 0:
-            return res
-        with torch.cuda.device(x.device):              # launches go to the tensor's device, not the caller's current one
-            _lib.check(_lib.lib().sdk_ddim_inpaint_step(
-                x.data_ptr(), eps_c, eps_u, scale, orig.data_ptr(), orig.shape[0], m8.data_ptr(), res.data_ptr(), b, ch, h * w,
-                tab.data_ptr(), self.noise_step, t_ptr, t_host, PRED_V if self.prediction_type == "v_prediction" else PRED_EPS,
-                _lib.current_stream(x.device)))
-        return res
 
     @staticmethod
     def from_config(cfg_path: str, use_cosine_schedule: bool = False, device: str = 'cpu'):

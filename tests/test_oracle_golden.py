@@ -109,6 +109,19 @@ def test_inpaint_step_bit_exact(sg, golden_dir, ptype):
         assert np.array_equal(y, g[f"{ptype}_{t}_nocfg"]), (ptype, t)
 
 
+def test_inpaint_step_ddpm_bit_exact(sg, golden_dir):
+    """The inpainting loop body with sampler='ddpm' (models/diffusion.py:314-316): oracle vs the reference's statements, with the
+    reference's own global-generator noise draw recorded in the fixture."""
+    g = np.load(os.path.join(golden_dir, "inpaint_golden.npz"))
+    ts = g["ddpm_ts"]
+    assert np.array_equal(ts, SO.strength_slice(SO.ddpm_timesteps(1000, 50), 50, 0.8))
+    mask = g["mask"][0, 0]
+    for t in (int(ts[0]), int(ts[17]), int(ts[-1])):
+        y = SO.inpaint_step(g["latent"], t, g["pred2"], g["encoded"], mask, 7.5, sg["alphas"], sg["alphas_hat"], 1000, 50,
+                            ddpm_noise=g[f"ddpm_{t}_noise"])
+        assert np.array_equal(y, g[f"ddpm_{t}_cfg"]), t
+
+
 def test_param_inventory():
     n15 = sum(int(np.prod(s)) for _, s in UO.param_spec(**UO.SD15))
     n21 = sum(int(np.prod(s)) for _, s in UO.param_spec(**UO.SD21))

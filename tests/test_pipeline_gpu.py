@@ -179,6 +179,19 @@ def test_inpaint_and_img2img_loops(net15, dev):
     e = rel_l2(got.cpu().numpy(), xo.numpy())
     print(f"inpaint loop fp32 vs oracle: rel-L2 {e:.3e}")
     assert e < 1e-4
+    # the same loop with sampler='ddpm' (diffusion.py:314-316): graph replays == step-by-step API under the same global seed
+    pm = DDPMSampler()
+    pm._set_inference_steps(10)
+    pm.set_strength(0.4)
+    with torch.no_grad():
+        torch.manual_seed(77)
+        got = inpaint(net15, pm, lat.to(dev), ctx.to(dev), enc.to(dev), mask.to(dev), do_cfg=True, cfg_scale=7.5)
+        torch.manual_seed(77)
+        x = lat.to(dev)
+        for ts in pm.timesteps.to(dev):
+            ts = ts.unsqueeze(0)
+            x = pm.inpaint_step(x, ts, net15(x.repeat(2, 1, 1, 1), ts, ctx.to(dev)), enc.to(dev), mask.to(dev), cfg_scale=7.5)
+        assert torch.isfinite(got).all() and torch.equal(got, x)
     # img2img
     d2 = DDIMSampler()
     d2._set_inference_steps(10)

@@ -128,6 +128,31 @@ def test_inpaint_step_golden_bit_exact(sg, golden_dir, dev, ptype):
         assert np.array_equal(got.cpu().numpy(), g[f"{ptype}_{int(t)}_nocfg"])
 
 
+@pytest.mark.gpu
+def test_inpaint_step_ddpm_golden_bit_exact(sg, golden_dir, dev):
+    """sdk_ddpm_inpaint_step (inpaint CFG form + re-noise + mask select + ancestral DDPM update) == the reference's statements with
+    sampler='ddpm' (models/diffusion.py:314-316,387-398), bit for bit, including t == 0 where the noise is multiplied by zero."""
+    g = np.load(os.path.join(golden_dir, "inpaint_golden.npz"))
+    s = DDPMSampler()
+    _use_golden_tables(s, sg)
+    s._set_inference_steps(50)
+    s.set_strength(0.8)
+    assert np.array_equal(s.timesteps.numpy(), g["ddpm_ts"])
+    lat, pred2, enc = (torch.from_numpy(g[k]).to(dev) for k in ("latent", "pred2", "encoded"))
+    mask = torch.from_numpy(g["mask"]).to(dev)
+    for t in (s.timesteps[0], s.timesteps[17], s.timesteps[-1]):
+        nz = torch.from_numpy(g[f"ddpm_{int(t)}_noise"]).to(dev)
+        got = s.inpaint_step(lat, t.unsqueeze(0).to(dev), pred2, enc, mask, cfg_scale=7.5, noise=nz)
+        assert np.array_equal(got.cpu().numpy(), g[f"ddpm_{int(t)}_cfg"]), int(t)
+    # without `noise` the draw comes from torch's global generator on the tensor's device, like ddpm.py:80
+    torch.manual_seed(3)
+    a = s.inpaint_step(lat, int(s.timesteps[0]), pred2, enc, mask, cfg_scale=7.5)
+    torch.manual_seed(3)
+    nz = torch.randn(lat.shape, dtype=lat.dtype, device=dev)
+    b = s.inpaint_step(lat, int(s.timesteps[0]), pred2, enc, mask, cfg_scale=7.5, noise=nz)
+    assert torch.equal(a, b)
+
+
 def test_out_of_range_timestep_poisons(dev):
     s = DDIMSampler()
     s._set_inference_steps(10)
