@@ -1061,7 +1061,8 @@ class StepProgram:
                 reg.append((t, 1, ""))
         reg += [(t, 1, "") for t in getattr(self, "kv", {}).values()]
         reg += [(t, 1, "") for t in self.keep if isinstance(t, torch.Tensor) and all(t is not c for c in self.consts)]
-        for name, attr in (("x", "x_in"), ("timestep", "t_in"), ("context", "cond_in"), ("out", "out")):
+        for name, attr in (("x", "x_in"), ("timestep", "t_in"), ("context", "cond_in"), ("out", "out"),
+                           ("z", "z_in"), ("ids", "ids_in")):         # VAE decode: "z" -> "out"; text encoder: "ids" -> "out"
             t = getattr(self, attr, None)
             if t is not None:
                 reg.append((t, 2, name))

@@ -149,6 +149,40 @@ def test_c_host_runs_forward_and_loop(net, dev, tmp_path):
     assert torch.equal(got, fwd_ref)
 
 
+def test_vae_and_text_encoder_engines(dev, tmp_path):
+    """The stages either side of the loop export the same way: VAE.decode ("z" -> "out") and the text encoder ("ids" -> "out")
+    reloaded from their engine files reproduce the Python host's results bit for bit."""
+    from oracle import vae_oracle as VO
+    from stable_diffusion_pytorch_b200 import VAE, TextEncoder
+    lib = _lib.lib()
+    vae = VAE()
+    vae.load_state_dict(VO.make_state_dict(3), strict=True)
+    vae = vae.to(dev).eval()
+    g = torch.Generator().manual_seed(9)
+    z = torch.randn((1, 4, 8, 8), generator=g)
+    enc = TextEncoder(n_vocab=1000, embed_dim=768, max_len=77, num_layers=2).to(dev).eval()
+    ids = torch.randint(0, 1000, (2, 77), generator=g)
+    with torch.no_grad():
+        img = vae.decode(z.to(dev)).cpu()
+        emb = enc(ids.to(dev)).cpu()
+    cases = [(next(iter(vae._plans.values())).prog, "z", z, img), (next(iter(enc._plans.values())).prog, "ids", ids, emb)]
+    for prog, name, inp, ref in cases:
+        path = str(tmp_path / f"{name}.engine")
+        prog.export_engine(path)
+        h = C.c_void_p()
+        _lib.check(lib.sdk_plan_load(path.encode(), C.byref(h)))
+        os.remove(path)
+        s = stream()
+        src = inp.contiguous()
+        _lib.check(lib.sdk_plan_upload(h, name.encode(), src.data_ptr(), src.numel() * src.element_size(), s))
+        _lib.check(lib.sdk_plan_launch(h, 0, s))
+        out = torch.empty_like(ref)
+        _lib.check(lib.sdk_plan_download(h, b"out", out.data_ptr(), out.numel() * 4, s))
+        torch.cuda.synchronize()
+        _lib.check(lib.sdk_plan_destroy(h))
+        assert torch.isfinite(out).all() and torch.equal(out, ref), name
+
+
 def test_plan_with_parameter_struct_launch(dev, tmp_path):
     """The exact-fp32 GEMM takes a host parameter struct: the plan copies it, relocates its pointers and replays it after a reload."""
     lib = _lib.lib()
