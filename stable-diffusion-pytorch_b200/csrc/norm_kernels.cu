@@ -179,9 +179,18 @@ gn_apply_kernel(GNApplyArgs a, int pix_per_chunk, int px_lanes, int q_iters) {
         // 8 threads per group: channel sums -> (mean, rstd), fixed order (double accumulation, as gn_stats_kernel's fold)
         const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
         double sum = 0.0, sq = 0.0;
-        for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
-            const double2 v = c < a.C0 ? __ldg(a.cs0 + (size_t)b * a.C0 + c) : __ldg(a.cs1 + (size_t)b * a.C1 + (c - a.C0));
-            sum += v.x; sq += v.y;
+        // all table loads of a thread in flight at once (up to 8 per batch = 64 channels per group and batch): the fold is the head
+        // of every launch's dependency chain, and one L2 round trip per loop iteration was most of a small launch's run time
+        for (int c0 = g * cpg + sub; c0 < (g + 1) * cpg; c0 += 64) {
+            double2 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = c0 + 8 * i;
+                v[i] = c >= (g + 1) * cpg ? make_double2(0.0, 0.0)
+                     : (c < a.C0 ? __ldg(a.cs0 + (size_t)b * a.C0 + c) : __ldg(a.cs1 + (size_t)b * a.C1 + (c - a.C0)));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sum += v[i].x; sq += v[i].y; }
         }
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
