@@ -3,6 +3,76 @@ import numpy as np
 import torch
 
 
+def run_kernels():
+    """The tensor-core kernels of the product path, launched directly through the C ABI on small tensors and checked against
+    fp32 torch: runs FIRST in smoke() so that a launch-capped profiler window names tcgen05 kernels (conv_gemm_tc*, linear_ln_kernel,
+    attention_tc_kernel) before the thousands of torch kernels of weight packing."""
+    import ctypes as C
+    import math
+    from stable_diffusion_pytorch_b200 import _lib
+    from stable_diffusion_pytorch_b200._lib import BF16_T, F32_T, LinearLnDesc, TcGemmDesc
+    lib, dev = _lib.lib(), torch.device("cuda:0")
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator().manual_seed(0)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    kmajor = lambda w: w.view(w.shape[0], w.shape[1] // 64, 64).permute(1, 0, 2).contiguous()
+    # 3x3 conv 320 -> 320 on a 2 x 16 x 16 NHWC map (implicit GEMM: TMA im2col, tcgen05.mma, TMEM accumulator, TMA-store epilogue)
+    a = torch.randn((2, 16, 16, 320), generator=g).to(dev).bfloat16()
+    w = (torch.randn((320, 9 * 320), generator=g) / math.sqrt(9 * 320)).to(dev).bfloat16()
+    bias = torch.randn((320,), generator=g).to(dev)
+    out = torch.empty((2, 16, 16, 320), device=dev)
+    wk = kmajor(w)
+    d = TcGemmDesc()
+    d.a[0], d.w[0], d.C[0], d.ksize[0], d.nseg, d.w_kmajor = a.data_ptr(), wk.data_ptr(), 320, 3, 1, 1
+    d.B, d.H, d.W, d.N, d.bias, d.out, d.out_dtype = 2, 16, 16, 320, bias.data_ptr(), out.data_ptr(), F32_T
+    h = C.c_void_p()
+    _lib.check(lib.sdk_tc_gemm_create(C.byref(d), C.byref(h)))
+    ws = torch.zeros(max(int(lib.sdk_tc_gemm_workspace_bytes(h)), 256), dtype=torch.uint8, device=dev)
+    _lib.check(lib.sdk_tc_gemm_set_workspace(h, ws.data_ptr()))
+    _lib.check(lib.sdk_tc_gemm_launch(h, stream))
+    torch.cuda.synchronize()
+    lib.sdk_tc_gemm_destroy(h)
+    want = torch.nn.functional.conv2d(a.float().permute(0, 3, 1, 2), w.float().view(320, 3, 3, 320).permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
+    e = rel(out, want)
+    assert e < 2e-5, f"tcgen05 implicit-GEMM conv rel-L2 {e:.2e}"
+    print(f"smoke: tcgen05 implicit-GEMM 3x3 conv (sdk_tc_gemm) rel-L2 {e:.1e} vs fp32 torch")
+    # projection + bias + residual + LayerNorm in one cluster launch
+    M, K = 512, 320
+    x = torch.randn((M, K), generator=g).to(dev).bfloat16()
+    w2 = (torch.randn((320, K), generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    res = torch.randn((M, 320), generator=g).to(dev)
+    gam, bet = torch.ones(320, device=dev), torch.zeros(320, device=dev)
+    o32 = torch.empty((M, 320), device=dev)
+    ln = torch.empty((M, 320), device=dev, dtype=torch.bfloat16)
+    w2k = kmajor(w2)
+    ld = LinearLnDesc()
+    ld.a, ld.w, ld.bias, ld.residual, ld.out, ld.ln_out = x.data_ptr(), w2k.data_ptr(), bias.data_ptr(), res.data_ptr(), o32.data_ptr(), ln.data_ptr()
+    ld.gamma, ld.beta, ld.eps, ld.M, ld.K, ld.N = gam.data_ptr(), bet.data_ptr(), 1e-5, M, K, 320
+    _lib.check(lib.sdk_linear_ln_create(C.byref(ld), C.byref(h)))
+    _lib.check(lib.sdk_linear_ln_launch(h, stream))
+    torch.cuda.synchronize()
+    lib.sdk_linear_ln_destroy(h)
+    want = x.float() @ w2.float().t() + bias + res
+    e1, e2 = rel(o32, want), rel(ln.float(), torch.nn.functional.layer_norm(o32, (320,)))
+    assert e1 < 2e-6 and e2 < 3e-3, f"linear_ln rel-L2 {e1:.2e} / {e2:.2e}"
+    print(f"smoke: projection + LayerNorm cluster kernel (sdk_linear_ln) rel-L2 {e1:.1e} (fp32 rows), {e2:.1e} (bf16 LayerNorm rows)")
+    # flash attention on the tensor core: 2 x 8 heads x 256 tokens, head_dim 40, q | k | v fused rows
+    B, H, S, D = 2, 8, 256, 40
+    qkv = torch.randn((B, S, 3 * H * D), generator=g).to(dev).bfloat16()
+    ao = torch.empty((B, S, H * D), device=dev, dtype=torch.bfloat16)
+    base, es, Cc = qkv.data_ptr(), 2, H * D
+    _lib.check(lib.sdk_attention_tc_create(base, 3 * Cc, S * 3 * Cc, base + Cc * es, 3 * Cc, S * 3 * Cc, base + 2 * Cc * es, 3 * Cc, S * 3 * Cc,
+                                           ao.data_ptr(), Cc, S * Cc, B, H, S, S, D, float(D ** -0.5), C.byref(h)))
+    _lib.check(lib.sdk_attention_tc_launch(h, stream))
+    torch.cuda.synchronize()
+    lib.sdk_attention_tc_destroy(h)
+    q, k, v = (t.float().view(B, S, H, D).transpose(1, 2) for t in qkv.split(Cc, dim=-1))
+    want = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, Cc)
+    e = rel(ao.float(), want)
+    assert e < 1e-2, f"tcgen05 attention rel-L2 {e:.2e}"
+    print(f"smoke: tcgen05 flash attention (sdk_attention_tc) rel-L2 {e:.1e} vs fp32 torch")
+
+
 def run():
     from oracle import unet_oracle as UO                       # checker only
     from stable_diffusion_pytorch_b200 import DDIMSampler, UNet

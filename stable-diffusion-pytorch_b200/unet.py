@@ -148,8 +148,8 @@ class PackedWeights:
             t[f"{p}.qkv.w"] = dev(torch.cat([sd[f"{b}.attn1.{n}_proj.weight"] for n in "qkv"], 0), wdt)
             t[f"{p}.o1.w"], t[f"{p}.o1.b"] = dev(sd[f"{b}.attn1.out_proj.weight"], wdt), dev(sd[f"{b}.attn1.out_proj.bias"])
             t[f"{p}.q2.w"] = dev(sd[f"{b}.attn2.q_proj.weight"], wdt)
-            if precision != "fp32":
-                # LayerNorm folded into the projection that consumes it (unet.py:137-149):
+            if precision != "fp32" and getattr(net, "ln_fold", False):
+                # (opt-in, SDB200_LN_FOLD=1) LayerNorm folded into the projection that consumes it (unet.py:137-149):
                 #   LN(x) W^T + c = rstd * (x W'^T - mean * colsum) + (c + W beta),  W' = W * gamma (bf16), colsum[n] = sum_k W'[n][k]
                 # colsum is taken from the ROUNDED W' so that the mean term cancels exactly against what the tensor core multiplies.
                 def fold(key, w, bias, ln):
@@ -171,7 +171,7 @@ class PackedWeights:
             w0, b0 = sd[f"{b}.ffn.0.proj.weight"], sd[f"{b}.ffn.0.proj.bias"]      # [8C, C]: rows [value(4C) ; gate(4C)]
             t[f"{p}.ff0.w"] = dev(torch.stack([w0[:4 * c], w0[4 * c:]], 1).reshape(8 * c, c), wdt)
             t[f"{p}.ff0.b"] = dev(torch.stack([b0[:4 * c], b0[4 * c:]], 1).reshape(8 * c))
-            if precision != "fp32":
+            if precision != "fp32" and getattr(net, "ln_fold", False):
                 fold("ff0", torch.stack([w0[:4 * c], w0[4 * c:]], 1).reshape(8 * c, c), torch.stack([b0[:4 * c], b0[4 * c:]], 1).reshape(8 * c), 3)
             t[f"{p}.ff1.w"], t[f"{p}.ff1.b"] = dev(sd[f"{b}.ffn.1.weight"], wdt), dev(sd[f"{b}.ffn.1.bias"])
         for st in a.down + a.up:
@@ -1193,7 +1193,7 @@ class UNet(nn.Module):
 
     # ---- forward ----------------------------------------------------------------------
     def _weights(self, device) -> PackedWeights:
-        key = (str(device), self.precision)
+        key = (str(device), self.precision, bool(getattr(self, "ln_fold", False)))      # the opt-in LayerNorm fold packs extra weights
         pw = self._packed.get(key)
         if pw is None:
             pw = PackedWeights(self, device, self.precision)
