@@ -38,6 +38,15 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def need_disk(path, gib):
+    """Engine files of the full SD-1.5 architecture carry 1.8 GB of packed weights (the reference only works with its fixed
+    block_out_channels, so there is no small model to export): skip rather than fail on a box without scratch space."""
+    import shutil
+    free = shutil.disk_usage(str(path)).free
+    if free < gib * (1 << 30):
+        pytest.skip(f"needs {gib} GiB of scratch space under {path}, {free / (1 << 30):.1f} GiB free")
+
+
 def test_plan_replay_equals_python_launches(net, dev):
     """One sdk_plan_launch per program == the same launches issued one by one from Python."""
     pw = net._weights(dev)
@@ -62,6 +71,7 @@ def test_plan_replay_equals_python_launches(net, dev):
 
 def test_engine_roundtrip_in_process(net, dev, tmp_path):
     """save -> load into a second plan with its own device memory -> same bits."""
+    need_disk(tmp_path, 4)
     lib = _lib.lib()
     g = torch.Generator().manual_seed(6)
     x = torch.randn((2, 4, 16, 16), generator=g).to(dev)
@@ -109,6 +119,7 @@ def test_engine_roundtrip_in_process(net, dev, tmp_path):
 
 def test_c_host_runs_forward_and_loop(net, dev, tmp_path):
     """tools/c_host/denoise.c (plain C, sdb200.h only) == UNet.forward and DenoiseLoop.run of the Python host, bit for bit."""
+    need_disk(tmp_path, 4)
     exe = str(tmp_path / "denoise")
     libdir = os.path.join(ROOT, "stable-diffusion-pytorch_b200")
     cc = subprocess.run(["gcc", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "c_host", "denoise.c"), "-o", exe,
