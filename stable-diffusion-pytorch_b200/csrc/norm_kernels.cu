@@ -179,6 +179,7 @@ gn_apply_kernel(GNApplyArgs a, int pix_per_chunk, int px_lanes, int q_iters) {
         // 8 threads per group: channel sums -> (mean, rstd), fixed order (double accumulation, as gn_stats_kernel's fold)
         const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
         double sum = 0.0, sq = 0.0;
+        const double inv_n = 1.0 / ((double)cpg * (double)a.HW);      // the one double division: independent of the loads below
         // all table loads of a thread in flight at once (up to 8 per batch = 64 channels per group and batch): the fold is the head
         // of every launch's dependency chain, and one L2 round trip per loop iteration was most of a small launch's run time
         for (int c0 = g * cpg + sub; c0 < (g + 1) * cpg; c0 += 64) {
@@ -195,11 +196,12 @@ gn_apply_kernel(GNApplyArgs a, int pix_per_chunk, int px_lanes, int q_iters) {
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
         if (sub == 0) {
-            const double n = (double)cpg * (double)a.HW;
-            const double mean = sum / n;
-            double var = sq / n - mean * mean;      // biased variance (nn.GroupNorm)
+            // sums stay in double (cancellation in E[x^2] - mean^2); the reciprocal square root is taken in fp32 like
+            // nn.GroupNorm's own rstd -- a double division + square root here was ~0.5 us at the head of every launch
+            const double mean = sum * inv_n;
+            double var = sq * inv_n - mean * mean;      // biased variance (nn.GroupNorm)
             if (var < 0.0) var = 0.0;
-            s_gstat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)a.eps)));
+            s_gstat[g] = make_float2((float)mean, 1.0f / sqrtf((float)var + a.eps));
         }
         __syncthreads();
     }
