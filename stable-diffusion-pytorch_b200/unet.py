@@ -62,7 +62,7 @@ def read_knobs(m):
     # bf16: projection (+ bias + residual) and the LayerNorm of its output rows in ONE cluster launch (linear_ln.cu) for layers
     # whose grid fits one wave of the chip -- the latency-bound case (every transformer layer at UNet batch 2)
     m.ln_fuse = os.environ.get("SDB200_LN_FUSE", "1") != "0"
-    m.ln_fuse_max_ctas = int(os.environ.get("SDB200_LN_FUSE_MAX_CTAS", "148"))
+    m.ln_fuse_max_ctas = int(os.environ.get("SDB200_LN_FUSE_MAX_CTAS", "0"))      # 0 = the SM count of the device (one wave)
     m.fold_gathers = os.environ.get("SDB200_FOLD_GATHERS", "1") != "0"   # bf16: stride-2 / upsample gathers inside the GEMM's TMA coordinates
     # ... where the layer has enough rows to fill the chip WITHOUT split-K (the folded form runs on the persistent kernel only; measured
     # on B200 at UNet batch 2: the 8x8 / 16x16 layers are weight-streaming bound and 1.6-3x faster as im2col / upsample + split-K GEMM)
@@ -619,7 +619,15 @@ class StepProgram:
         if self.act == F32_T or not getattr(self.net, "ln_fuse", False):
             return None
         bn = 160 if (N % 160 == 0 and N // 160 <= 8) else (128 if (N % 128 == 0 and N // 128 <= 8) else 0)
-        if not bn or K % 64 != 0 or ((rows + 127) // 128) * (N // bn) > self.net.ln_fuse_max_ctas:
+        max_ctas = self.net.ln_fuse_max_ctas
+        if max_ctas <= 0:
+            if not hasattr(self, "_sm_count"):
+                info = (C.c_int * 4)()
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.sdk_device_info(info, 4))
+                self._sm_count = int(info[0])
+            max_ctas = self._sm_count
+        if not bn or K % 64 != 0 or ((rows + 127) // 128) * (N // bn) > max_ctas:
             return None
         out = self.pool.get(rows, N, F32_T)
         ln = self.pool.get(rows, N, BF16_T)

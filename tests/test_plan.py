@@ -90,3 +90,35 @@ def test_slots_encode_floats_and_negative_ints():
     assert s[3] == 0x3727C5AC
     with pytest.raises(RuntimeError):
         StepProgram._slots("sdk_layernorm", (1, 2, 3))
+
+
+def test_save_load_roundtrip_and_truncation(tmp_path):
+    """The engine file format without a GPU: a plan whose launches carry no device memory saves and loads on the CPU; every
+    truncation of the file is rejected cleanly (no crash, no partial plan)."""
+    lib = _lib.lib()
+    h = C.c_void_p()
+    assert lib.sdk_plan_create(C.byref(h)) == 0
+    assert lib.sdk_plan_add_launch(h, 2, b"sdk_zero", _args(0, 0), 2) == 0
+    assert lib.sdk_plan_add_launch(h, 2, b"sdk_x0_from_eps", _args(0, 0, 0x3F7F0000, 0x3D8C7E28, 0, 0), 6) == 0
+    assert lib.sdk_plan_add_launch(h, 5, b"sdk_gather_row", _args(0, 20160, 50, 0, 0xFFFFFFFFFFFFFFFF, 0), 6) == 0
+    path = tmp_path / "tiny.engine"
+    assert lib.sdk_plan_save(h, str(path).encode()) == 0, lib.sdk_last_error()
+    assert lib.sdk_plan_destroy(h) == 0
+    data = path.read_bytes()
+    assert data[:8] == b"SDB200PL" and len(data) < 4096
+    h2 = C.c_void_p()
+    assert lib.sdk_plan_load(str(path).encode(), C.byref(h2)) == 0, lib.sdk_last_error()
+    assert [lib.sdk_plan_num_launches(h2, i) for i in (0, 2, 5)] == [0, 2, 1]
+    assert lib.sdk_plan_destroy(h2) == 0
+    for cut in list(range(0, len(data), 7)) + [len(data) - 1]:
+        f = tmp_path / f"cut{cut}.engine"
+        f.write_bytes(data[:cut])
+        h3 = C.c_void_p()
+        assert lib.sdk_plan_load(str(f).encode(), C.byref(h3)) == -1, cut
+    # a corrupted launch name is rejected too
+    bad = bytearray(data)
+    i = bad.find(b"sdk_zero")
+    bad[i:i + 8] = b"sdk_zerx"
+    f = tmp_path / "bad.engine"
+    f.write_bytes(bytes(bad))
+    assert lib.sdk_plan_load(str(f).encode(), C.byref(C.c_void_p())) == -1
