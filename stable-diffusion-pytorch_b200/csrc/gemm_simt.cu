@@ -11,6 +11,7 @@
 // shared memory (conflict-free float4 fragment reads), register double-buffering of the next tile.
 #define SDK_PDL_CAT 1
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/sdb200.h"
 
 namespace {
@@ -278,6 +279,84 @@ conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /* [3][3
         atomicAdd(reinterpret_cast<double*>(cstat + (size_t)b * N) + i, acc);
     }
 }
+
+// Register-blocked form for W % 4 == 0: a thread owns FOUR consecutive pixels of a row for its channel quad, so every weight float4
+// read from shared memory feeds 16 FMAs instead of 4 -- the per-pixel kernel above is bound by shared-memory bandwidth (one LDS.128
+// per 4 FFMA = a quarter of the FP32 rate).  Same (tap, input channel) summation order per output value, so the results are
+// bit-identical to the per-pixel kernel (out-of-image taps add 0 * w instead of being skipped).
+constexpr int CI4_PIX = 32;                        // pixels per CTA (8 groups of 4)
+__global__ void __launch_bounds__(CI_THREADS)
+conv_in4_kernel(const float* __restrict__ x, const float* __restrict__ w /* [3][3][4][N] */, const float* __restrict__ bias, float* __restrict__ out,
+                double2* __restrict__ cstat, int B, int H, int W, int N) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ float sm[];
+    float* w_s = sm;                                   // [36][N]
+    float* s_red = sm + 36 * N;                        // [px_lanes][N][2] column partials
+    const int quads = N >> 2, px_lanes = CI_THREADS / quads;
+    const int pl = threadIdx.x / quads, qd = threadIdx.x - pl * quads;
+    for (int i = threadIdx.x; i < 9 * N; i += CI_THREADS)
+        reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+    __syncthreads();
+    const int HW = H * W;
+    const int p0 = blockIdx.x * CI4_PIX;
+    const int b = blockIdx.y;
+    float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pl < px_lanes) {
+        const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias) + qd) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int pg = pl; pg < CI4_PIX / 4; pg += px_lanes) {
+            const int pix = p0 + 4 * pg;
+            if (pix >= HW) break;
+            const int oy = pix / W, ox = pix - oy * W;             // W % 4 == 0: the four pixels share the row
+            float4 acc[4] = {bv, bv, bv, bv};
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int iy = oy + dy - 1;
+                float4 v[6];                                       // input pixels ox-1 .. ox+4 of row iy (zeros outside the image)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int ix = ox + k - 1;
+                    v[k] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                               ? __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + iy) * W + ix) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int t = dy * 3 + kx;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 ww = *reinterpret_cast<const float4*>(w_s + (t * 4 + c) * N + (qd << 2));
+#pragma unroll
+                        for (int pp = 0; pp < 4; ++pp) {
+                            const float4 vv = v[pp + kx];
+                            const float xv = c == 0 ? vv.x : c == 1 ? vv.y : c == 2 ? vv.z : vv.w;
+                            acc[pp].x = fmaf(xv, ww.x, acc[pp].x); acc[pp].y = fmaf(xv, ww.y, acc[pp].y);
+                            acc[pp].z = fmaf(xv, ww.z, acc[pp].z); acc[pp].w = fmaf(xv, ww.w, acc[pp].w);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+                *reinterpret_cast<float4*>(out + ((size_t)b * HW + pix + pp) * N + (qd << 2)) = acc[pp];
+                sa[0] += acc[pp].x; sa[1] += acc[pp].y; sa[2] += acc[pp].z; sa[3] += acc[pp].w;
+                qa[0] = fmaf(acc[pp].x, acc[pp].x, qa[0]); qa[1] = fmaf(acc[pp].y, acc[pp].y, qa[1]);
+                qa[2] = fmaf(acc[pp].z, acc[pp].z, qa[2]); qa[3] = fmaf(acc[pp].w, acc[pp].w, qa[3]);
+            }
+        }
+    }
+    if (!cstat) return;
+    if (pl < px_lanes) {
+        float* d = s_red + ((size_t)pl * N + (qd << 2)) * 2;
+        *reinterpret_cast<float4*>(d) = make_float4(sa[0], qa[0], sa[1], qa[1]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(sa[2], qa[2], sa[3], qa[3]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * N; i += CI_THREADS) {         // i = channel * 2 + which
+        double acc = 0.0;
+        for (int l = 0; l < px_lanes; ++l) acc += (double)s_red[(size_t)l * N * 2 + i];
+        atomicAdd(reinterpret_cast<double*>(cstat + (size_t)b * N) + i, acc);
+    }
+}
 }  // namespace
 
 extern "C" int sdk_conv_in(const float* x, const float* w_t, const float* bias, float* out, double* chan_stats,
@@ -288,6 +367,15 @@ extern "C" int sdk_conv_in(const float* x, const float* w_t, const float* bias, 
     const int px_lanes = CI_THREADS / (N / 4);
     const size_t smem = sizeof(float) * ((size_t)36 * N + (size_t)px_lanes * N * 2);
     SDK_CHECK_ARG(smem <= 200 * 1024, "sdk_conv_in: N=%d needs too much shared memory", N);
+    static const int blocked = getenv("SDB200_CONV_IN4") ? atoi(getenv("SDB200_CONV_IN4")) : 1;
+    if (blocked && W % 4 == 0 && (long long)H * W < (1ll << 30)) {
+        SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_in4_kernel), (int)smem));
+        const int chunks = (H * W + CI4_PIX - 1) / CI4_PIX;
+        SDK_CUDA(sdk_launch(conv_in4_kernel, dim3(chunks, B), dim3(CI_THREADS), smem, (cudaStream_t)stream, x, w_t, bias, out,
+                            reinterpret_cast<double2*>(chan_stats), B, H, W, N));
+        SDK_LAUNCH_CHECK();
+        return SDK_OK;
+    }
     SDK_CUDA(sdk_ensure_dyn_smem(reinterpret_cast<const void*>(conv_in_kernel), (int)smem));
     const int chunks = (H * W + CI_PIX - 1) / CI_PIX;
     SDK_CUDA(sdk_launch(conv_in_kernel, dim3(chunks, B), dim3(CI_THREADS), smem, (cudaStream_t)stream, x, w_t, bias, out,

@@ -405,9 +405,10 @@ def test_groupnorm_from_channel_sums(dev, shape):
         assert rel_l2(raw.float(), x) < (1e-7 if odt == F32_T else 4e-3)
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 64, 320), (3, 24, 40, 320), (1, 8, 8, 64)])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 320), (3, 24, 40, 320), (1, 8, 8, 64), (2, 96, 96, 320), (1, 6, 10, 64), (2, 5, 7, 320)])
 def test_conv_in(dev, shape):
-    """conv_in kernel (3x3, Cin=4, fp32) and its statistics table vs F.conv2d."""
+    """conv_in kernels (3x3, Cin=4, fp32: four-pixel register-blocked for W % 4 == 0, per-pixel otherwise) and their statistics
+    table vs F.conv2d."""
     B, H, W, N = shape
     lib = _lib.lib()
     x = gen((B, H, W, 4), 71, dev)
