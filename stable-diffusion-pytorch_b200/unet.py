@@ -1238,6 +1238,23 @@ class UNet(nn.Module):
             self._plans[key] = plan
         return plan(x, timestep, cond).to(x.dtype)
 
+    def export_engine(self, path: str, batch: int, height: int, width: int, *, context_len: int = 77,
+                      context_batch: Optional[int] = None, per_sample_timesteps: bool = False, device=None):
+        """Plan ``forward`` for a (batch, 4, height, width) latent and write its engine file (sdk_plan_save): a host without Python
+        loads it with sdk_plan_load, fills the regions "x", "timestep", "context" and runs program 1 (context) then 0 (forward);
+        the result is region "out".  See INTEGRATION.md 2b; the whole sampling loop exports through DenoiseLoop.export_engine."""
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("export_engine needs the UNet on a CUDA device (the plan is built for that device's kernels)")
+        bc = batch if context_batch is None else context_batch
+        nt = batch if per_sample_timesteps else 1
+        key = (str(dev), self.precision, batch, height, width, nt, bc, context_len)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = _Runner(StepProgram(self, self._weights(dev), batch, height, width, nt, bc, context_len), self.use_cuda_graph)
+            self._plans[key] = plan
+        plan.prog.export_engine(path)
+
     @staticmethod
     def from_pretrained(pretrained_dir: str, device: str = 'cpu', sd_version: str = "1.5"):
         """reference: unet.py:445-461 — diffusers-layout directory (config.json + safetensors)."""

@@ -81,7 +81,7 @@ def test_engine_roundtrip_in_process(net, dev, tmp_path):
         ref = net(x, t, ctx)
     prog = next(p.prog for k, p in net._plans.items() if k[2:5] == (2, 16, 16))
     path = str(tmp_path / "unet.engine")
-    prog.export_engine(path)
+    net.export_engine(path, 2, 16, 16)                              # the plan forward() just used
     assert os.path.getsize(path) > 1_000_000_000                   # the packed bf16 weights travel with the launch lists
     h = C.c_void_p()
     _lib.check(lib.sdk_plan_load(path.encode(), C.byref(h)))
