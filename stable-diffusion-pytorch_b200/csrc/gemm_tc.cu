@@ -1060,9 +1060,9 @@ conv_gemm_tc_persistent_kernel(const __grid_constant__ TcParams p) {
 
             ptx::mbar_wait(&acc_full[ab], (uint32_t)(lt >> 1) & 1u);
             ptx::tc_fence_after();
-#pragma unroll 1
             int last_c = grp;
             if (grp >= NCH && et == 0) ptx::mbar_arrive(&acc_empty[ab]);   // BN = 32: the second group has nothing to drain
+#pragma unroll 1
             for (int c = grp; c < NCH; c += 2, ++gc) {
                 last_c = c;
                 uint32_t u[32];
