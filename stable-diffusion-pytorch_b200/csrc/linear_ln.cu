@@ -24,6 +24,7 @@
 #include "../../include/sdb200.h"
 #include <new>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -353,7 +354,11 @@ extern "C" int sdk_linear_ln_create(const SdkLinearLnDesc* d, void** handle) {
     if (d->M >= (1ll << 31) - BM) return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_linear_ln_create: too many rows");
     // the n-tiles of a row block are one thread-block cluster (<= 8 CTAs, the portable limit): N = nc * BN
     int bn = 0;
-    if (d->N % 160 == 0 && d->N / 160 <= MAX_CLUSTER) bn = 160;
+    // both tile widths valid (N = 640): the 128-column tile gives clusters of 5 instead of 4 -- more CTAs per row block, 32 KB instead
+    // of 36 KB per k-block and SM, four epilogue chunks instead of five (measured: 0.540 -> 0.533 ms per step for the 48 launches)
+    static const int prefer128 = getenv("SDB200_LLN_PREFER128") ? atoi(getenv("SDB200_LLN_PREFER128")) : 1;
+    if (prefer128 && d->N % 128 == 0 && d->N / 128 <= MAX_CLUSTER) bn = 128;
+    else if (d->N % 160 == 0 && d->N / 160 <= MAX_CLUSTER) bn = 160;
     else if (d->N % 128 == 0 && d->N / 128 <= MAX_CLUSTER) bn = 128;
     if (!bn) return sdk_fail(SDK_ERR_UNSUPPORTED, "sdk_linear_ln_create: N=%d is not 160*k or 128*k with k <= 8", d->N);
     LinearLn* g = new (std::nothrow) LinearLn();

@@ -619,6 +619,8 @@ class StepProgram:
         if self.act == F32_T or not getattr(self.net, "ln_fuse", False):
             return None
         bn = 160 if (N % 160 == 0 and N // 160 <= 8) else (128 if (N % 128 == 0 and N // 128 <= 8) else 0)
+        if os.environ.get("SDB200_LLN_PREFER128", "1") != "0" and N % 128 == 0 and N // 128 <= 8:
+            bn = 128                                           # the library's own preference (N = 640: clusters of 5)
         max_ctas = self.net.ln_fuse_max_ctas
         if max_ctas <= 0:
             if not hasattr(self, "_sm_count"):
